@@ -1,0 +1,137 @@
+/*
+ * regrid_b200.h -- C ABI of the B200-native regridding engine.
+ *
+ * The reference (xarray-regrid v0.4.2) is pure Python with no FFI; the narrowest
+ * seams a native engine plugs into are the three array-math calls its methods
+ * delegate to (reference paths relative to src/xarray_regrid/):
+ *
+ *   apply_weights(da, weights, skipna, nan_threshold)   methods/conservative.py:181-208
+ *   data.interp(coords=..., method=...)                  methods/interp.py:43-46
+ *   flox.xarray.xarray_reduce(...)                       methods/flox_reduce.py:89-96, 174-182
+ *
+ * Every entry point below replaces one of those calls (cited per function).
+ * Conventions:
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - "device" pointers are CUDA device memory of the current device, owned by the
+ *     caller; the library never allocates or frees caller-visible memory;
+ *   - calls are asynchronous and ordered on `stream` (a cudaStream_t passed as void*;
+ *     NULL = the legacy default stream); they are re-entrant and keep no global state;
+ *   - return value: 0 = RG_OK, negative = argument error (RG_ERR_*), positive = the
+ *     cudaError_t of the failing runtime call.  No exceptions cross the boundary.
+ *   - data layout: [batch, rows(lat), cols(lon)], unit stride along cols; batch and row
+ *     strides are given in ELEMENTS.  All non-spatial dims are flattened into `batch`.
+ */
+#ifndef REGRID_B200_H
+#define REGRID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_OK 0
+#define RG_ERR_NULL (-1)      /* required pointer is NULL                         */
+#define RG_ERR_SHAPE (-2)     /* non-positive / inconsistent extent or stride      */
+#define RG_ERR_SMEM (-3)      /* problem does not fit the kernel's shared memory   */
+#define RG_ERR_UNSUPPORTED (-4)
+#define RG_ERR_ALIGN (-5)
+
+#define RG_ABI_VERSION 1
+
+/* ABI version of the loaded library (== RG_ABI_VERSION of the header it was built from). */
+int rg_abi_version(void);
+/* Static, human-readable text for a return code (RG_ERR_* or a cudaError_t). */
+const char* rg_error_string(int code);
+/* Number of SMs of the current device (grid sizing is done inside the library). */
+int rg_device_sm_count(void);
+
+/*
+ * Banded per-axis weight table ("ELL", tap-major).
+ *
+ * Replaces the dense [n_src, n_tgt] weight matrix of utils.py:145-169 /
+ * methods/conservative.py:219-244 (get_weights, apply_spherical_correction,
+ * format_weights): only structurally non-zero entries are kept, like the
+ * reference's sparse.COO weights (conservative.py:297-300).
+ *
+ *   idx[t * n_out + o]   source index of tap t of output o (0 <= idx < n_src), or
+ *                        n_src + {0,1} for the synthetic south / north pole row of
+ *                        utils.py:313-336 (rows axis only, needs `pole` below)
+ *   w  [t * n_out + o]   its weight, float type = the data's (float for f32, double for f64)
+ *   cnt[o]               number of taps of output o (taps t >= cnt[o] are ignored)
+ *   cover[o]             1 if the target centre lies inside the source centres' range
+ *                        (conservative.py:123-125), 0 -> the output is NaN
+ */
+typedef struct rg_band {
+  const int32_t* idx;   /* device, [k_max * n_out] */
+  const void* w;        /* device, [k_max * n_out] */
+  const int32_t* cnt;   /* device, [n_out]         */
+  const uint8_t* cover; /* device, [n_out]         */
+  int32_t n_out;
+  int32_t k_max;
+  int32_t n_src;
+} rg_band_t;
+
+/*
+ * Fused conservative regrid of a [batch, H, W] stack onto [batch, Ho, Wo]:
+ *
+ *   valid[b,k,l] = sum_ij notnull(x[b,i,j]) * Wlat[i,k] * Wlon[j,l]
+ *   out  [b,k,l] = sum_ij fillna0(x[b,i,j]) * Wlat[i,k] * Wlon[j,l]
+ *   skipna:  y = out / valid where valid >= valid_thr else NaN
+ *   !skipna: y = out (NaN propagates through non-zero taps only)
+ *   y = NaN where !(cover_lat[k] && cover_lon[l])
+ *
+ * Replaces apply_weights (methods/conservative.py:181-208) plus the coverage mask of
+ * conservative.py:161-164 in ONE pass over x (no fillna/notnull/divide/where passes).
+ * `valid_thr` is get_valid_threshold(nan_threshold) (conservative.py:211-216), computed
+ * by the caller.  `pole` is NULL or a device [batch, 2] array holding the longitude-mean
+ * of the first / last source row (rg_row_nanmean_*), referenced by idx == H / H+1.
+ * H = rows.n_src, W = cols.n_src, Ho = rows.n_out, Wo = cols.n_out.  y is dense
+ * [batch, Ho, Wo] with batch stride y_batch_stride.
+ */
+int rg_conservative_f64(const double* x, double* y, int64_t batch,
+                        int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
+                        const rg_band_t* rows, const rg_band_t* cols,
+                        int32_t skipna, double valid_thr, const double* pole, void* stream);
+int rg_conservative_f32(const float* x, float* y, int64_t batch,
+                        int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
+                        const rg_band_t* rows, const rg_band_t* cols,
+                        int32_t skipna, float valid_thr, const float* pole, void* stream);
+
+/*
+ * Longitude-mean (NaN-skipping) of the first and last row of every slab:
+ * pole[b,0] = nanmean(x[b,0,:]), pole[b,1] = nanmean(x[b,H-1,:]); all-NaN -> NaN.
+ * Replaces the `.mean(lon_coord)` of format_lat (utils.py:320-333).
+ */
+int rg_row_nanmean_f64(const double* x, double* pole, int64_t batch, int32_t H, int32_t W,
+                       int64_t x_batch_stride, int64_t x_row_stride, void* stream);
+int rg_row_nanmean_f32(const float* x, float* pole, int64_t batch, int32_t H, int32_t W,
+                       int64_t x_batch_stride, int64_t x_row_stride, void* stream);
+
+/*
+ * Host-buffer variant of rg_conservative_*: x_host / y_host are HOST pointers
+ * (pinned memory gives full PCIe bandwidth; pageable memory works but is staged by the
+ * driver).  The stack is cut into chunks of `chunk_batch` slabs that are copied in,
+ * regridded and copied out on three internal streams so that H2D, the kernel and D2H
+ * overlap (stands in for the reference's dask chunk scheduling,
+ * methods/conservative.py:263-302).  `workspace` is caller-owned DEVICE memory of at
+ * least rg_conservative_host_workspace(...) bytes.  The call returns after the last
+ * D2H copy has completed (it synchronises its internal streams, not the device).
+ * Host layout is dense: x_host [batch, H, W], y_host [batch, Ho, Wo].
+ */
+size_t rg_conservative_host_workspace(int64_t chunk_batch, int32_t H, int32_t W, int32_t Ho,
+                                      int32_t Wo, int32_t elem_size);
+int rg_conservative_host_f64(const double* x_host, double* y_host, int64_t batch,
+                             int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
+                             int32_t skipna, double valid_thr, int32_t pole_rows,
+                             void* workspace, size_t workspace_bytes);
+int rg_conservative_host_f32(const float* x_host, float* y_host, int64_t batch,
+                             int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
+                             int32_t skipna, float valid_thr, int32_t pole_rows,
+                             void* workspace, size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGRID_B200_H */

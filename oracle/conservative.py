@@ -31,13 +31,15 @@ def cell_edges(coords):
     Interior edges are midpoints; the two outer edges mirror the first / last
     midpoint about the first / last centre.  A single point spans all of space.
     """
-    coords = np.asarray(coords, dtype=np.float64)
+    coords = np.asarray(coords)
     if coords.size <= 1:
         return np.array([-np.inf, np.inf])
+    # arithmetic in the coordinate's own dtype (float32 coords -> float32 midpoints), then
+    # float64: pandas' IntervalIndex.from_breaks stores float64 edges
     mid = (coords[:-1] + coords[1:]) / 2
     first = 2 * coords[0] - mid[0]
     last = 2 * coords[-1] - mid[-1]
-    return np.concatenate([[first], mid, [last]])
+    return np.concatenate([[first], mid, [last]]).astype(np.float64)
 
 
 def overlap_matrix(src_edges, tgt_edges):

@@ -1,0 +1,92 @@
+"""Host-side tables (product code) against the oracle / the reference's golden weights."""
+
+import numpy as np
+import pytest
+
+from oracle import conservative as oc
+from oracle import formatting as of
+from xarray_regrid_b200 import tables
+
+AXIS_CASES = [
+    "c1_lat", "c1_lon", "era5_to_2p2_lat", "cellcentred_lat", "upsample",
+    "irregular", "single_target", "tgt_outside",
+]
+
+
+@pytest.mark.parametrize("name", AXIS_CASES)
+@pytest.mark.parametrize("spherical", [False, True])
+def test_band_equals_reference_dense_weights(golden_helpers, name, spherical):
+    g = golden_helpers
+    key = f"axis/{name}/weights_spherical" if spherical else f"axis/{name}/weights"
+    if key not in g:
+        pytest.skip("no spherical variant")
+    src, tgt = g[f"axis/{name}/src"], g[f"axis/{name}/tgt"]
+    band = tables.conservative_band(tables.plain_axis(src), tgt, spherical=spherical)
+    dense = band.dense()
+    ref = g[key]
+    # entry for entry; column sums are taken over the band only, so allow the last bit
+    np.testing.assert_allclose(dense, ref, rtol=4e-16, atol=0)
+    assert ((dense != 0) == (ref != 0)).all(), "band must hold exactly the non-zero taps"
+    assert band.k_max == max(int((ref != 0).sum(axis=0).max()), 1)
+    np.testing.assert_array_equal(band.cover.astype(bool), oc.covered_mask(src, tgt))
+
+
+def test_c1_band_shape():
+    lat = np.arange(-90, 90.25, 0.25)
+    lon = np.arange(0, 360, 0.25)
+    tlat = np.arange(-90.0, 91.0, 1.0)
+    tlon = np.arange(0.0, 360.0, 1.0)
+    rows = tables.conservative_band(tables.format_lat_axis(lat), tlat, spherical=True)
+    cols = tables.conservative_band(tables.format_lon_axis(lon, tlon), tlon)
+    assert (rows.n_out, rows.k_max, cols.n_out, cols.k_max) == (181, 5, 360, 5)
+    assert rows.cnt[0] == 2 and rows.cnt[-1] == 2  # zero-area pole rows dropped
+    assert cols.idx.min() == 0 and cols.idx.max() == 1439  # wrap folded into the indices
+    np.testing.assert_array_equal(cols.idx[: cols.cnt[0], 0], [1438, 1439, 0, 1, 2])
+    assert not rows.meta["pole_rows"]
+
+
+@pytest.mark.parametrize(
+    "src,tgt",
+    [
+        (np.arange(1.0, 360, 2), np.arange(0.0, 361, 1)),       # test_no_edges
+        (np.arange(0.0, 361, 2), np.arange(-180.0, 181, 1)),    # 360 -> 180
+        (np.arange(-180.0, 181, 2), np.arange(0.0, 361, 1)),    # 180 -> 360
+        (np.arange(-360.0, 1, 2), np.arange(0.0, 361, 1)),      # 0 -> 360
+        (np.arange(-180.0, 181, 2), np.arange(270.0, 301, 1)),  # global -> local
+        (np.arange(0.0, 360, 0.25), np.arange(0.0, 360, 1.0)),  # C1
+        (np.arange(359.75, -0.1, -0.25), np.arange(0.0, 360, 1.0)),  # descending source
+    ],
+)
+def test_lon_formatting_matches_oracle(src, tgt):
+    ax = tables.format_lon_axis(src, tgt)
+    data = np.arange(src.size, dtype=np.float64)[None, :]
+    out, _, lon = of.format_for_regrid(data, None, src, None, tgt)
+    np.testing.assert_array_equal(ax.values, lon)
+    np.testing.assert_array_equal(ax.source, out[0].astype(int))
+
+
+def test_lat_formatting_matches_oracle():
+    lat = np.arange(-89.5, 90, 1.0)
+    ax = tables.format_lat_axis(lat)
+    assert ax.values[0] == -90 and ax.values[-1] == 90 and ax.has_pole_rows
+    np.testing.assert_array_equal(ax.source, np.concatenate([[180], np.arange(180), [181]]))
+    ax = tables.format_lat_axis(np.arange(-90.0, 91, 1.0))
+    assert ax.is_identity
+    ax = tables.format_lat_axis(np.arange(-88.0, 89, 1.0))
+    assert ax.is_identity
+    ax = tables.format_lat_axis(np.arange(90.0, -91, -1.0))  # descending: sorted via indices
+    np.testing.assert_array_equal(ax.source, np.arange(180, -1, -1))
+
+
+def test_reversed_target_is_folded_into_band():
+    src = np.arange(0.0, 10.0, 1.0)
+    tgt = np.arange(0.5, 9.0, 2.0)
+    fwd = tables.conservative_band(tables.plain_axis(src), tgt)
+    rev = tables.conservative_band(tables.plain_axis(src), tgt[::-1])
+    np.testing.assert_array_equal(rev.dense(), fwd.dense()[:, ::-1])
+
+
+def test_valid_threshold(golden_helpers):
+    g = golden_helpers
+    got = np.array([tables.valid_threshold(t) for t in g["threshold/in"]])
+    np.testing.assert_array_equal(got, g["threshold/out"])

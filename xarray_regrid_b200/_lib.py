@@ -1,0 +1,72 @@
+"""ctypes binding of the engine's C ABI (``include/regrid_b200.h``).
+
+There is no CPU fallback: if ``csrc/libregrid_b200.so`` is missing this module raises at
+import time with the command that builds it.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_CSRC = Path(__file__).resolve().parent / "csrc"
+LIB_PATH = _CSRC / "libregrid_b200.so"
+
+RG_ABI_VERSION = 1
+
+
+class RegridB200Error(RuntimeError):
+    """A C-ABI call returned a non-zero code (argument error or CUDA error)."""
+
+
+class rg_band_t(C.Structure):  # noqa: N801 - mirrors the C name
+    _fields_ = [
+        ("idx", C.c_void_p),
+        ("w", C.c_void_p),
+        ("cnt", C.c_void_p),
+        ("cover", C.c_void_p),
+        ("n_out", C.c_int32),
+        ("k_max", C.c_int32),
+        ("n_src", C.c_int32),
+    ]
+
+
+def _load():
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA engine is not built and there is no CPU fallback. "
+            f"Build it with `make -C {_CSRC}` (or `python -c 'import __graft_entry__ as g; g.build()'`)."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    p, i32, i64, f32, f64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
+    band = C.POINTER(rg_band_t)
+    sig = {
+        "rg_abi_version": (C.c_int, []),
+        "rg_error_string": (C.c_char_p, [C.c_int]),
+        "rg_device_sm_count": (C.c_int, []),
+        "rg_conservative_f64": (C.c_int, [p, p, i64, i64, i64, i64, band, band, i32, f64, p, p]),
+        "rg_conservative_f32": (C.c_int, [p, p, i64, i64, i64, i64, band, band, i32, f32, p, p]),
+        "rg_row_nanmean_f64": (C.c_int, [p, p, i64, i32, i32, i64, i64, p]),
+        "rg_row_nanmean_f32": (C.c_int, [p, p, i64, i32, i32, i64, i64, p]),
+        "rg_conservative_host_workspace": (sz, [i64, i32, i32, i32, i32, i32]),
+        "rg_conservative_host_f64": (C.c_int, [p, p, i64, i64, band, band, i32, f64, i32, p, sz]),
+        "rg_conservative_host_f32": (C.c_int, [p, p, i64, i64, band, band, i32, f32, i32, p, sz]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rg_abi_version() != RG_ABI_VERSION:
+        raise ImportError(
+            f"{LIB_PATH} has ABI version {lib.rg_abi_version()}, expected {RG_ABI_VERSION}: rebuild it"
+        )
+    return lib, sig
+
+
+lib, SIGNATURES = _load()
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        text = lib.rg_error_string(code).decode()
+        raise RegridB200Error(f"{what} failed with code {code}: {text}")

@@ -1,0 +1,384 @@
+// Fused conservative regridding for sm_100a.
+//
+// One pass over the source stack: for a (slab b, target row k) task a CTA
+//   phase 1  streams the <= k_max source rows of the latitude band with 16-byte
+//            read-only loads, contracts them per source column into shared memory
+//            (value mass t[j] and, for skipna, valid mass v[j]);
+//   phase 2  contracts t / v along longitude out of shared memory with the column
+//            band (whose indices already contain the reference's +-360 shift and
+//            wrap padding), divides, applies the nan_threshold and coverage masks and
+//            writes the Wo outputs coalesced.
+// No intermediate touches HBM.  Replaces apply_weights + masks of the reference
+// (src/xarray_regrid/methods/conservative.py:181-208, 161-164).
+//
+// Roofline: HBM.  Algorithmic bytes per task = (band rows * W + Wo) * sizeof(T); flops are
+// ~0.4 per byte, far below the fp64 ridge, so tensor cores are not used.
+
+#include "common.cuh"
+
+namespace rg {
+
+constexpr int kConsThreads = 256;
+constexpr int kRowChunk = 8;  // independent row loads in flight per thread
+
+template <typename T, bool SKIPNA, int VEC>
+__global__ void __launch_bounds__(kConsThreads)
+conservative_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch,
+                    long long xbs, long long xrs, long long ybs, Band<T> rows, Band<T> cols,
+                    T thr, const T* __restrict__ pole, int w_pad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* s_t = reinterpret_cast<T*>(smem_raw);
+  T* s_v = s_t + w_pad;  // valid only when SKIPNA
+  long long* s_off = reinterpret_cast<long long*>(s_t + (SKIPNA ? 2 : 1) * w_pad);
+  T* s_w = reinterpret_cast<T*>(s_off + rows.k_max);
+
+  const int H = rows.n_src, W = cols.n_src, Ho = rows.n_out, Wo = cols.n_out;
+  const long long tasks = batch * Ho;
+  const T nan = quiet_nan<T>();
+
+  for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int k = static_cast<int>(task % Ho);
+    const long long b = task / Ho;
+    T* yrow = y + b * ybs + static_cast<long long>(k) * Wo;
+
+    if (!rows.cover[k]) {  // CTA-uniform: target latitude outside the source range
+      for (int l = threadIdx.x; l < Wo; l += kConsThreads) st_stream(yrow + l, nan);
+      continue;
+    }
+
+    const int cnt = rows.cnt[k];
+    if (threadIdx.x < cnt) {
+      const int r = rows.idx[threadIdx.x * Ho + k];
+      // r >= H addresses the synthetic pole rows (value pole[b, r - H] for every column)
+      s_off[threadIdx.x] = r < H ? static_cast<long long>(r) * xrs : -static_cast<long long>(r - H) - 1;
+      s_w[threadIdx.x] = rows.w[threadIdx.x * Ho + k];
+    }
+    __syncthreads();
+
+    // ---- phase 1: latitude contraction, one source column group per thread ----------
+    const T* xb = x + b * xbs;
+    for (int j = threadIdx.x * VEC; j < W; j += kConsThreads * VEC) {
+      T acc[VEC], vac[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { acc[e] = T(0); vac[e] = T(0); }
+      const bool full = (j + VEC <= W);
+      for (int r0 = 0; r0 < cnt; r0 += kRowChunk) {
+        Pack<T, VEC> val[kRowChunk];
+#pragma unroll
+        for (int i = 0; i < kRowChunk; ++i) {
+          if (r0 + i < cnt) {
+            const long long off = s_off[r0 + i];
+            if (off >= 0) {
+              if (full) {
+                val[i] = ld_stream<T, VEC>(xb + off + j);
+              } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                  val[i].v[e] = (j + e < W) ? ld_stream<T, 1>(xb + off + j + e).v[0] : T(0);
+              }
+            } else {
+              const T pv = pole[b * 2 + (-off - 1)];
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) val[i].v[e] = pv;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kRowChunk; ++i) {
+          if (r0 + i < cnt) {
+            const T w = s_w[r0 + i];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              const T xv = val[i].v[e];
+              if (SKIPNA) {
+                const bool ok = (xv == xv);
+                acc[e] = fma(w, ok ? xv : T(0), acc[e]);
+                vac[e] += ok ? w : T(0);
+              } else {
+                acc[e] = fma(w, xv, acc[e]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (j + e < W) {
+          s_t[j + e] = acc[e];
+          if (SKIPNA) s_v[j + e] = vac[e];
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: longitude contraction out of shared memory, normalise, mask, store -
+    for (int l = threadIdx.x; l < Wo; l += kConsThreads) {
+      T out = nan;
+      if (cols.cover[l]) {
+        const int c = cols.cnt[l];
+        T so = T(0), sv = T(0);
+        for (int t = 0; t < c; ++t) {
+          const int j = cols.idx[t * Wo + l];
+          const T w = cols.w[t * Wo + l];
+          so = fma(w, s_t[j], so);
+          if (SKIPNA) sv = fma(w, s_v[j], sv);
+        }
+        if (SKIPNA) {
+          out = (sv >= thr) ? so / sv : nan;
+        } else {
+          out = so;
+        }
+      }
+      st_stream(yrow + l, out);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ pole rows (format_lat)
+template <typename T>
+__global__ void __launch_bounds__(256)
+row_nanmean_kernel(const T* __restrict__ x, T* __restrict__ pole, long long batch, int H, int W,
+                   long long xbs, long long xrs) {
+  __shared__ double s_sum[8];
+  __shared__ long long s_cnt[8];
+  const long long b = blockIdx.x >> 1;
+  const int which = blockIdx.x & 1;
+  const T* row = x + b * xbs + (which ? static_cast<long long>(H - 1) * xrs : 0);
+  double sum = 0.0;
+  long long n = 0;
+  for (int j = threadIdx.x; j < W; j += 256) {
+    const T v = row[j];
+    if (v == v) { sum += static_cast<double>(v); ++n; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = n; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0;
+    long long tn = 0;
+    for (int i = 0; i < 8; ++i) { ts += s_sum[i]; tn += s_cnt[i]; }
+    pole[b * 2 + which] = tn > 0 ? static_cast<T>(ts / static_cast<double>(tn)) : quiet_nan<T>();
+  }
+}
+
+template <typename T>
+int row_nanmean_launch(const T* x, T* pole, int64_t batch, int32_t H, int32_t W, int64_t xbs,
+                       int64_t xrs, cudaStream_t stream) {
+  if (!x || !pole) return RG_ERR_NULL;
+  if (batch < 0 || H <= 0 || W <= 0 || xrs < W) return RG_ERR_SHAPE;
+  if (batch == 0) return RG_OK;
+  if (batch * 2 > 0x7fffffffLL) return RG_ERR_SHAPE;
+  row_nanmean_kernel<T><<<static_cast<unsigned>(batch * 2), 256, 0, stream>>>(x, pole, batch, H, W,
+                                                                              xbs, xrs);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------- launcher
+template <typename T>
+int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
+                        const rg_band_t* rows_c, const rg_band_t* cols_c, int32_t skipna, T thr,
+                        const T* pole, cudaStream_t stream) {
+  if (!x || !y) return RG_ERR_NULL;
+  Band<T> rows, cols;
+  int rc = make_band<T>(rows_c, &rows);
+  if (rc != RG_OK) return rc;
+  rc = make_band<T>(cols_c, &cols);
+  if (rc != RG_OK) return rc;
+  if (batch < 0) return RG_ERR_SHAPE;
+  if (batch == 0) return RG_OK;
+  const int W = cols.n_src;
+  if (xrs < W || xbs < 0 || ybs < static_cast<int64_t>(rows.n_out) * cols.n_out) return RG_ERR_SHAPE;
+  if (rows.k_max > kConsThreads) return RG_ERR_UNSUPPORTED;
+
+  constexpr int kMaxVec = 16 / sizeof(T);
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (xbs % kMaxVec == 0) &&
+                       (xrs % kMaxVec == 0);
+  const int w_pad = (W + kMaxVec - 1) / kMaxVec * kMaxVec;
+  const size_t smem = static_cast<size_t>(skipna ? 2 : 1) * w_pad * sizeof(T) +
+                      static_cast<size_t>(rows.k_max) * (sizeof(long long) + sizeof(T));
+
+  DeviceInfo dev;
+  rc = device_info(&dev);
+  if (rc != RG_OK) return rc;
+  if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_SMEM;
+
+  using Kernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>,
+                          Band<T>, T, const T*, int);
+  Kernel kern;
+  if (aligned) {
+    kern = skipna ? conservative_kernel<T, true, kMaxVec> : conservative_kernel<T, false, kMaxVec>;
+  } else {
+    kern = skipna ? conservative_kernel<T, true, 1> : conservative_kernel<T, false, 1>;
+  }
+  if (smem > 48 * 1024) {
+    RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  }
+  int per_sm = 0;
+  RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kConsThreads, smem));
+  if (per_sm < 1) return RG_ERR_SMEM;
+  const long long tasks = static_cast<long long>(batch) * rows.n_out;
+  long long grid = static_cast<long long>(dev.sm_count) * per_sm;
+  if (grid > tasks) grid = tasks;
+  kern<<<static_cast<unsigned>(grid), kConsThreads, smem, stream>>>(x, y, batch, xbs, xrs, ybs, rows,
+                                                                   cols, thr, pole, w_pad);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------ host-buffer streaming pipeline
+constexpr int kSlots = 3;
+
+inline size_t round256(size_t n) { return (n + 255) / 256 * 256; }
+
+struct PipelineResources {
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  cudaEvent_t in_done[kSlots] = {}, k_done[kSlots] = {}, out_done[kSlots] = {};
+  int create() {
+    RG_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    RG_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+    RG_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kSlots; ++i) {
+      RG_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
+      RG_CUDA(cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
+      RG_CUDA(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
+    }
+    return RG_OK;
+  }
+  ~PipelineResources() {
+    for (int i = 0; i < kSlots; ++i) {
+      if (in_done[i]) cudaEventDestroy(in_done[i]);
+      if (k_done[i]) cudaEventDestroy(k_done[i]);
+      if (out_done[i]) cudaEventDestroy(out_done[i]);
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_k) cudaStreamDestroy(s_k);
+    if (s_out) cudaStreamDestroy(s_out);
+  }
+};
+
+template <typename T>
+int conservative_host(const T* xh, T* yh, int64_t batch, int64_t chunk, const rg_band_t* rows,
+                      const rg_band_t* cols, int32_t skipna, T thr, int32_t pole_rows, void* ws,
+                      size_t ws_bytes) {
+  if (!xh || !yh || !ws || !rows || !cols) return RG_ERR_NULL;
+  if (batch < 0 || chunk <= 0) return RG_ERR_SHAPE;
+  if (batch == 0) return RG_OK;
+  const int64_t H = rows->n_src, W = cols->n_src, Ho = rows->n_out, Wo = cols->n_out;
+  const size_t in_b = round256(static_cast<size_t>(chunk) * H * W * sizeof(T));
+  const size_t out_b = round256(static_cast<size_t>(chunk) * Ho * Wo * sizeof(T));
+  const size_t pole_b = round256(static_cast<size_t>(chunk) * 2 * sizeof(T));
+  if (ws_bytes < kSlots * (in_b + out_b + pole_b)) return RG_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(ws) % 256 != 0) return RG_ERR_ALIGN;
+
+  PipelineResources res;
+  int rc = res.create();
+  if (rc != RG_OK) return rc;
+
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  T* d_in[kSlots];
+  T* d_out[kSlots];
+  T* d_pole[kSlots];
+  for (int s = 0; s < kSlots; ++s) {
+    d_in[s] = reinterpret_cast<T*>(base + s * (in_b + out_b + pole_b));
+    d_out[s] = reinterpret_cast<T*>(base + s * (in_b + out_b + pole_b) + in_b);
+    d_pole[s] = reinterpret_cast<T*>(base + s * (in_b + out_b + pole_b) + in_b + out_b);
+  }
+
+  const int64_t n_chunks = (batch + chunk - 1) / chunk;
+  for (int64_t i = 0; i < n_chunks; ++i) {
+    const int s = static_cast<int>(i % kSlots);
+    const int64_t b0 = i * chunk;
+    const int64_t nb = (batch - b0 < chunk) ? batch - b0 : chunk;
+    // the input slot is free once the kernel that consumed its previous content is done
+    if (i >= kSlots) RG_CUDA(cudaStreamWaitEvent(res.s_in, res.k_done[s], 0));
+    RG_CUDA(cudaMemcpyAsync(d_in[s], xh + b0 * H * W, static_cast<size_t>(nb) * H * W * sizeof(T),
+                            cudaMemcpyHostToDevice, res.s_in));
+    RG_CUDA(cudaEventRecord(res.in_done[s], res.s_in));
+
+    RG_CUDA(cudaStreamWaitEvent(res.s_k, res.in_done[s], 0));
+    // the output slot is free once its previous content has reached the host
+    if (i >= kSlots) RG_CUDA(cudaStreamWaitEvent(res.s_k, res.out_done[s], 0));
+    if (pole_rows) {
+      rc = row_nanmean_launch<T>(d_in[s], d_pole[s], nb, static_cast<int32_t>(H),
+                                 static_cast<int32_t>(W), H * W, W, res.s_k);
+      if (rc != RG_OK) return rc;
+    }
+    rc = conservative_launch<T>(d_in[s], d_out[s], nb, H * W, W, Ho * Wo, rows, cols, skipna, thr,
+                                pole_rows ? d_pole[s] : nullptr, res.s_k);
+    if (rc != RG_OK) return rc;
+    RG_CUDA(cudaEventRecord(res.k_done[s], res.s_k));
+
+    RG_CUDA(cudaStreamWaitEvent(res.s_out, res.k_done[s], 0));
+    RG_CUDA(cudaMemcpyAsync(yh + b0 * Ho * Wo, d_out[s],
+                            static_cast<size_t>(nb) * Ho * Wo * sizeof(T), cudaMemcpyDeviceToHost,
+                            res.s_out));
+    RG_CUDA(cudaEventRecord(res.out_done[s], res.s_out));
+  }
+  RG_CUDA(cudaStreamSynchronize(res.s_out));
+  RG_CUDA(cudaStreamSynchronize(res.s_k));
+  RG_CUDA(cudaStreamSynchronize(res.s_in));
+  return RG_OK;
+}
+
+}  // namespace rg
+
+// ------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int rg_conservative_f64(const double* x, double* y, int64_t batch, int64_t xbs, int64_t xrs,
+                        int64_t ybs, const rg_band_t* rows, const rg_band_t* cols, int32_t skipna,
+                        double valid_thr, const double* pole, void* stream) {
+  return rg::conservative_launch<double>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna, valid_thr,
+                                         pole, static_cast<cudaStream_t>(stream));
+}
+
+int rg_conservative_f32(const float* x, float* y, int64_t batch, int64_t xbs, int64_t xrs,
+                        int64_t ybs, const rg_band_t* rows, const rg_band_t* cols, int32_t skipna,
+                        float valid_thr, const float* pole, void* stream) {
+  return rg::conservative_launch<float>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna, valid_thr,
+                                        pole, static_cast<cudaStream_t>(stream));
+}
+
+int rg_row_nanmean_f64(const double* x, double* pole, int64_t batch, int32_t H, int32_t W,
+                       int64_t xbs, int64_t xrs, void* stream) {
+  return rg::row_nanmean_launch<double>(x, pole, batch, H, W, xbs, xrs,
+                                        static_cast<cudaStream_t>(stream));
+}
+
+int rg_row_nanmean_f32(const float* x, float* pole, int64_t batch, int32_t H, int32_t W,
+                       int64_t xbs, int64_t xrs, void* stream) {
+  return rg::row_nanmean_launch<float>(x, pole, batch, H, W, xbs, xrs,
+                                       static_cast<cudaStream_t>(stream));
+}
+
+size_t rg_conservative_host_workspace(int64_t chunk_batch, int32_t H, int32_t W, int32_t Ho,
+                                      int32_t Wo, int32_t elem_size) {
+  if (chunk_batch <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || elem_size <= 0) return 0;
+  const size_t in_b = rg::round256(static_cast<size_t>(chunk_batch) * H * W * elem_size);
+  const size_t out_b = rg::round256(static_cast<size_t>(chunk_batch) * Ho * Wo * elem_size);
+  const size_t pole_b = rg::round256(static_cast<size_t>(chunk_batch) * 2 * elem_size);
+  return rg::kSlots * (in_b + out_b + pole_b);
+}
+
+int rg_conservative_host_f64(const double* x_host, double* y_host, int64_t batch,
+                             int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
+                             int32_t skipna, double valid_thr, int32_t pole_rows, void* workspace,
+                             size_t workspace_bytes) {
+  return rg::conservative_host<double>(x_host, y_host, batch, chunk_batch, rows, cols, skipna,
+                                       valid_thr, pole_rows, workspace, workspace_bytes);
+}
+
+int rg_conservative_host_f32(const float* x_host, float* y_host, int64_t batch,
+                             int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
+                             int32_t skipna, float valid_thr, int32_t pole_rows, void* workspace,
+                             size_t workspace_bytes) {
+  return rg::conservative_host<float>(x_host, y_host, batch, chunk_batch, rows, cols, skipna,
+                                      valid_thr, pole_rows, workspace, workspace_bytes);
+}
+
+}  // extern "C"

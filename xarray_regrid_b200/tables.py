@@ -1,0 +1,275 @@
+"""Host-side table construction for the B200 regrid kernels (numpy only, no CUDA).
+
+Everything the reference computes per AXIS -- a few thousand numbers -- is computed here
+with the reference's own floating-point expressions, then shipped to the GPU as small
+index / weight tables.  Everything the reference does per CELL happens in the kernels.
+
+What is folded into tables instead of touching the data (reference paths relative to
+``src/xarray_regrid/``):
+
+* ``ensure_monotonic``  (utils.py:411-421)   -> a permutation composed into the indices
+* ``format_lon``        (utils.py:341-390)   -> the +-360 shift, the re-sort and the wrap
+  padding become a gather map ``formatted column -> original column``
+* ``format_lat``        (utils.py:289-338)   -> pole rows become the virtual row indices
+  ``n_src`` (south) and ``n_src + 1`` (north), whose value is the longitude-mean of the
+  edge row (computed on device by ``rg_row_nanmean_*``)
+* ``get_weights`` / ``apply_spherical_correction`` (methods/conservative.py:219-260) ->
+  banded (ELL) weights holding only the structurally non-zero taps, built in
+  O(n_src + n_tgt) with ``searchsorted`` instead of the dense [n_src, n_tgt] overlap matrix
+* ``reindex_like(target)`` (conservative.py:99) -> the output permutation ``restore``
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+LAT_NAMES = ("lat", "latitude")
+LON_NAMES = ("lon", "longitude")
+
+
+# ------------------------------------------------------------------------------ sorting
+def monotonic_order(coord):
+    """Index array that sorts ``coord`` ascending (stable) and drops duplicate labels,
+    or None when the coordinate is already strictly usable as is (utils.py:411-421)."""
+    coord = np.asarray(coord)
+    order = None
+    if coord.size > 1 and np.any(coord[1:] < coord[:-1]):
+        order = np.argsort(coord, kind="stable")
+        coord = coord[order]
+    if coord.size > 1 and np.any(coord[1:] == coord[:-1]):
+        _, first = np.unique(coord, return_index=True)
+        first = np.sort(first)
+        order = first if order is None else order[first]
+    return order
+
+
+@dataclass
+class FormattedAxis:
+    """A source axis after the reference's pre-formatting.
+
+    ``values[i]`` is the coordinate label of formatted position ``i`` and ``source[i]`` the
+    position in the ORIGINAL array it reads from (``n_src`` / ``n_src + 1`` = south / north
+    pole row).
+    """
+
+    values: np.ndarray
+    source: np.ndarray
+    n_src: int
+
+    @property
+    def has_pole_rows(self) -> bool:
+        return bool(self.source.size and self.source.max() >= self.n_src)
+
+    @property
+    def is_identity(self) -> bool:
+        return self.source.size == self.n_src and bool(
+            np.array_equal(self.source, np.arange(self.n_src))
+        )
+
+
+def plain_axis(coord) -> FormattedAxis:
+    """Sort / de-duplicate only (coordinates that are not named lat / lon)."""
+    coord = np.asarray(coord)
+    order = monotonic_order(coord)
+    src = np.arange(coord.size, dtype=np.int64) if order is None else order.astype(np.int64)
+    return FormattedAxis(coord[src], src, coord.size)
+
+
+def format_lat_axis(lat) -> FormattedAxis:
+    """utils.py:313-336: add -90 / +90 rows when the edge row is within one (maximum)
+    spacing of the pole but not on it."""
+    ax = plain_axis(lat)
+    vals, src = ax.values, ax.source
+    if vals.size > 1:
+        dy = np.diff(vals).max()
+        south = dy - 90 >= vals[0] > -90
+        north = 90 - dy <= vals[-1] < 90
+        if south:
+            vals = np.concatenate([[-90], vals])
+            src = np.concatenate([[ax.n_src], src])
+        if north:
+            vals = np.concatenate([vals, [90]])
+            src = np.concatenate([src, [ax.n_src + 1]])
+    return FormattedAxis(vals, src, ax.n_src)
+
+
+def format_lon_axis(lon, tgt_lon) -> FormattedAxis:
+    """utils.py:358-388 on indices: shift by +-360 about the wrap point, sort, wrap-pad."""
+    lon = np.asarray(lon)
+    tgt = np.asarray(tgt_lon)
+    t_order = monotonic_order(tgt)
+    if t_order is not None:
+        tgt = tgt[t_order]
+    ax = plain_axis(lon)
+    vals, src = ax.values, ax.source
+
+    wrap_point = (tgt[-1] + tgt[0] + 360) / 2
+    vals = np.where(vals < wrap_point - 360, vals + 360, vals)
+    vals = np.where(vals > wrap_point, vals - 360, vals)
+    order = monotonic_order(vals)
+    if order is not None:
+        vals, src = vals[order], src[order]
+
+    if vals.size > 1 and tgt.size > 1:
+        dx_s = np.diff(vals).max()
+        dx_t = np.diff(tgt).max()
+        if vals.max() - vals.min() >= 360 - dx_s:
+            left = (vals[0] - tgt[0] + dx_t / 2) / dx_s
+            right = (tgt[-1] - vals[-1] + dx_t / 2) / dx_s
+            left = int(np.ceil(max(left, 0)))
+            right = int(np.ceil(max(right, 0)))
+            n = vals.size
+            gather = np.concatenate([np.arange(n - left, n), np.arange(n), np.arange(0, right)])
+            new_vals = vals[gather].astype(np.result_type(vals.dtype, np.float64), copy=True)
+            if left:
+                new_vals[:left] = vals[n - left:] - 360
+            if right:
+                new_vals[new_vals.size - right:] = vals[:right] + 360
+            vals, src = new_vals, src[gather]
+            order = monotonic_order(vals)
+            if order is not None:
+                vals, src = vals[order], src[order]
+    return FormattedAxis(vals, src, ax.n_src)
+
+
+# ------------------------------------------------------------------- conservative bands
+def cell_edges(coords):
+    """utils.py:128-140: midpoints inside, mirrored outer edges, one point spans all space."""
+    coords = np.asarray(coords)
+    if coords.size <= 1:
+        return np.array([-np.inf, np.inf])
+    mid = (coords[:-1] + coords[1:]) / 2  # in the coordinate's own dtype, like the reference
+    first = 2 * coords[0] - mid[0]
+    last = 2 * coords[-1] - mid[-1]
+    return np.concatenate([[first], mid, [last]]).astype(np.float64)
+
+
+def lat_weight(lat_deg, res_deg):
+    """methods/conservative.py:247-260."""
+    dlat = np.radians(res_deg)
+    lat = np.radians(lat_deg)
+    h = np.sin(lat + dlat / 2) - np.sin(lat - dlat / 2)
+    return h * dlat / (np.pi * 4)
+
+
+def valid_threshold(nan_threshold: float) -> float:
+    """methods/conservative.py:211-216."""
+    return float(1 - np.clip(nan_threshold, 1e-6, 1.0 - 1e-6))
+
+
+@dataclass
+class Band:
+    """Tap-major ELL band: ``idx[t, o]`` / ``w[t, o]`` for tap ``t < cnt[o]`` of output ``o``."""
+
+    idx: np.ndarray  # int32 [k_max, n_out]
+    w: np.ndarray  # float64 [k_max, n_out]
+    cnt: np.ndarray  # int32 [n_out]
+    cover: np.ndarray  # uint8 [n_out]
+    n_src: int
+    restore: np.ndarray | None = None  # output permutation back to the target's own order
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_out(self) -> int:
+        return int(self.cnt.size)
+
+    @property
+    def k_max(self) -> int:
+        return int(self.idx.shape[0])
+
+    def dense(self, n_src_total=None) -> np.ndarray:
+        """[n_src, n_out] matrix (tests / debugging only)."""
+        n = self.n_src if n_src_total is None else n_src_total
+        out = np.zeros((n, self.n_out))
+        for t in range(self.k_max):
+            use = self.cnt > t
+            np.add.at(out, (self.idx[t, use], np.nonzero(use)[0]), self.w[t, use])
+        return out
+
+
+def _pack(first, count, weights_fn):
+    """Evaluate ``weights_fn(src_index[k, n_out], valid[k, n_out])`` on the candidate window
+    ``first[o] .. first[o] + count[o] - 1`` of every output."""
+    k = int(max(count.max(), 1)) if count.size else 1
+    taps = np.arange(k)[:, None]
+    idx = first[None, :] + taps
+    valid = taps < count[None, :]
+    return idx, valid, weights_fn(np.where(valid, idx, 0), valid)
+
+
+def _normalize(w):
+    total = w.sum(axis=0)
+    total[total == 0] = 1e-12  # utils.py:168
+    return w / total
+
+
+def _compress(idx, w):
+    """Keep only the non-zero taps of every column, in their original order."""
+    keep = w != 0
+    cnt = keep.sum(axis=0).astype(np.int32)
+    k = int(max(cnt.max(), 1)) if cnt.size else 1
+    order = np.argsort(~keep, axis=0, kind="stable")[:k]
+    idx_c = np.take_along_axis(idx, order, axis=0)
+    w_c = np.take_along_axis(w, order, axis=0)
+    dead = np.arange(k)[:, None] >= cnt[None, :]
+    idx_c = np.where(dead, 0, idx_c)
+    w_c = np.where(dead, 0.0, w_c)
+    return idx_c.astype(np.int32), w_c, cnt
+
+
+def conservative_band(axis: FormattedAxis, tgt, spherical: bool = False) -> Band:
+    """Banded equivalent of ``get_weights`` (+ ``apply_spherical_correction``) for one axis.
+
+    The weights equal the reference's dense matrix entry for entry (the same ``min/max``
+    overlap expression, the same two normalisations); exact zeros are dropped, which is
+    what the reference's ``sparse.COO`` weights do (conservative.py:297-300).
+    """
+    tgt = np.asarray(tgt)
+    t_order = monotonic_order(tgt)
+    tgt_sorted = tgt if t_order is None else tgt[t_order]
+    restore = None
+    if t_order is not None or tgt_sorted.size != tgt.size:
+        restore = np.searchsorted(tgt_sorted, tgt).astype(np.int64)  # reindex_like(target)
+
+    src = axis.values
+    se = cell_edges(src)
+    te = cell_edges(tgt_sorted)
+    s_lo, s_hi = se[:-1], se[1:]
+    t_lo, t_hi = te[:-1], te[1:]
+    # candidate window: source cells with s_hi > t_lo and s_lo < t_hi
+    first = np.searchsorted(s_hi, t_lo, side="right")
+    last = np.searchsorted(s_lo, t_hi, side="left") - 1
+    count = np.maximum(last - first + 1, 0)
+
+    def overlap(i, valid):
+        ov = np.minimum(s_hi[i], t_hi[None, :]) - np.maximum(s_lo[i], t_lo[None, :])
+        return np.where(valid, np.maximum(ov, 0), 0.0)
+
+    idx, valid, w = _pack(first, count, overlap)
+    w = _normalize(w)
+    if spherical:
+        res = np.median(np.diff(src, 1))
+        lw = lat_weight(src, res)
+        w = _normalize(w * np.where(valid, lw[np.where(valid, idx, 0)], 0.0))
+    idx_c, w_c, cnt = _compress(np.where(valid, idx, 0), w)
+
+    cover = ((tgt_sorted <= src.max()) & (tgt_sorted >= src.min())).astype(np.uint8)
+    # formatted position -> original position (sort, lon shift / wrap, pole rows)
+    idx_src = axis.source[idx_c].astype(np.int32)
+    idx_src = np.where(np.arange(idx_c.shape[0])[:, None] < cnt[None, :], idx_src, 0).astype(np.int32)
+    if restore is not None:
+        # emit the outputs directly in the target's own order: reindex_like costs nothing
+        idx_src, w_c, cnt, cover = idx_src[:, restore], w_c[:, restore], cnt[restore], cover[restore]
+    return Band(np.ascontiguousarray(idx_src), np.ascontiguousarray(w_c), np.ascontiguousarray(cnt),
+                np.ascontiguousarray(cover), axis.n_src, restore,
+                {"formatted_size": int(src.size), "pole_rows": axis.has_pole_rows})
+
+
+def identity_band(n: int) -> Band:
+    """Pass-through axis (used when only one spatial coordinate is regridded)."""
+    return Band(
+        np.arange(n, dtype=np.int32)[None, :], np.ones((1, n)), np.ones(n, np.int32),
+        np.ones(n, np.uint8), n,
+    )
