@@ -74,6 +74,40 @@ typedef struct rg_band {
 } rg_band_t;
 
 /*
+ * Optional row-ring schedule for the TMA-pipelined conservative kernel.
+ *
+ * The fast kernel is persistent and warp-specialised: a producer thread streams whole
+ * source rows into a shared-memory ring with cp.async.bulk (TMA) + mbarriers and the
+ * consumer warps contract them, so every source row is read from HBM once per run even
+ * though neighbouring target rows share rows.  The schedule tells the producer in which
+ * order to load rows and the consumers where each tap lives.  It is derived from the rows
+ * band on the host (tables.row_ring_schedule); outputs are grouped into `n_runs`
+ * contiguous runs, one (slab, run) pair = one unit of work for a CTA.
+ *
+ *   sched_row[p]              source row loaded at schedule position p
+ *   run_first[r], run_sched[r]   first output / first schedule position of run r
+ *                             (arrays of n_runs + 1 entries)
+ *   tap_pos[t * n_out + o]    schedule position, RELATIVE to its run's first, of tap t of o
+ *   need[o]                   relative positions that must have landed before o is computed
+ *   release[o]                relative positions that are dead once o has been computed
+ *   max_live                  max over o of rows simultaneously alive (ring must hold them)
+ *
+ * Passing NULL selects the generic kernel (any band, pole rows, unaligned rows).
+ */
+typedef struct rg_row_ring {
+  const int32_t* sched_row; /* device, [n_sched]          */
+  const int32_t* tap_pos;   /* device, [k_max * n_out]    */
+  const int32_t* need;      /* device, [n_out]            */
+  const int32_t* release;   /* device, [n_out]            */
+  const int32_t* run_first; /* device, [n_runs + 1]       */
+  const int32_t* run_sched; /* device, [n_runs + 1]       */
+  int32_t n_runs;
+  int32_t n_sched;
+  int32_t max_live;
+  int32_t pad_shift; /* shared-memory column padding: slot(j) = j + (j >> pad_shift); 31 = none */
+} rg_row_ring_t;
+
+/*
  * Fused conservative regrid of a [batch, H, W] stack onto [batch, Ho, Wo]:
  *
  *   valid[b,k,l] = sum_ij notnull(x[b,i,j]) * Wlat[i,k] * Wlon[j,l]
@@ -88,16 +122,20 @@ typedef struct rg_band {
  * by the caller.  `pole` is NULL or a device [batch, 2] array holding the longitude-mean
  * of the first / last source row (rg_row_nanmean_*), referenced by idx == H / H+1.
  * H = rows.n_src, W = cols.n_src, Ho = rows.n_out, Wo = cols.n_out.  y is dense
- * [batch, Ho, Wo] with batch stride y_batch_stride.
+ * [batch, Ho, Wo] with batch stride y_batch_stride.  `ring` is NULL or the row-ring
+ * schedule above; the library silently uses the generic kernel when the ring kernel's
+ * preconditions (16-byte aligned rows, no pole rows, ring fits shared memory) do not hold.
  */
 int rg_conservative_f64(const double* x, double* y, int64_t batch,
                         int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
                         const rg_band_t* rows, const rg_band_t* cols,
-                        int32_t skipna, double valid_thr, const double* pole, void* stream);
+                        int32_t skipna, double valid_thr, const double* pole,
+                        const rg_row_ring_t* ring, void* stream);
 int rg_conservative_f32(const float* x, float* y, int64_t batch,
                         int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
                         const rg_band_t* rows, const rg_band_t* cols,
-                        int32_t skipna, float valid_thr, const float* pole, void* stream);
+                        int32_t skipna, float valid_thr, const float* pole,
+                        const rg_row_ring_t* ring, void* stream);
 
 /*
  * Longitude-mean (NaN-skipping) of the first and last row of every slab:
@@ -125,11 +163,11 @@ size_t rg_conservative_host_workspace(int64_t chunk_batch, int32_t H, int32_t W,
 int rg_conservative_host_f64(const double* x_host, double* y_host, int64_t batch,
                              int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
                              int32_t skipna, double valid_thr, int32_t pole_rows,
-                             void* workspace, size_t workspace_bytes);
+                             const rg_row_ring_t* ring, void* workspace, size_t workspace_bytes);
 int rg_conservative_host_f32(const float* x_host, float* y_host, int64_t batch,
                              int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
                              int32_t skipna, float valid_thr, int32_t pole_rows,
-                             void* workspace, size_t workspace_bytes);
+                             const rg_row_ring_t* ring, void* workspace, size_t workspace_bytes);
 
 #ifdef __cplusplus
 }

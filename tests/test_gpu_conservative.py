@@ -40,13 +40,15 @@ def _latlon_plan(engine, lat, lon, tlat, tlon):
 
 
 @pytest.mark.parametrize("skipna", [False, True])
-def test_c1_fp64(eng, skipna):
-    """BASELINE config 1: one 721x1440 fp64 step -> 181x360, no NaNs."""
+@pytest.mark.parametrize("ring", [True, False])
+def test_c1_fp64(eng, skipna, ring):
+    """BASELINE config 1: one 721x1440 fp64 step -> 181x360, no NaNs (TMA ring and generic kernel)."""
     engine, syn = eng
     lat, lon = syn.grid_025()
     tlat, tlon = syn.grid_1()
     x = syn.conservative_stack(1, lat, lon, nan_fraction=0.0)
     plan = _latlon_plan(engine, lat, lon, tlat, tlon)
+    plan.use_ring = ring
     y = plan(x, skipna=skipna)
     want = oc.regrid_latlon(x.cpu().numpy(), lat, lon, tlat, tlon, skipna=skipna)
     assert y.shape == (1, 181, 360) and y.dtype == torch.float64
@@ -54,7 +56,8 @@ def test_c1_fp64(eng, skipna):
 
 
 @pytest.mark.parametrize("nan_threshold", [0.0, 0.25, 0.5, 1.0])
-def test_c2_nan_semantics_fp64(eng, nan_threshold):
+@pytest.mark.parametrize("ring", [True, False])
+def test_c2_nan_semantics_fp64(eng, nan_threshold, ring):
     """BASELINE config 2 semantics on 3 steps: 10 % NaN, skipna=True, joint 2-D valid mass."""
     engine, syn = eng
     lat, lon = syn.grid_025()
@@ -62,6 +65,7 @@ def test_c2_nan_semantics_fp64(eng, nan_threshold):
     x = syn.conservative_stack(3, lat, lon, nan_fraction=0.10, chunk=2)
     x[2, 100:140, 200:300] = float("nan")  # a block that wipes out whole target cells
     plan = _latlon_plan(engine, lat, lon, tlat, tlon)
+    plan.use_ring = ring
     y = plan(x, skipna=True, nan_threshold=nan_threshold)
     want = oc.regrid_latlon(x.cpu().numpy(), lat, lon, tlat, tlon, skipna=True,
                             nan_threshold=nan_threshold)
@@ -69,12 +73,14 @@ def test_c2_nan_semantics_fp64(eng, nan_threshold):
     _check(y, want, 1e-12)
 
 
-def test_fp32(eng):
+@pytest.mark.parametrize("ring", [True, False])
+def test_fp32(eng, ring):
     engine, syn = eng
     lat, lon = syn.grid_025()
     tlat, tlon = syn.grid_1()
     x = syn.conservative_stack(2, lat, lon, dtype=torch.float32, nan_fraction=0.10)
     plan = _latlon_plan(engine, lat, lon, tlat, tlon)
+    plan.use_ring = ring
     y = plan(x, skipna=True, nan_threshold=0.5)
     assert y.dtype == torch.float32
     want = oc.regrid_latlon(x.cpu().numpy(), lat, lon, tlat, tlon, skipna=True, nan_threshold=0.5)
@@ -259,6 +265,12 @@ def test_properties_at_scale(eng):
     for s in (0, 1, steps // 2, steps - 1):
         want = oc.regrid_latlon(x[s].cpu().numpy(), lat, lon, tlat, tlon, skipna=True, nan_threshold=0.5)
         _check(y[s], want, 1e-12)
+    # the generic (non-TMA) kernel must agree with the ring kernel to the last few bits
+    plan.use_ring = False
+    yg = plan(x[:64], skipna=True, nan_threshold=0.5)
+    plan.use_ring = True
+    assert torch.equal(torch.isnan(yg), torch.isnan(y[:64]))
+    assert torch.allclose(torch.nan_to_num(yg), torch.nan_to_num(y[:64]), rtol=1e-14, atol=0)
     # constant field -> the same constant wherever defined (weights are normalised)
     c = torch.full((4, 721, 1440), 3.25, dtype=torch.float64, device="cuda")
     yc = plan(c, skipna=True)

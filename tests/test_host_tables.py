@@ -90,3 +90,42 @@ def test_valid_threshold(golden_helpers):
     g = golden_helpers
     got = np.array([tables.valid_threshold(t) for t in g["threshold/in"]])
     np.testing.assert_array_equal(got, g["threshold/out"])
+
+
+@pytest.mark.parametrize("n_runs", [1, 3, 50, 181])
+@pytest.mark.parametrize("descending", [False, True])
+def test_row_ring_schedule_invariants(n_runs, descending):
+    """What the TMA row-ring kernel relies on: every tap of an output is in the ring (loaded,
+    not yet released) when the output is computed, rows are released in FIFO order, and the
+    number of simultaneously live rows never exceeds max_live."""
+    lat = np.arange(-90, 90.25, 0.25)
+    tlat = np.arange(-90.0, 91.0, 1.0)
+    if descending:
+        lat, tlat = lat[::-1].copy(), tlat[::-1].copy()
+    rows = tables.conservative_band(tables.format_lat_axis(lat), tlat, spherical=True)
+    ring = tables.row_ring_schedule(rows, n_runs)
+    assert ring.n_runs == min(n_runs, 181)
+    assert ring.run_first[0] == 0 and ring.run_first[-1] == rows.n_out
+    assert ring.run_sched[-1] == ring.sched_row.size
+    for r in range(ring.n_runs):
+        k0, k1 = ring.run_first[r], ring.run_first[r + 1]
+        s0, s1 = ring.run_sched[r], ring.run_sched[r + 1]
+        prev_release = 0
+        for k in range(k0, k1):
+            assert prev_release <= ring.release[k] <= ring.need[k] <= s1 - s0
+            assert ring.need[k] - prev_release <= ring.max_live
+            for t in range(rows.cnt[k]):
+                p = ring.tap_pos[t, k]
+                assert prev_release <= p < ring.need[k]
+                assert ring.sched_row[s0 + p] == rows.idx[t, k]
+            prev_release = ring.release[k]
+        assert prev_release == s1 - s0, "every row must be released at the end of its run"
+    if n_runs == 1:
+        assert ring.sched_row.size == 719  # every source row with non-zero weight, exactly once
+
+
+def test_row_ring_schedule_rejects_pole_rows():
+    rows = tables.conservative_band(tables.format_lat_axis(np.arange(-89.0, 90, 2)),
+                                    np.arange(-90.0, 91, 1), spherical=True)
+    if (rows.idx >= rows.n_src).any():
+        assert tables.row_ring_schedule(rows, 1) is None

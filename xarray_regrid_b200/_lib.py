@@ -31,6 +31,21 @@ class rg_band_t(C.Structure):  # noqa: N801 - mirrors the C name
     ]
 
 
+class rg_row_ring_t(C.Structure):  # noqa: N801 - mirrors the C name
+    _fields_ = [
+        ("sched_row", C.c_void_p),
+        ("tap_pos", C.c_void_p),
+        ("need", C.c_void_p),
+        ("release", C.c_void_p),
+        ("run_first", C.c_void_p),
+        ("run_sched", C.c_void_p),
+        ("n_runs", C.c_int32),
+        ("n_sched", C.c_int32),
+        ("max_live", C.c_int32),
+        ("pad_shift", C.c_int32),
+    ]
+
+
 def _load():
     if not LIB_PATH.exists():
         raise ImportError(
@@ -40,17 +55,18 @@ def _load():
     lib = C.CDLL(str(LIB_PATH))
     p, i32, i64, f32, f64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
     band = C.POINTER(rg_band_t)
+    ring = C.POINTER(rg_row_ring_t)
     sig = {
         "rg_abi_version": (C.c_int, []),
         "rg_error_string": (C.c_char_p, [C.c_int]),
         "rg_device_sm_count": (C.c_int, []),
-        "rg_conservative_f64": (C.c_int, [p, p, i64, i64, i64, i64, band, band, i32, f64, p, p]),
-        "rg_conservative_f32": (C.c_int, [p, p, i64, i64, i64, i64, band, band, i32, f32, p, p]),
+        "rg_conservative_f64": (C.c_int, [p, p, i64, i64, i64, i64, band, band, i32, f64, p, ring, p]),
+        "rg_conservative_f32": (C.c_int, [p, p, i64, i64, i64, i64, band, band, i32, f32, p, ring, p]),
         "rg_row_nanmean_f64": (C.c_int, [p, p, i64, i32, i32, i64, i64, p]),
         "rg_row_nanmean_f32": (C.c_int, [p, p, i64, i32, i32, i64, i64, p]),
         "rg_conservative_host_workspace": (sz, [i64, i32, i32, i32, i32, i32]),
-        "rg_conservative_host_f64": (C.c_int, [p, p, i64, i64, band, band, i32, f64, i32, p, sz]),
-        "rg_conservative_host_f32": (C.c_int, [p, p, i64, i64, band, band, i32, f32, i32, p, sz]),
+        "rg_conservative_host_f64": (C.c_int, [p, p, i64, i64, band, band, i32, f64, i32, ring, p, sz]),
+        "rg_conservative_host_f32": (C.c_int, [p, p, i64, i64, band, band, i32, f32, i32, ring, p, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

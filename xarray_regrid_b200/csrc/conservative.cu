@@ -15,6 +15,7 @@
 // ~0.4 per byte, far below the fp64 ridge, so tensor cores are not used.
 
 #include "common.cuh"
+#include "conservative_ring.cuh"
 
 namespace rg {
 
@@ -182,7 +183,7 @@ int row_nanmean_launch(const T* x, T* pole, int64_t batch, int32_t H, int32_t W,
 template <typename T>
 int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
                         const rg_band_t* rows_c, const rg_band_t* cols_c, int32_t skipna, T thr,
-                        const T* pole, cudaStream_t stream) {
+                        const T* pole, const rg_row_ring_t* ring_c, cudaStream_t stream) {
   if (!x || !y) return RG_ERR_NULL;
   Band<T> rows, cols;
   int rc = make_band<T>(rows_c, &rows);
@@ -205,6 +206,31 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   DeviceInfo dev;
   rc = device_info(&dev);
   if (rc != RG_OK) return rc;
+
+  // ---- fast path: TMA row-ring kernel (needs 16-byte aligned rows, no pole rows, a ring that fits)
+  if (ring_c && !pole && aligned && (static_cast<size_t>(W) * sizeof(T)) % 16 == 0 &&
+      ring_c->n_runs > 0 && ring_c->sched_row && ring_c->tap_pos && ring_c->need && ring_c->release &&
+      ring_c->run_first && ring_c->run_sched) {
+    const RingLayout probe = ring_layout<T>(W, cols.n_out, cols.k_max, ring_c->pad_shift, skipna != 0, 0);
+    const long long room = static_cast<long long>(dev.max_smem_optin) - static_cast<long long>(probe.total);
+    int slots = room > 0 ? static_cast<int>(room / probe.row_stride) : 0;
+    if (slots > kRingMaxSlots) slots = kRingMaxSlots;
+    if (slots >= ring_c->max_live + 1 && slots >= 2) {
+      const RingLayout L = ring_layout<T>(W, cols.n_out, cols.k_max, ring_c->pad_shift, skipna != 0, slots);
+      RingDev ring{ring_c->sched_row, ring_c->tap_pos, ring_c->need,     ring_c->release,
+                   ring_c->run_first, ring_c->run_sched, ring_c->n_runs, ring_c->n_sched,
+                   ring_c->max_live,  ring_c->pad_shift};
+      auto kern = skipna ? conservative_ring_kernel<T, true> : conservative_ring_kernel<T, false>;
+      RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(L.total)));
+      const long long tasks = static_cast<long long>(batch) * ring.n_runs;
+      long long grid = dev.sm_count;
+      if (grid > tasks) grid = tasks;
+      kern<<<static_cast<unsigned>(grid), kRingThreads, L.total, stream>>>(x, y, batch, xbs, xrs, ybs, rows,
+                                                                          cols, ring, thr, slots);
+      return static_cast<int>(cudaGetLastError());
+    }
+  }
   if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_SMEM;
 
   using Kernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>,
@@ -263,8 +289,8 @@ struct PipelineResources {
 
 template <typename T>
 int conservative_host(const T* xh, T* yh, int64_t batch, int64_t chunk, const rg_band_t* rows,
-                      const rg_band_t* cols, int32_t skipna, T thr, int32_t pole_rows, void* ws,
-                      size_t ws_bytes) {
+                      const rg_band_t* cols, int32_t skipna, T thr, int32_t pole_rows,
+                      const rg_row_ring_t* ring, void* ws, size_t ws_bytes) {
   if (!xh || !yh || !ws || !rows || !cols) return RG_ERR_NULL;
   if (batch < 0 || chunk <= 0) return RG_ERR_SHAPE;
   if (batch == 0) return RG_OK;
@@ -309,7 +335,7 @@ int conservative_host(const T* xh, T* yh, int64_t batch, int64_t chunk, const rg
       if (rc != RG_OK) return rc;
     }
     rc = conservative_launch<T>(d_in[s], d_out[s], nb, H * W, W, Ho * Wo, rows, cols, skipna, thr,
-                                pole_rows ? d_pole[s] : nullptr, res.s_k);
+                                pole_rows ? d_pole[s] : nullptr, ring, res.s_k);
     if (rc != RG_OK) return rc;
     RG_CUDA(cudaEventRecord(res.k_done[s], res.s_k));
 
@@ -332,16 +358,16 @@ extern "C" {
 
 int rg_conservative_f64(const double* x, double* y, int64_t batch, int64_t xbs, int64_t xrs,
                         int64_t ybs, const rg_band_t* rows, const rg_band_t* cols, int32_t skipna,
-                        double valid_thr, const double* pole, void* stream) {
+                        double valid_thr, const double* pole, const rg_row_ring_t* ring, void* stream) {
   return rg::conservative_launch<double>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna, valid_thr,
-                                         pole, static_cast<cudaStream_t>(stream));
+                                         pole, ring, static_cast<cudaStream_t>(stream));
 }
 
 int rg_conservative_f32(const float* x, float* y, int64_t batch, int64_t xbs, int64_t xrs,
                         int64_t ybs, const rg_band_t* rows, const rg_band_t* cols, int32_t skipna,
-                        float valid_thr, const float* pole, void* stream) {
+                        float valid_thr, const float* pole, const rg_row_ring_t* ring, void* stream) {
   return rg::conservative_launch<float>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna, valid_thr,
-                                        pole, static_cast<cudaStream_t>(stream));
+                                        pole, ring, static_cast<cudaStream_t>(stream));
 }
 
 int rg_row_nanmean_f64(const double* x, double* pole, int64_t batch, int32_t H, int32_t W,
@@ -367,18 +393,18 @@ size_t rg_conservative_host_workspace(int64_t chunk_batch, int32_t H, int32_t W,
 
 int rg_conservative_host_f64(const double* x_host, double* y_host, int64_t batch,
                              int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
-                             int32_t skipna, double valid_thr, int32_t pole_rows, void* workspace,
-                             size_t workspace_bytes) {
+                             int32_t skipna, double valid_thr, int32_t pole_rows,
+                             const rg_row_ring_t* ring, void* workspace, size_t workspace_bytes) {
   return rg::conservative_host<double>(x_host, y_host, batch, chunk_batch, rows, cols, skipna,
-                                       valid_thr, pole_rows, workspace, workspace_bytes);
+                                       valid_thr, pole_rows, ring, workspace, workspace_bytes);
 }
 
 int rg_conservative_host_f32(const float* x_host, float* y_host, int64_t batch,
                              int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
-                             int32_t skipna, float valid_thr, int32_t pole_rows, void* workspace,
-                             size_t workspace_bytes) {
+                             int32_t skipna, float valid_thr, int32_t pole_rows,
+                             const rg_row_ring_t* ring, void* workspace, size_t workspace_bytes) {
   return rg::conservative_host<float>(x_host, y_host, batch, chunk_batch, rows, cols, skipna,
-                                      valid_thr, pole_rows, workspace, workspace_bytes);
+                                      valid_thr, pole_rows, ring, workspace, workspace_bytes);
 }
 
 }  // extern "C"

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib, tables
-from ._lib import check, lib, rg_band_t
+from ._lib import check, lib, rg_band_t, rg_row_ring_t
 
 
 def _require_cuda(device=None) -> torch.device:
@@ -49,6 +49,29 @@ class DeviceBand:
         self.c = rg_band_t(
             self.idx.data_ptr(), self.w.data_ptr(), self.cnt.data_ptr(), self.cover.data_ptr(),
             band.n_out, band.k_max, band.n_src,
+        )
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+
+class DeviceRing:
+    """A ``tables.RowRing`` uploaded to the GPU, plus the ``rg_row_ring_t`` that points at it."""
+
+    def __init__(self, ring: tables.RowRing, device: torch.device):
+        self.host = ring
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+
+        self.sched_row, self.tap_pos = up(ring.sched_row), up(ring.tap_pos)
+        self.need, self.release = up(ring.need), up(ring.release)
+        self.run_first, self.run_sched = up(ring.run_first), up(ring.run_sched)
+        self.c = rg_row_ring_t(
+            self.sched_row.data_ptr(), self.tap_pos.data_ptr(), self.need.data_ptr(),
+            self.release.data_ptr(), self.run_first.data_ptr(), self.run_sched.data_ptr(),
+            ring.n_runs, int(ring.sched_row.size), ring.max_live, ring.pad_shift,
         )
 
     @property
@@ -118,8 +141,23 @@ class ConservativePlan:
             (self.rows_band.idx >= self.rows_band.n_src).any()
         )
         self._dev: dict = {}
+        self._rings: dict = {}
+        self.use_ring = True  # tests flip this to exercise the generic kernel
 
     # ------------------------------------------------------------------------------
+    def _ring(self, batch: int, n_cols: int):
+        """Row-ring schedule sized so that (slabs x runs) fills the SMs about twice over."""
+        if not self.use_ring or self.pole_rows:
+            return None
+        sms = max(sm_count(), 1)
+        n_runs = int(min(self.rows_band.n_out, max(1, -(-2 * sms // max(batch, 1)))))
+        key = (n_runs, n_cols)
+        if key not in self._rings:
+            cols = self.cols_band if self.cols_band is not None else tables.identity_band(n_cols)
+            host = tables.row_ring_schedule(self.rows_band, n_runs, cols)
+            self._rings[key] = None if host is None else DeviceRing(host, self.device)
+        return self._rings[key]
+
     def _bands(self, dtype: torch.dtype, n_cols: int):
         key = (dtype, n_cols)
         if key not in self._dev:
@@ -128,9 +166,8 @@ class ConservativePlan:
                               DeviceBand(cols, dtype, self.device))
         return self._dev[key]
 
-    @property
-    def out_shape(self):
-        return (self.rows_band.n_out, None if self.cols_band is None else self.cols_band.n_out)
+    def _out_hw(self, n_cols: int):
+        return (self.rows_band.n_out, n_cols if self.cols_band is None else self.cols_band.n_out)
 
     def __call__(self, x: torch.Tensor, skipna: bool = True, nan_threshold: float = 1.0,
                  out: torch.Tensor | None = None) -> torch.Tensor:
@@ -141,6 +178,8 @@ class ConservativePlan:
         dtype = _result_dtype(x)
         x3, lead = _as_batch(x, dtype)
         B, H, W = x3.shape
+        if B == 0:
+            return torch.empty(tuple(x.shape[:-2]) + self._out_hw(W), dtype=dtype, device=x.device)
         rows, cols = self._bands(dtype, W)
         if H != rows.host.n_src or W != cols.host.n_src:
             raise ValueError(
@@ -162,10 +201,11 @@ class ConservativePlan:
                   "rg_row_nanmean")
         fn = lib.rg_conservative_f64 if dtype == torch.float64 else lib.rg_conservative_f32
         thr = tables.valid_threshold(nan_threshold)
+        ring = self._ring(B, W)
         check(
             fn(x3.data_ptr(), y.data_ptr(), B, x3.stride(0) if B > 1 else H * x3.stride(1),
                x3.stride(1), Ho * Wo, rows.ref, cols.ref, int(bool(skipna)), thr,
-               None if pole is None else pole.data_ptr(), stream),
+               None if pole is None else pole.data_ptr(), None if ring is None else ring.ref, stream),
             "rg_conservative",
         )
         return y.view(tuple(lead) + (Ho, Wo))
@@ -193,9 +233,11 @@ class ConservativePlan:
             if workspace is None or workspace.numel() * workspace.element_size() < need:
                 workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
             fn = lib.rg_conservative_host_f64 if dtype == torch.float64 else lib.rg_conservative_host_f32
+            ring = self._ring(min(chunk_batch, B), W)
             check(
                 fn(x3.data_ptr(), out_host.data_ptr(), B, chunk_batch, rows.ref, cols.ref,
                    int(bool(skipna)), tables.valid_threshold(nan_threshold), int(self.pole_rows),
+                   None if ring is None else ring.ref,
                    workspace.data_ptr(), workspace.numel() * workspace.element_size()),
                 "rg_conservative_host",
             )

@@ -273,3 +273,83 @@ def identity_band(n: int) -> Band:
         np.arange(n, dtype=np.int32)[None, :], np.ones((1, n)), np.ones(n, np.int32),
         np.ones(n, np.uint8), n,
     )
+
+
+# ------------------------------------------------------------- TMA row-ring schedule
+@dataclass
+class RowRing:
+    """Load order / liveness schedule of the rows band for the TMA row-ring kernel
+    (``rg_row_ring_t`` in include/regrid_b200.h)."""
+
+    sched_row: np.ndarray  # int32 [n_sched]
+    tap_pos: np.ndarray  # int32 [k_max, n_out], relative to the run's first position
+    need: np.ndarray  # int32 [n_out]
+    release: np.ndarray  # int32 [n_out]
+    run_first: np.ndarray  # int32 [n_runs + 1]
+    run_sched: np.ndarray  # int32 [n_runs + 1]
+    max_live: int
+    pad_shift: int
+
+    @property
+    def n_runs(self) -> int:
+        return int(self.run_first.size - 1)
+
+
+def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None) -> RowRing | None:
+    """Schedule for streaming the source rows of ``rows`` through a shared-memory ring.
+
+    Outputs are visited in order and split into ``n_runs`` contiguous runs.  Inside a run a
+    source row is loaded when first needed and stays in the ring until its last use, so rows
+    shared by neighbouring outputs are read once.  Returns None when the band references the
+    synthetic pole rows (the generic kernel handles those).
+    """
+    n_out, k_max = rows.n_out, rows.k_max
+    cnt = np.where(rows.cover > 0, rows.cnt, 0)
+    if n_out == 0 or (rows.idx >= rows.n_src).any():
+        return None
+    n_runs = int(max(1, min(n_runs, n_out)))
+    run_first = np.unique(np.round(np.linspace(0, n_out, n_runs + 1)).astype(np.int64))
+    tap_pos = np.zeros((k_max, n_out), np.int32)
+    need = np.zeros(n_out, np.int32)
+    release = np.zeros(n_out, np.int32)
+    sched: list[int] = []
+    run_sched = [0]
+    max_live = 1
+    for r in range(run_first.size - 1):
+        k0, k1 = int(run_first[r]), int(run_first[r + 1])
+        last_use: dict[int, int] = {}
+        for k in range(k0, k1):
+            for t in range(int(cnt[k])):
+                last_use[int(rows.idx[t, k])] = k
+        pos_of: dict[int, int] = {}
+        order: list[int] = []
+        freed = 0
+        for k in range(k0, k1):
+            for t in range(int(cnt[k])):
+                row = int(rows.idx[t, k])
+                if row not in pos_of:
+                    pos_of[row] = len(order)
+                    order.append(row)
+                tap_pos[t, k] = pos_of[row]
+            need[k] = len(order)
+            max_live = max(max_live, len(order) - freed)
+            while freed < len(order) and last_use[order[freed]] <= k:
+                freed += 1
+            release[k] = freed
+        assert freed == len(order)
+        sched.extend(order)
+        run_sched.append(len(sched))
+
+    # shared-memory padding of the t / v column arrays: with an integer power-of-two ratio r
+    # of source to target columns the longitude pass reads with stride r; one pad word every
+    # r makes the stride odd and the accesses bank-conflict free
+    pad_shift = 31
+    if cols is not None and cols.n_out > 0:
+        ratio = cols.n_src / cols.n_out
+        r = int(round(ratio))
+        if r >= 2 and abs(ratio - r) < 0.26 and (r & (r - 1)) == 0:
+            pad_shift = r.bit_length() - 1
+    return RowRing(
+        np.asarray(sched, np.int32), tap_pos, need, release,
+        run_first.astype(np.int32), np.asarray(run_sched, np.int32), int(max_live), pad_shift,
+    )
