@@ -87,24 +87,43 @@ typedef struct rg_band {
  *   sched_row[p]              source row loaded at schedule position p
  *   run_first[r], run_sched[r]   first output / first schedule position of run r
  *                             (arrays of n_runs + 1 entries)
- *   tap_pos[t * n_out + o]    schedule position, RELATIVE to its run's first, of tap t of o
- *   need[o]                   relative positions that must have landed before o is computed
- *   release[o]                relative positions that are dead once o has been computed
+ *   krec[4 * o + 0..3]        per output row o, one 16-byte record:
+ *                               [0] need     positions (relative to the run's first) that must
+ *                                            have landed before o is computed
+ *                               [1] release  relative positions that are dead once o is computed
+ *                               [2] kcnt     taps of o (<= 8), or -1 when o is not covered (NaN row)
+ *                               [3] tap_back 8 x 4 bits: where tap t lives, in rows back from the
+ *                                            newest landed row (= need - 1 - its relative position)
+ *   wrec[8 * o + t]           weight of tap t of output row o (element type of the data, zero
+ *                             padded): the rows band's weights, output-major
  *   max_live                  max over o of rows simultaneously alive (ring must hold them)
+ *
+ * Column decomposition: the target columns are cut into `n_strips` strips of <= 32 outputs;
+ * consumer warp w of `n_warps` handles strips w, w + n_warps, ...  For strip s
+ *   strip_l0[s] .. strip_l0[s+1]-1   its target columns
+ *   strip_c0[s], strip_nc[s]         the source columns (a range modulo n_src that may wrap
+ *                                    around the date line) covering every tap of those targets;
+ *                                    both are multiples of 16 / sizeof(element)
+ *   strip_cols_max                   max over s of strip_nc[s]
  *
  * Passing NULL selects the generic kernel (any band, pole rows, unaligned rows).
  */
 typedef struct rg_row_ring {
   const int32_t* sched_row; /* device, [n_sched]          */
-  const int32_t* tap_pos;   /* device, [k_max * n_out]    */
-  const int32_t* need;      /* device, [n_out]            */
-  const int32_t* release;   /* device, [n_out]            */
+  const int32_t* krec;      /* device, [4 * n_out], 16-byte aligned */
+  const void* wrec;         /* device, [8 * n_out], 16-byte aligned */
   const int32_t* run_first; /* device, [n_runs + 1]       */
   const int32_t* run_sched; /* device, [n_runs + 1]       */
+  const int32_t* strip_l0;  /* device, [n_strips + 1]     */
+  const int32_t* strip_c0;  /* device, [n_strips]         */
+  const int32_t* strip_nc;  /* device, [n_strips]         */
   int32_t n_runs;
   int32_t n_sched;
   int32_t max_live;
   int32_t pad_shift; /* shared-memory column padding: slot(j) = j + (j >> pad_shift); 31 = none */
+  int32_t n_strips;
+  int32_t strip_cols_max;
+  int32_t n_warps;   /* consumer warps (1..24); the kernel adds one producer warp */
 } rg_row_ring_t;
 
 /*
@@ -124,7 +143,8 @@ typedef struct rg_row_ring {
  * H = rows.n_src, W = cols.n_src, Ho = rows.n_out, Wo = cols.n_out.  y is dense
  * [batch, Ho, Wo] with batch stride y_batch_stride.  `ring` is NULL or the row-ring
  * schedule above; the library silently uses the generic kernel when the ring kernel's
- * preconditions (16-byte aligned rows, no pole rows, ring fits shared memory) do not hold.
+ * preconditions (16-byte aligned rows, no pole rows, <= 8 taps per axis, ring fits shared
+ * memory) do not hold.
  */
 int rg_conservative_f64(const double* x, double* y, int64_t batch,
                         int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,

@@ -114,8 +114,10 @@ def test_row_ring_schedule_invariants(n_runs, descending):
         for k in range(k0, k1):
             assert prev_release <= ring.release[k] <= ring.need[k] <= s1 - s0
             assert ring.need[k] - prev_release <= ring.max_live
+            assert ring.kcnt[k] == rows.cnt[k]
             for t in range(rows.cnt[k]):
-                p = ring.tap_pos[t, k]
+                assert 0 <= ring.tap_back[t, k] < ring.max_live
+                p = ring.need[k] - 1 - ring.tap_back[t, k]
                 assert prev_release <= p < ring.need[k]
                 assert ring.sched_row[s0 + p] == rows.idx[t, k]
             prev_release = ring.release[k]

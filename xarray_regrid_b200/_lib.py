@@ -34,15 +34,20 @@ class rg_band_t(C.Structure):  # noqa: N801 - mirrors the C name
 class rg_row_ring_t(C.Structure):  # noqa: N801 - mirrors the C name
     _fields_ = [
         ("sched_row", C.c_void_p),
-        ("tap_pos", C.c_void_p),
-        ("need", C.c_void_p),
-        ("release", C.c_void_p),
+        ("krec", C.c_void_p),
+        ("wrec", C.c_void_p),
         ("run_first", C.c_void_p),
         ("run_sched", C.c_void_p),
+        ("strip_l0", C.c_void_p),
+        ("strip_c0", C.c_void_p),
+        ("strip_nc", C.c_void_p),
         ("n_runs", C.c_int32),
         ("n_sched", C.c_int32),
         ("max_live", C.c_int32),
         ("pad_shift", C.c_int32),
+        ("n_strips", C.c_int32),
+        ("strip_cols_max", C.c_int32),
+        ("n_warps", C.c_int32),
     ]
 
 

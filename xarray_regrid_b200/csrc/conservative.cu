@@ -207,27 +207,61 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   rc = device_info(&dev);
   if (rc != RG_OK) return rc;
 
-  // ---- fast path: TMA row-ring kernel (needs 16-byte aligned rows, no pole rows, a ring that fits)
+  // ---- fast path: TMA row-ring kernel (needs 16-byte aligned rows, no pole rows, <= 8 taps per
+  //      axis, a ring that fits shared memory)
   if (ring_c && !pole && aligned && (static_cast<size_t>(W) * sizeof(T)) % 16 == 0 &&
-      ring_c->n_runs > 0 && ring_c->sched_row && ring_c->tap_pos && ring_c->need && ring_c->release &&
-      ring_c->run_first && ring_c->run_sched) {
-    const RingLayout probe = ring_layout<T>(W, cols.n_out, cols.k_max, ring_c->pad_shift, skipna != 0, 0);
+      rows.k_max <= kRingMaxTaps && cols.k_max <= 8 && ring_c->n_runs > 0 && ring_c->n_strips > 0 &&
+      ring_c->n_warps >= 1 && ring_c->n_warps <= kRingMaxWarps && ring_c->max_live < kRingMaxSlots &&
+      ring_c->sched_row && ring_c->krec && ring_c->wrec && ring_c->run_first && ring_c->run_sched &&
+      ring_c->strip_l0 && ring_c->strip_c0 && ring_c->strip_nc) {
+    const int kw = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : cols.k_max <= 3 ? 3 : cols.k_max <= 5 ? 5 : 8;
+    const RingLayout probe =
+        ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, 0);
     const long long room = static_cast<long long>(dev.max_smem_optin) - static_cast<long long>(probe.total);
     int slots = room > 0 ? static_cast<int>(room / probe.row_stride) : 0;
     if (slots > kRingMaxSlots) slots = kRingMaxSlots;
     if (slots >= ring_c->max_live + 1 && slots >= 2) {
-      const RingLayout L = ring_layout<T>(W, cols.n_out, cols.k_max, ring_c->pad_shift, skipna != 0, slots);
-      RingDev ring{ring_c->sched_row, ring_c->tap_pos, ring_c->need,     ring_c->release,
-                   ring_c->run_first, ring_c->run_sched, ring_c->n_runs, ring_c->n_sched,
-                   ring_c->max_live,  ring_c->pad_shift};
-      auto kern = skipna ? conservative_ring_kernel<T, true> : conservative_ring_kernel<T, false>;
+      const RingLayout L =
+          ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, slots);
+      RingDev ring{ring_c->sched_row,
+                   reinterpret_cast<const int4*>(ring_c->krec),
+                   ring_c->wrec,
+                   ring_c->run_first,
+                   ring_c->run_sched,
+                   ring_c->strip_l0,
+                   ring_c->strip_c0,
+                   ring_c->strip_nc,
+                   ring_c->n_runs,
+                   ring_c->n_sched,
+                   ring_c->max_live,
+                   ring_c->pad_shift,
+                   ring_c->n_strips,
+                   ring_c->strip_cols_max,
+                   ring_c->n_warps};
+      using RingKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev,
+                                  T, int);
+      const int warps = ring.n_warps + 2;  // + producer + sync
+      const bool small = warps <= 14;
+      RingKernel kern = nullptr;
+#define RG_PICK(KW)                                                                                   \
+  case KW:                                                                                            \
+    kern = skipna ? (small ? conservative_ring_kernel<T, true, KW, 14>                                \
+                           : conservative_ring_kernel<T, true, KW, 26>)                               \
+                  : (small ? conservative_ring_kernel<T, false, KW, 14>                               \
+                           : conservative_ring_kernel<T, false, KW, 26>);                             \
+    break;
+      switch (kw) {
+        RG_PICK(1) RG_PICK(2) RG_PICK(3) RG_PICK(5) RG_PICK(8)
+        default: break;
+      }
+#undef RG_PICK
       RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(L.total)));
       const long long tasks = static_cast<long long>(batch) * ring.n_runs;
       long long grid = dev.sm_count;
       if (grid > tasks) grid = tasks;
-      kern<<<static_cast<unsigned>(grid), kRingThreads, L.total, stream>>>(x, y, batch, xbs, xrs, ybs, rows,
-                                                                          cols, ring, thr, slots);
+      kern<<<static_cast<unsigned>(grid), warps * 32, L.total, stream>>>(x, y, batch, xbs, xrs, ybs, cols,
+                                                                        ring, thr, slots);
       return static_cast<int>(cudaGetLastError());
     }
   }

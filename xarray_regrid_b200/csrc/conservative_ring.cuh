@@ -1,18 +1,23 @@
-// TMA row-ring conservative kernel (sm_100a): persistent, warp-specialised.
+// TMA row-ring conservative kernel (sm_100a): persistent, warp-specialised, barrier-free.
 //
-//   producer (1 elected thread of warp 8)   streams whole source rows HBM -> shared-memory ring
-//                                           with cp.async.bulk (TMA, SASS: UBLKCP) and arms one
-//                                           "full" mbarrier per ring slot with the row's byte count
-//   consumers (warps 0-7)                   wait on "full", contract the band's rows along latitude
-//                                           into double-buffered t / v column arrays (phase 1),
-//                                           hand dead rows back through "empty" mbarriers, then
-//                                           contract t / v along longitude, normalise, mask and
-//                                           store one output row (phase 2)
+//   producer (one elected thread of warp n_warps)
+//       streams whole source rows HBM -> shared-memory ring with cp.async.bulk (TMA, SASS: UBLKCP)
+//       and arms one "full" mbarrier per ring slot with the row's byte count; a slot is reused once
+//       every consumer warp has published (st.release) that it is done with the row it held
+//   sync (one elected thread of warp n_warps + 1)
+//       waits on the "full" mbarriers in order and publishes the number of landed rows in one
+//       shared counter, so a consumer's wait is a single ld.acquire instead of per-row barrier math
+//   consumer warps (all other warps), each owning strips of <= 32 target columns
+//       poll the landed counter; contract the band's rows along latitude for the source columns their strip
+//       needs (its taps + halo) into a warp-private shared buffer of {t, v} pairs (phase 1);
+//       __syncwarp; contract along longitude, normalise, mask and store their part of the output
+//       row (phase 2); publish their progress so the producer can recycle dead rows
 //
-// A unit of work is (slab b, run of consecutive target rows); the ring keeps rows alive across
-// the target rows that share them, so every source row crosses HBM->SM exactly once per run and
-// the producer prefetches across row, run and slab boundaries (no load/compute phase bubbles).
-// The load order / liveness schedule is precomputed on the host (rg_row_ring_t).
+// There is no CTA-wide barrier after start-up: warps run decoupled, limited only by the ring.
+// A unit of work is (slab b, run of consecutive target rows); the ring keeps rows alive across the
+// target rows that share them, so every source row crosses HBM->SM exactly once per run and the
+// producer prefetches across row, run and slab boundaries.  Load order / liveness (rows) and the
+// strip decomposition (columns) are precomputed on the host (rg_row_ring_t).
 #pragma once
 
 #include "common.cuh"
@@ -21,49 +26,47 @@ namespace rg {
 
 struct RingDev {
   const int32_t* __restrict__ sched_row;
-  const int32_t* __restrict__ tap_pos;
-  const int32_t* __restrict__ need;
-  const int32_t* __restrict__ release;
+  const int4* __restrict__ krec;   // per output row: {need, release, kcnt, 8 x 4-bit tap_back}
+  const void* __restrict__ wrec;   // per output row: 8 tap weights (zero padded), output-major
   const int32_t* __restrict__ run_first;
   const int32_t* __restrict__ run_sched;
-  int n_runs, n_sched, max_live, pad_shift;
+  const int32_t* __restrict__ strip_l0;
+  const int32_t* __restrict__ strip_c0;
+  const int32_t* __restrict__ strip_nc;
+  int n_runs, n_sched, max_live, pad_shift, n_strips, strip_cols_max, n_warps;
 };
 
-constexpr int kRingConsumers = 256;
-constexpr int kRingThreads = kRingConsumers + 32;
 constexpr int kRingMaxSlots = 16;
-constexpr int kTapChunk = 8;
+constexpr int kRingMaxTaps = 8;   // row taps per output handled by the ring kernel
+constexpr int kRingMaxWarps = 24; // consumer warps
 
 // Shared-memory carve-up, computed identically on host and device.
 struct RingLayout {
-  int ring_slots, row_stride, w_slots, tv_stride;
-  size_t off_bar, off_tv, off_cw, off_cidx, off_ccnt, total;
+  int ring_slots, row_stride, strip_slots;
+  size_t strip_bytes;  // one warp-private {t, v} buffer
+  size_t off_bar, off_flags, off_strip, total;
 };
 
 template <typename T>
-__host__ __device__ inline RingLayout ring_layout(int W, int Wo, int Kw, int pad_shift, bool skipna,
-                                                  int ring_slots) {
+__host__ __device__ inline RingLayout ring_layout(int W, int pad_shift, bool skipna, int strip_cols_max,
+                                                  int n_warps, int ring_slots) {
   RingLayout L;
   L.ring_slots = ring_slots;
   L.row_stride = (W * static_cast<int>(sizeof(T)) + 127) / 128 * 128;
-  L.w_slots = ((W + (pad_shift < 31 ? (W >> pad_shift) : 0) + 4) + 3) / 4 * 4;
-  L.tv_stride = (skipna ? 2 : 1) * L.w_slots;
+  L.strip_slots = strip_cols_max + (pad_shift < 31 ? (strip_cols_max >> pad_shift) : 0) + 1;
+  L.strip_bytes = (static_cast<size_t>(L.strip_slots) * (skipna ? 2 : 1) * sizeof(T) + 127) / 128 * 128;
   size_t off = static_cast<size_t>(ring_slots) * L.row_stride;
   L.off_bar = off;
-  off += static_cast<size_t>(2 * kRingMaxSlots) * sizeof(unsigned long long);
-  L.off_tv = off;
-  off += static_cast<size_t>(2) * L.tv_stride * sizeof(T);
-  L.off_cw = off;
-  off += (static_cast<size_t>(Kw) * Wo * sizeof(T) + 15) / 16 * 16;
-  L.off_cidx = off;
-  off += (static_cast<size_t>(Kw) * Wo * sizeof(int32_t) + 15) / 16 * 16;
-  L.off_ccnt = off;
-  off += (static_cast<size_t>(Wo) * sizeof(int32_t) + 15) / 16 * 16;
+  off += static_cast<size_t>(kRingMaxSlots) * sizeof(unsigned long long);
+  L.off_flags = off;  // [0] = rows landed, [1 + w] = rows released by consumer warp w
+  off += 128;
+  L.off_strip = off;
+  off += static_cast<size_t>(n_warps) * L.strip_bytes;
   L.total = off;
   return L;
 }
 
-// ------------------------------------------------------------------ mbarrier / TMA PTX
+// ------------------------------------------------------------------ mbarrier / TMA / flag PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -73,95 +76,188 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar_addr), "r"(parity)
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA, no tensor map needed).
-__device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes,
-                                             unsigned long long* bar) {
+__device__ __forceinline__ void tma_load_row(uint32_t dst_addr, const void* src, uint32_t bytes,
+                                             uint32_t bar_addr) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_addr),
+      "l"(src), "r"(bytes), "r"(bar_addr)
       : "memory");
 }
-__device__ __forceinline__ void consumer_barrier() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kRingConsumers) : "memory");
+__device__ __forceinline__ uint32_t ld_acquire_smem(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_smem(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-template <typename T, bool SKIPNA>
-__global__ void __launch_bounds__(kRingThreads, 1)
-conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
-                         long long xrs, long long ybs, Band<T> rows, Band<T> cols, RingDev ring, T thr,
-                         int ring_slots) {
+// {t, v} entry of the warp-private strip buffer.
+template <typename T, bool SKIPNA> struct TV;
+template <typename T> struct alignas(2 * sizeof(T)) TV<T, true> { T t, v; };
+template <typename T> struct TV<T, false> { T t; };
+
+// acc += w * x and vac += w, both skipped when x is NaN: bit-identical to the reference's
+// fillna(0) / notnull() contributions (w * 0 adds nothing).
+template <typename T>
+__device__ __forceinline__ void accum_valid(T& acc, T& vac, T w, T x) {
+  const bool ok = (x == x);
+  acc = fma(w, ok ? x : T(0), acc);
+  vac += ok ? w : T(0);
+}
+
+// Latitude contraction of the CNT taps of one output for one strip of source columns
+// [col0, col0 + ncols) (mod W), 16 bytes per lane per step.  CNT is a compile-time constant: the
+// CNT shared-memory loads issue back to back and the tap loop is branch-free.
+template <typename T, bool SKIPNA, int CNT>
+__device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row_stride, int ring_slots,
+                                            int newest, uint32_t back, const T* __restrict__ wk,
+                                            TV<T, SKIPNA>* s_tv, int W, int col0, int ncols, int pad_shift,
+                                            int lane) {
   constexpr int VEC = 16 / sizeof(T);
+  constexpr int N = CNT > 0 ? CNT : 1;
+  const unsigned char* rowp[N];
+  T w[N];
+  // weights of this output: one or more 16-byte loads from the output-major record
+  {
+    Pack<T, VEC> wv[(N + VEC - 1) / VEC];
+#pragma unroll
+    for (int i = 0; i < (CNT + VEC - 1) / VEC; ++i) wv[i] = reinterpret_cast<const Pack<T, VEC>*>(wk)[i];
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) w[i] = wv[i / VEC].v[i % VEC];
+  }
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    int slot = newest - static_cast<int>((back >> (4 * i)) & 15u);  // rows back from the newest landed row
+    if (slot < 0) slot += ring_slots;
+    rowp[i] = s_ring + slot * row_stride;
+  }
+  // valid mass of a column without NaNs: the taps' weights summed in tap order
+  T wsum = T(0);
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) wsum += w[i];
+
+  for (int q = lane * VEC; q < ncols; q += 32 * VEC) {
+    int j = col0 + q;
+    if (j >= W) j -= W;  // strips may wrap around the date line
+    Pack<T, VEC> val[N];
+#pragma unroll
+    for (int i = 0; i < CNT; ++i)
+      val[i] = *reinterpret_cast<const Pack<T, VEC>*>(rowp[i] + j * static_cast<int>(sizeof(T)));
+    // Fast path: contract as if nothing were missing.  The result is NaN iff some tap is NaN (or
+    // infinities cancel); only then redo the group with per-tap NaN handling.  For NaN-free groups
+    // this is bit-identical to the slow path (a valid tap adds w * x and w in the same order).
+    T acc[VEC], vac[VEC];
+    bool redo = false;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      acc[e] = T(0);
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) acc[e] = fma(w[i], val[i].v[e], acc[e]);
+      vac[e] = wsum;
+      if (SKIPNA) redo |= (acc[e] != acc[e]);
+    }
+    if (SKIPNA && redo) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { acc[e] = T(0); vac[e] = T(0); }
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) accum_valid(acc[e], vac[e], w[i], val[i].v[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int s = (q + e) + (pad_shift < 31 ? ((q + e) >> pad_shift) : 0);
+      if constexpr (SKIPNA) {
+        s_tv[s] = TV<T, true>{acc[e], vac[e]};
+      } else {
+        s_tv[s].t = acc[e];
+      }
+    }
+  }
+}
+
+template <typename T, bool SKIPNA, int KW, int MAXWARPS>
+__global__ void __launch_bounds__(MAXWARPS * 32, 1)
+conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
+                         long long xrs, long long ybs, Band<T> cols, RingDev ring, T thr, int ring_slots) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int W = cols.n_src, Wo = cols.n_out, Kw = cols.k_max, Ho = rows.n_out;
+  const int W = cols.n_src, Wo = cols.n_out;
   const int pad_shift = ring.pad_shift;
-  const RingLayout L = ring_layout<T>(W, Wo, Kw, pad_shift, SKIPNA, ring_slots);
-  unsigned char* s_ring = smem;
+  const int n_warps = ring.n_warps;  // consumer warps; then one producer warp and one sync warp
+  const RingLayout L = ring_layout<T>(W, pad_shift, SKIPNA, ring.strip_cols_max, n_warps, ring_slots);
   unsigned long long* s_full = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
-  unsigned long long* s_empty = s_full + kRingMaxSlots;
-  T* s_tv = reinterpret_cast<T*>(smem + L.off_tv);
-  T* s_cw = reinterpret_cast<T*>(smem + L.off_cw);
-  int32_t* s_cidx = reinterpret_cast<int32_t*>(smem + L.off_cidx);
-  int32_t* s_ccnt = reinterpret_cast<int32_t*>(smem + L.off_ccnt);
+  uint32_t* s_flags = reinterpret_cast<uint32_t*>(smem + L.off_flags);
 
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < ring_slots; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 1);
-    }
+    for (int s = 0; s < ring_slots; ++s) mbar_init(&s_full[s], 1);
     fence_mbar_init();
   }
-  // longitude band -> shared memory once per (persistent) CTA; indices pre-mapped to padded slots
-  for (int i = tid; i < Kw * Wo; i += kRingThreads) {
-    const int j = cols.idx[i];
-    s_cidx[i] = j + (pad_shift < 31 ? (j >> pad_shift) : 0);
-    s_cw[i] = cols.w[i];
-  }
-  for (int i = tid; i < Wo; i += kRingThreads) s_ccnt[i] = cols.cover[i] ? cols.cnt[i] : -1;
+  if (tid < 32) s_flags[tid] = 0;
   __syncthreads();
 
   const long long tasks = batch * ring.n_runs;
   const uint32_t row_bytes = static_cast<uint32_t>(W) * sizeof(T);
+  const uint32_t full0 = smem_u32(s_full), flags0 = smem_u32(s_flags), ring0 = smem_u32(smem);
 
-  // ================================================================ producer warp
-  if (tid >= kRingConsumers) {
-    if (tid == kRingConsumers) {
+  // ================================================================ producer: TMA row loads
+  if (warp == n_warps) {
+    if (lane == 0) {
+      uint32_t g = 0, freed = 0;  // rows issued / rows released by every consumer warp
       int slot = 0;
-      uint32_t parity = 1;  // waiting on the "previous" phase of a fresh barrier returns at once
       for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
         const int run = static_cast<int>(task % ring.n_runs);
         const T* xb = x + (task / ring.n_runs) * xbs;
         const int p1 = ring.run_sched[run + 1];
         for (int p = ring.run_sched[run]; p < p1; ++p) {
-          mbar_wait(&s_empty[slot], parity);
-          mbar_arrive_expect_tx(&s_full[slot], row_bytes);
-          tma_load_row(s_ring + static_cast<size_t>(slot) * L.row_stride,
-                       xb + static_cast<long long>(ring.sched_row[p]) * xrs, row_bytes, &s_full[slot]);
+          const long long off = static_cast<long long>(ring.sched_row[p]) * xrs;
+          while (static_cast<int>(g - freed) >= ring_slots) {  // ring full: wait for the slowest warp
+            uint32_t m = ld_acquire_smem(flags0 + 4);
+            for (int w = 1; w < n_warps; ++w) {
+              const uint32_t d = ld_acquire_smem(flags0 + 4 * (1 + w));
+              if (static_cast<int>(d - m) < 0) m = d;
+            }
+            freed = m;
+            if (static_cast<int>(g - freed) >= ring_slots) __nanosleep(64);
+          }
+          mbar_arrive_expect_tx(full0 + 8u * slot, row_bytes);
+          tma_load_row(ring0 + static_cast<uint32_t>(slot) * L.row_stride, xb + off, row_bytes,
+                       full0 + 8u * slot);
+          ++g;
+          if (++slot == ring_slots) slot = 0;
+        }
+      }
+    }
+    return;
+  }
+  // ================================================================ sync: relay TMA completion
+  if (warp > n_warps) {
+    if (warp == n_warps + 1 && lane == 0) {
+      uint32_t g = 0, parity = 0;
+      int slot = 0;
+      for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
+        const int run = static_cast<int>(task % ring.n_runs);
+        const int n = ring.run_sched[run + 1] - ring.run_sched[run];
+        for (int i = 0; i < n; ++i) {
+          while (!mbar_try_wait(full0 + 8u * slot, parity)) {
+          }
+          st_release_smem(flags0, ++g);  // rows [0, g) are in the ring and visible
           if (++slot == ring_slots) { slot = 0; parity ^= 1; }
         }
       }
@@ -171,126 +267,100 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
 
   // ================================================================ consumer warps
   const T nan = quiet_nan<T>();
-  uint32_t gbase = 0;                       // ring position of the current run's first row
-  uint32_t landed = 0, landed_slot = 0, landed_parity = 0;
-  uint32_t released = 0, released_slot = 0;
-  int buf = 0;
+  using Entry = TV<T, SKIPNA>;
+  Entry* s_tv = reinterpret_cast<Entry*>(smem + L.off_strip + static_cast<size_t>(warp) * L.strip_bytes);
+  const T* wrec = static_cast<const T*>(ring.wrec);
+  uint32_t gbase = 0;    // ring position of the current run's first row
+  uint32_t newest_g = 0; // ring position + 1 of the newest row needed so far
+  int newest = ring_slots - 1;
+
+  // The longitude taps of the output this lane produces stay in registers (reloaded only if a warp
+  // owns more than one strip).  Indices are mapped to padded slots of the strip buffer; taps beyond
+  // the output's own count get weight 0 on its first index, so the longitude pass is branch-free.
+  int cur = -1, l0 = 0, nl = 0, col0 = 0, ncols = 0, ccnt = -1;
+  T tw[KW];
+  int ci[KW];
+  auto load_strip = [&](int st) {
+    cur = st;
+    l0 = ring.strip_l0[st];
+    nl = ring.strip_l0[st + 1] - l0;
+    col0 = ring.strip_c0[st];
+    ncols = ring.strip_nc[st];
+    const int l = l0 + (lane < nl ? lane : 0);
+    const int n = cols.cnt[l];
+    ccnt = (lane < nl && cols.cover[l]) ? n : -1;
+#pragma unroll
+    for (int i = 0; i < KW; ++i) {
+      const bool live = i < n && i < cols.k_max;
+      int j = live ? cols.idx[i * Wo + l] : (n > 0 ? cols.idx[l] : col0);
+      j -= col0;
+      if (j < 0) j += W;
+      ci[i] = j + (pad_shift < 31 ? (j >> pad_shift) : 0);
+      tw[i] = live ? cols.w[i * Wo + l] : T(0);
+    }
+  };
+  if (warp < ring.n_strips) load_strip(warp);
 
   for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
     const int run = static_cast<int>(task % ring.n_runs);
     const long long b = task / ring.n_runs;
-    const int k1 = ring.run_first[run + 1];
-    for (int k = ring.run_first[run]; k < k1; ++k) {
-      const bool covered = rows.cover[k] != 0;
-      const int cnt = covered ? rows.cnt[k] : 0;
-      T* s_t = s_tv + buf * L.tv_stride;
-      T* s_v = s_t + L.w_slots;
+    const int k0 = ring.run_first[run], k1 = ring.run_first[run + 1];
+    int4 rec_n = ring.krec[k0];
+    for (int k = k0; k < k1; ++k) {
+      const int4 rec = rec_n;  // {need, release, kcnt (-1: latitude not covered), packed tap_back}
+      if (k + 1 < k1) rec_n = ring.krec[k + 1];  // prefetch: hides the global-load latency
+      const uint32_t need_g = gbase + static_cast<uint32_t>(rec.x);
+      const int cnt = rec.z > 0 ? rec.z : 0;
 
       // ---- wait until every row this output needs has landed in the ring
-      const uint32_t need_g = gbase + static_cast<uint32_t>(ring.need[k]);
-      while (landed < need_g) {
-        mbar_wait(&s_full[landed_slot], landed_parity);
-        ++landed;
-        if (++landed_slot == static_cast<uint32_t>(ring_slots)) { landed_slot = 0; landed_parity ^= 1; }
-      }
+      while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(32);
+      newest += static_cast<int>(need_g - newest_g);
+      newest_g = need_g;
+      if (newest >= ring_slots) newest -= ring_slots;
 
-      // ---- phase 1: latitude contraction out of the ring
-      for (int c0 = 0; c0 < cnt || c0 == 0; c0 += kTapChunk) {
-        const unsigned char* rowp[kTapChunk];
-        T w[kTapChunk];
-#pragma unroll
-        for (int i = 0; i < kTapChunk; ++i) {
-          if (c0 + i < cnt) {
-            const uint32_t pos = gbase + static_cast<uint32_t>(ring.tap_pos[(c0 + i) * Ho + k]);
-            rowp[i] = s_ring + static_cast<size_t>(pos % static_cast<uint32_t>(ring_slots)) * L.row_stride;
-            w[i] = rows.w[(c0 + i) * Ho + k];
-          }
-        }
-        for (int j = tid * VEC; j < W; j += kRingConsumers * VEC) {
-          T acc[VEC], vac[VEC];
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) { acc[e] = T(0); vac[e] = T(0); }
-          Pack<T, VEC> val[kTapChunk];
-#pragma unroll
-          for (int i = 0; i < kTapChunk; ++i) {
-            if (c0 + i < cnt) val[i] = *reinterpret_cast<const Pack<T, VEC>*>(rowp[i] + j * sizeof(T));
-          }
-#pragma unroll
-          for (int i = 0; i < kTapChunk; ++i) {
-            if (c0 + i < cnt) {
-#pragma unroll
-              for (int e = 0; e < VEC; ++e) {
-                const T xv = val[i].v[e];
-                if (SKIPNA) {
-                  const bool ok = (xv == xv);
-                  acc[e] = fma(w[i], ok ? xv : T(0), acc[e]);
-                  vac[e] += ok ? w[i] : T(0);
-                } else {
-                  acc[e] = fma(w[i], xv, acc[e]);
-                }
-              }
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            if (j + e < W) {
-              const int s = (j + e) + (pad_shift < 31 ? ((j + e) >> pad_shift) : 0);
-              if (c0 == 0) {
-                s_t[s] = acc[e];
-                if (SKIPNA) s_v[s] = vac[e];
-              } else {
-                s_t[s] += acc[e];
-                if (SKIPNA) s_v[s] += vac[e];
-              }
-            }
-          }
-        }
-      }
-      consumer_barrier();  // t / v complete, ring reads of this output complete
-
-      // ---- hand dead rows back to the producer
-      const uint32_t rel_g = gbase + static_cast<uint32_t>(ring.release[k]);
-      while (released < rel_g) {
-        if (tid == 0) mbar_arrive(&s_empty[released_slot]);
-        ++released;
-        if (++released_slot == static_cast<uint32_t>(ring_slots)) released_slot = 0;
-      }
-
-      // ---- phase 2: longitude contraction, normalise, mask, store
       T* yrow = y + b * ybs + static_cast<long long>(k) * Wo;
-      for (int l = tid; l < Wo; l += kRingConsumers) {
-        const int c = s_ccnt[l];
-        T out = nan;
-        if (covered && c >= 0) {
-          T so = T(0), sv = T(0);
-          for (int t0 = 0; t0 < c; t0 += 4) {
-            T tw[4], tt[4], tvv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (t0 + i < c) {
-                const int s = s_cidx[(t0 + i) * Wo + l];
-                tw[i] = s_cw[(t0 + i) * Wo + l];
-                tt[i] = s_t[s];
-                if (SKIPNA) tvv[i] = s_v[s];
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (t0 + i < c) {
-                so = fma(tw[i], tt[i], so);
-                if (SKIPNA) sv = fma(tw[i], tvv[i], sv);
-              }
-            }
-          }
-          if (SKIPNA) {
-            out = (sv >= thr) ? so / sv : nan;
-          } else {
-            out = so;
-          }
+      const T* wk = wrec + static_cast<long long>(k) * kRingMaxTaps;
+      for (int st = warp; st < ring.n_strips; st += n_warps) {
+        if (st != cur) load_strip(st);
+        __syncwarp();  // the previous longitude pass is done reading the strip buffer
+        // ---- phase 1: latitude contraction out of the ring
+#define RG_P1(C)                                                                                          \
+  case C:                                                                                                 \
+    ring_phase1<T, SKIPNA, C>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk,   \
+                              s_tv, W, col0, ncols, pad_shift, lane);                                     \
+    break;
+        switch (cnt) {
+          RG_P1(0) RG_P1(1) RG_P1(2) RG_P1(3) RG_P1(4) RG_P1(5) RG_P1(6) RG_P1(7)
+          default:
+            ring_phase1<T, SKIPNA, 8>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
+                                      wk, s_tv, W, col0, ncols, pad_shift, lane);
+            break;
         }
-        st_stream(yrow + l, out);
+#undef RG_P1
+        __syncwarp();
+        // rows that are dead after this output are no longer read once the LAST strip's latitude
+        // pass is done: publish this warp's progress so the producer can recycle them early
+        if (st + n_warps >= ring.n_strips && lane == 0)
+          st_release_smem(flags0 + 4u * (1 + warp), gbase + static_cast<uint32_t>(rec.y));
+        // ---- phase 2: longitude contraction, normalise, mask, store
+        if (lane < nl) {
+          T out = nan;
+          if (rec.z >= 0 && ccnt >= 0) {
+            Entry e[KW];
+#pragma unroll
+            for (int i = 0; i < KW; ++i) e[i] = s_tv[ci[i]];
+            T so = T(0), sv = T(0);
+#pragma unroll
+            for (int i = 0; i < KW; ++i) {
+              so = fma(tw[i], e[i].t, so);
+              if constexpr (SKIPNA) sv = fma(tw[i], e[i].v, sv);
+            }
+            if constexpr (SKIPNA) out = (sv >= thr) ? so / sv : nan;
+            else out = so;
+          }
+          st_stream(yrow + l0 + lane, out);
+        }
       }
-      buf ^= 1;  // double-buffered t / v: the next phase 1 may start while others finish phase 2
     }
     gbase += static_cast<uint32_t>(ring.run_sched[run + 1] - ring.run_sched[run]);
   }

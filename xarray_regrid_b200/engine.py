@@ -59,19 +59,23 @@ class DeviceBand:
 class DeviceRing:
     """A ``tables.RowRing`` uploaded to the GPU, plus the ``rg_row_ring_t`` that points at it."""
 
-    def __init__(self, ring: tables.RowRing, device: torch.device):
+    def __init__(self, ring: tables.RowRing, rows: tables.Band, dtype: torch.dtype, device: torch.device):
         self.host = ring
 
         def up(a):
             return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
 
-        self.sched_row, self.tap_pos = up(ring.sched_row), up(ring.tap_pos)
-        self.need, self.release = up(ring.need), up(ring.release)
+        np_dtype = np.float32 if dtype == torch.float32 else np.float64
+        self.sched_row, self.krec = up(ring.sched_row), up(ring.krec())
+        self.wrec = torch.from_numpy(np.ascontiguousarray(ring.wrec(rows, np_dtype))).to(device)
         self.run_first, self.run_sched = up(ring.run_first), up(ring.run_sched)
+        self.strip_l0, self.strip_c0, self.strip_nc = up(ring.strip_l0), up(ring.strip_c0), up(ring.strip_nc)
         self.c = rg_row_ring_t(
-            self.sched_row.data_ptr(), self.tap_pos.data_ptr(), self.need.data_ptr(),
-            self.release.data_ptr(), self.run_first.data_ptr(), self.run_sched.data_ptr(),
+            self.sched_row.data_ptr(), self.krec.data_ptr(), self.wrec.data_ptr(),
+            self.run_first.data_ptr(), self.run_sched.data_ptr(), self.strip_l0.data_ptr(),
+            self.strip_c0.data_ptr(), self.strip_nc.data_ptr(),
             ring.n_runs, int(ring.sched_row.size), ring.max_live, ring.pad_shift,
+            ring.n_strips, ring.strip_cols_max, ring.n_warps,
         )
 
     @property
@@ -145,17 +149,18 @@ class ConservativePlan:
         self.use_ring = True  # tests flip this to exercise the generic kernel
 
     # ------------------------------------------------------------------------------
-    def _ring(self, batch: int, n_cols: int):
+    def _ring(self, batch: int, n_cols: int, dtype: torch.dtype):
         """Row-ring schedule sized so that (slabs x runs) fills the SMs about twice over."""
         if not self.use_ring or self.pole_rows:
             return None
         sms = max(sm_count(), 1)
         n_runs = int(min(self.rows_band.n_out, max(1, -(-2 * sms // max(batch, 1)))))
-        key = (n_runs, n_cols)
+        vec = 2 if dtype == torch.float64 else 4
+        key = (n_runs, n_cols, vec)
         if key not in self._rings:
             cols = self.cols_band if self.cols_band is not None else tables.identity_band(n_cols)
-            host = tables.row_ring_schedule(self.rows_band, n_runs, cols)
-            self._rings[key] = None if host is None else DeviceRing(host, self.device)
+            host = tables.row_ring_schedule(self.rows_band, n_runs, cols, vec)
+            self._rings[key] = None if host is None else DeviceRing(host, self.rows_band, dtype, self.device)
         return self._rings[key]
 
     def _bands(self, dtype: torch.dtype, n_cols: int):
@@ -201,7 +206,7 @@ class ConservativePlan:
                   "rg_row_nanmean")
         fn = lib.rg_conservative_f64 if dtype == torch.float64 else lib.rg_conservative_f32
         thr = tables.valid_threshold(nan_threshold)
-        ring = self._ring(B, W)
+        ring = self._ring(B, W, dtype)
         check(
             fn(x3.data_ptr(), y.data_ptr(), B, x3.stride(0) if B > 1 else H * x3.stride(1),
                x3.stride(1), Ho * Wo, rows.ref, cols.ref, int(bool(skipna)), thr,
@@ -233,7 +238,7 @@ class ConservativePlan:
             if workspace is None or workspace.numel() * workspace.element_size() < need:
                 workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
             fn = lib.rg_conservative_host_f64 if dtype == torch.float64 else lib.rg_conservative_host_f32
-            ring = self._ring(min(chunk_batch, B), W)
+            ring = self._ring(min(chunk_batch, B), W, dtype)
             check(
                 fn(x3.data_ptr(), out_host.data_ptr(), B, chunk_batch, rows.ref, cols.ref,
                    int(bool(skipna)), tables.valid_threshold(nan_threshold), int(self.pole_rows),

@@ -282,20 +282,98 @@ class RowRing:
     (``rg_row_ring_t`` in include/regrid_b200.h)."""
 
     sched_row: np.ndarray  # int32 [n_sched]
-    tap_pos: np.ndarray  # int32 [k_max, n_out], relative to the run's first position
+    tap_back: np.ndarray  # int32 [k_max, n_out]: rows back from the newest landed row
+    kcnt: np.ndarray  # int32 [n_out]: taps per output, -1 = not covered
     need: np.ndarray  # int32 [n_out]
     release: np.ndarray  # int32 [n_out]
     run_first: np.ndarray  # int32 [n_runs + 1]
     run_sched: np.ndarray  # int32 [n_runs + 1]
     max_live: int
     pad_shift: int
+    strip_l0: np.ndarray = None  # int32 [n_strips + 1]
+    strip_c0: np.ndarray = None  # int32 [n_strips]
+    strip_nc: np.ndarray = None  # int32 [n_strips]
+    n_warps: int = 0
+
+    @property
+    def n_strips(self) -> int:
+        return int(self.strip_c0.size)
+
+    def krec(self) -> np.ndarray:
+        """int32 [n_out, 4] = {need, release, kcnt, 8 x 4-bit tap_back} (the kernel's 16-byte record)."""
+        packed = np.zeros(self.need.size, np.uint32)
+        for t in range(min(self.tap_back.shape[0], 8)):
+            packed |= (self.tap_back[t].astype(np.uint32) & 15) << np.uint32(4 * t)
+        return np.stack([self.need, self.release, self.kcnt, packed.view(np.int32)], axis=1).astype(np.int32)
+
+    def wrec(self, rows: "Band", dtype) -> np.ndarray:
+        """[n_out, 8] tap weights of the rows band, output-major, zero padded."""
+        out = np.zeros((rows.n_out, 8), dtype)
+        k = min(rows.k_max, 8)
+        live = np.arange(k)[:, None] < rows.cnt[None, :]
+        out[:, :k] = np.where(live, rows.w[:k], 0.0).T.astype(dtype)
+        return out
+
+    @property
+    def strip_cols_max(self) -> int:
+        return int(self.strip_nc.max())
 
     @property
     def n_runs(self) -> int:
         return int(self.run_first.size - 1)
 
 
-def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None) -> RowRing | None:
+def column_strips(cols: Band, vec: int, max_warps: int = 24):
+    """Cut the target columns into strips of <= 32 outputs for the consumer warps of the ring
+    kernel and find, per strip, the (circular) range of source columns that covers all its taps.
+
+    Returns ``(strip_l0, strip_c0, strip_nc, n_warps)``.  The warp count minimises a simple
+    instruction-count model of the kernel (per-warp fixed cost + 32-lane steps of the latitude
+    pass), which favours strips whose source range is just under a multiple of 32 lane steps.
+    """
+    n_out, n_src = cols.n_out, cols.n_src
+
+    def build(tps):
+        l0 = np.arange(0, n_out, tps)
+        l0 = np.append(l0, n_out)
+        c0s, ncs = [], []
+        for a, b in zip(l0[:-1], l0[1:]):
+            taps = [cols.idx[: cols.cnt[l], l] for l in range(a, b) if cols.cnt[l] > 0]
+            if not taps:
+                c0s.append(0)
+                ncs.append(vec)
+                continue
+            s = np.unique(np.concatenate(taps)).astype(np.int64)
+            gaps = np.diff(np.append(s, s[0] + n_src))  # circular gaps
+            g = int(np.argmax(gaps))
+            start, end = int(s[(g + 1) % s.size]), int(s[g])
+            length = (end - start) % n_src + 1
+            c0 = start - start % vec
+            length += start - c0
+            length = -(-length // vec) * vec
+            if length >= n_src:
+                c0, length = 0, n_src
+            c0s.append(c0)
+            ncs.append(length)
+        return l0.astype(np.int32), np.asarray(c0s, np.int32), np.asarray(ncs, np.int32)
+
+    best = None
+    for n_warps in range(1, max_warps + 1):
+        tps = min(32, -(-n_out // n_warps))
+        l0, c0, nc = build(tps)
+        steps = -(-(nc // vec) // 32)
+        per_strip = steps * 63 + 75
+        per_warp = np.zeros(n_warps)
+        for i, c in enumerate(per_strip):
+            per_warp[i % n_warps] += c
+        # total issue work (with a fixed per-warp cost) and the critical path of the busiest warp
+        cost = per_strip.sum() + 75 * min(n_warps, c0.size) + 2.0 * per_warp.max()
+        if best is None or cost < best[0] - 1e-9:
+            best = (cost, l0, c0, nc, min(n_warps, c0.size))
+    return best[1:]
+
+
+def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: int = 2) -> RowRing | None:
     """Schedule for streaming the source rows of ``rows`` through a shared-memory ring.
 
     Outputs are visited in order and split into ``n_runs`` contiguous runs.  Inside a run a
@@ -306,6 +384,8 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None) -> RowR
     n_out, k_max = rows.n_out, rows.k_max
     cnt = np.where(rows.cover > 0, rows.cnt, 0)
     if n_out == 0 or (rows.idx >= rows.n_src).any():
+        return None
+    if k_max > 8:
         return None
     n_runs = int(max(1, min(n_runs, n_out)))
     run_first = np.unique(np.round(np.linspace(0, n_out, n_runs + 1)).astype(np.int64))
@@ -349,7 +429,17 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None) -> RowR
         r = int(round(ratio))
         if r >= 2 and abs(ratio - r) < 0.26 and (r & (r - 1)) == 0:
             pad_shift = r.bit_length() - 1
-    return RowRing(
-        np.asarray(sched, np.int32), tap_pos, need, release,
+    live = np.arange(k_max)[:, None] < cnt[None, :]
+    tap_back = np.where(live, need[None, :] - 1 - tap_pos, 0).astype(np.int32)
+    kcnt = np.where(rows.cover > 0, rows.cnt, -1).astype(np.int32)
+    if max_live > 15:
+        return None
+    ring = RowRing(
+        np.asarray(sched, np.int32), tap_back, kcnt, need, release,
         run_first.astype(np.int32), np.asarray(run_sched, np.int32), int(max_live), pad_shift,
     )
+    if cols is not None:
+        if cols.n_src % vec != 0:
+            return None
+        ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = column_strips(cols, vec)
+    return ring
