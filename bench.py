@@ -288,7 +288,7 @@ def run_engine_arm(args) -> None:
     achieved = bytes_per_step / (avg_launch_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "kernel": "rg::conservative_kernel<double, skipna, vec2>",
+        "traffic": None, "kernel": "rg::conservative_ring_kernel<double, skipna=true, KW=5, 14 warps>",
         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_step,
         "launch_ms_avg": avg_launch_ms, "launch_ms_min": min(launch_ms),
     }

@@ -1,0 +1,40 @@
+"""The C-ABI library loads without a GPU and exports every function include/regrid_b200.h declares."""
+
+import ctypes
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "regrid_b200.h"
+LIB = ROOT / "xarray_regrid_b200" / "csrc" / "libregrid_b200.so"
+
+
+def declared_functions():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(rg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert LIB.exists(), "run `python -c 'import __graft_entry__ as g; g.build()'` first"
+    lib = ctypes.CDLL(str(LIB))
+    names = declared_functions()
+    assert len(names) >= 10
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert missing == []
+
+
+def test_python_binding_covers_the_header():
+    from xarray_regrid_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+    assert _lib.lib.rg_abi_version() == _lib.RG_ABI_VERSION
+    assert b"NULL" in _lib.lib.rg_error_string(-1)
+
+
+def test_argument_errors_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on the CPU box."""
+    from xarray_regrid_b200 import _lib
+
+    assert _lib.lib.rg_conservative_f64(None, None, 1, 1, 1, 1, None, None, 1, 0.5, None, None, None) == -1
+    assert _lib.lib.rg_conservative_host_workspace(0, 1, 1, 1, 1, 8) == 0
+    assert _lib.lib.rg_conservative_host_workspace(2, 721, 1440, 181, 360, 8) >= 3 * 2 * (721 * 1440 + 181 * 360) * 8

@@ -1,0 +1,45 @@
+"""The oracle is test infrastructure: nothing in the product package may import or execute it,
+and the product must fail loudly (not fall back) when the CUDA library is missing."""
+
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "xarray_regrid_b200"
+
+
+def test_product_never_imports_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|importlib\.import_module\(\s*['\"]oracle", re.M)
+    offenders = [str(p) for p in PKG.rglob("*.py") if pat.search(p.read_text())]
+    assert offenders == []
+    for p in list(PKG.rglob("*.cu")) + list(PKG.rglob("*.cuh")) + [ROOT / "include" / "regrid_b200.h"]:
+        assert "oracle" not in p.read_text().lower(), p
+
+
+def test_bench_uses_oracle_only_in_cpu_legs():
+    src = (ROOT / "bench.py").read_text()
+    engine_arm = src[src.index("def run_engine_arm"):src.index("def main")]
+    assert "from oracle" not in engine_arm and "import oracle" not in engine_arm
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """Import the package from a copy that has no built .so: must raise ImportError, not fall back."""
+    code = (
+        "import sys, importlib.util, pathlib\n"
+        f"src = pathlib.Path({str(PKG)!r})\n"
+        f"dst = pathlib.Path({str(tmp_path)!r}) / 'xarray_regrid_b200'\n"
+        "dst.mkdir()\n"
+        "[ (dst / p.name).write_text(p.read_text()) for p in src.glob('*.py') ]\n"
+        f"sys.path.insert(0, {str(tmp_path)!r})\n"
+        "try:\n"
+        "    import xarray_regrid_b200\n"
+        "except ImportError as e:\n"
+        "    assert 'no CPU fallback' in str(e), e\n"
+        "    print('OK')\n"
+        "else:\n"
+        "    raise SystemExit('import succeeded without the CUDA library')\n"
+    )
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=tmp_path)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr

@@ -1,0 +1,32 @@
+"""Multi-GPU partitioning: contiguous blocks of the flattened batch (time x level x member) per rank.
+
+Every 2-D slab is regridded independently with replicated KB-sized tables, so the data path needs no
+collective.  ``torch.distributed`` is only used by callers for barriers / timing
+reductions and, optionally, to gather results on one rank.
+"""
+
+from __future__ import annotations
+
+
+def shard_bounds(n_items: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Half-open range ``[start, stop)`` of ``n_items`` owned by ``rank``: contiguous, balanced to
+    within one item, earlier ranks take the remainder."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError(f"bad rank {rank} / world size {world_size}")
+    if n_items < 0:
+        raise ValueError("n_items must be non-negative")
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_items: int, world_size: int) -> list[int]:
+    return [b - a for a, b in (shard_bounds(n_items, world_size, r) for r in range(world_size))]
+
+
+def regrid_sharded(plan, x_full, rank: int, world_size: int, **kw):
+    """Apply ``plan`` to this rank's contiguous block of the leading (batch) dimension of ``x_full``
+    and return ``(start, stop, y_block)``.  ``x_full`` may be any indexable stack (a memory-mapped
+    array, a host tensor, ...); only the rank's block is touched."""
+    start, stop = shard_bounds(x_full.shape[0], world_size, rank)
+    return start, stop, plan(x_full[start:stop], **kw)
