@@ -217,7 +217,7 @@ def run_reference_arm(args) -> None:
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------- GPU arm
@@ -372,9 +372,28 @@ def run_engine_arm(args) -> None:
             "gpu_launches": args.steps,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr so that the
+    ONE JSON line is the only thing on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main() -> None:
@@ -393,6 +412,7 @@ def main() -> None:
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
 
     if args.impl == "reference":
+        _quiet_stdout()
         run_reference_arm(args)
         return
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
@@ -401,6 +421,7 @@ def main() -> None:
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29517",
                str(Path(__file__).resolve())] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    _quiet_stdout()
     run_engine_arm(args)
 
 

@@ -189,6 +189,61 @@ int rg_conservative_host_f32(const float* x_host, float* y_host, int64_t batch,
                              int32_t skipna, float valid_thr, int32_t pole_rows,
                              const rg_row_ring_t* ring, void* workspace, size_t workspace_bytes);
 
+/*
+ * Separable banded contraction y[b,k,l] = sum_t sum_c wr[t,k] * wc[c,l] * x[b, ri[t,k], ci[c,l]] with NaN
+ * propagating through every tap (weight 0 included) and y = NaN where !(cover_r[k] && cover_c[l]).
+ * Same kernels as rg_conservative_* with skipna = 0.  It replaces `data.interp(coords, method)`
+ * (methods/interp.py:43-46 -> scipy interp1d per axis) for
+ *   linear: 2-tap bands (tables.linear_band);
+ *   cubic : first the prefilter bands (A^-1 of the not-a-knot collocation system, source grid ->
+ *           formatted source grid), then the 4-tap B-spline evaluation bands (tables.cubic_bands);
+ *   nearest on floating-point data: 1-tap bands (integers: rg_nearest below).
+ */
+int rg_separable_f64(const double* x, double* y, int64_t batch,
+                     int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
+                     const rg_band_t* rows, const rg_band_t* cols, const double* pole,
+                     const rg_row_ring_t* ring, void* stream);
+int rg_separable_f32(const float* x, float* y, int64_t batch,
+                     int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
+                     const rg_band_t* rows, const rg_band_t* cols, const float* pole,
+                     const rg_row_ring_t* ring, void* stream);
+
+/* Element type codes for the type-generic entry points. */
+#define RG_U8 0
+#define RG_I8 1
+#define RG_I16 2
+#define RG_I32 3
+#define RG_I64 4
+#define RG_F32 5
+#define RG_F64 6
+
+/*
+ * Nearest-neighbour regrid as a pure index gather (bit-exact):
+ *   y[b,k,l] = (out_type) x[b, row_idx[k], col_idx[l]]   where row_ok[k] && col_ok[l], else `fill`.
+ * row_idx / col_idx are computed on the host with scipy's own expression
+ * (searchsorted(x[1:]/2 + x[:-1]/2, t, side="left"): ties go to the lower neighbour), *_ok marks
+ * targets inside [x[0], x[-1]].  out_type is in_type, or RG_F64 (the reference returns float64 with NaN
+ * for integer input: scipy/interpolate/_interpolate.py:336-338).  Replaces data.interp(method="nearest")
+ * (methods/interp.py:43-46).
+ */
+int rg_nearest(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t batch,
+               int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
+               int32_t Ho, int32_t Wo, const int32_t* row_idx, const uint8_t* row_ok,
+               const int32_t* col_idx, const uint8_t* col_ok, double fill, void* stream);
+
+/*
+ * The cubic spline's NaN rule (scipy interp1d: one NaN anywhere in the array makes the WHOLE result
+ * NaN, _interpolate.py:409-437): rg_nan_flag_* ORs 1 into *flag (device int32, zeroed by the caller)
+ * if any element of the [batch, H, W] stack is NaN; rg_poison_if_* overwrites y[0..n) with NaN when
+ * *flag != 0.  Both are stream-ordered; the flag never visits the host.
+ */
+int rg_nan_flag_f64(const double* x, int64_t batch, int32_t H, int32_t W, int64_t x_batch_stride,
+                    int64_t x_row_stride, int32_t* flag, void* stream);
+int rg_nan_flag_f32(const float* x, int64_t batch, int32_t H, int32_t W, int64_t x_batch_stride,
+                    int64_t x_row_stride, int32_t* flag, void* stream);
+int rg_poison_if_f64(double* y, int64_t n, const int32_t* flag, void* stream);
+int rg_poison_if_f32(float* y, int64_t n, const int32_t* flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

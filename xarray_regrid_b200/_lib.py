@@ -69,6 +69,13 @@ def _load():
         "rg_conservative_f32": (C.c_int, [p, p, i64, i64, i64, i64, band, band, i32, f32, p, ring, p]),
         "rg_row_nanmean_f64": (C.c_int, [p, p, i64, i32, i32, i64, i64, p]),
         "rg_row_nanmean_f32": (C.c_int, [p, p, i64, i32, i32, i64, i64, p]),
+        "rg_separable_f64": (C.c_int, [p, p, i64, i64, i64, i64, band, band, p, ring, p]),
+        "rg_separable_f32": (C.c_int, [p, p, i64, i64, i64, i64, band, band, p, ring, p]),
+        "rg_nearest": (C.c_int, [p, p, i32, i32, i64, i64, i64, i64, i32, i32, p, p, p, p, f64, p]),
+        "rg_nan_flag_f64": (C.c_int, [p, i64, i32, i32, i64, i64, p, p]),
+        "rg_nan_flag_f32": (C.c_int, [p, i64, i32, i32, i64, i64, p, p]),
+        "rg_poison_if_f64": (C.c_int, [p, i64, p, p]),
+        "rg_poison_if_f32": (C.c_int, [p, i64, p, p]),
         "rg_conservative_host_workspace": (sz, [i64, i32, i32, i32, i32, i32]),
         "rg_conservative_host_f64": (C.c_int, [p, p, i64, i64, band, band, i32, f64, i32, ring, p, sz]),
         "rg_conservative_host_f32": (C.c_int, [p, p, i64, i64, band, band, i32, f32, i32, ring, p, sz]),

@@ -416,6 +416,20 @@ int rg_row_nanmean_f32(const float* x, float* pole, int64_t batch, int32_t H, in
                                        static_cast<cudaStream_t>(stream));
 }
 
+int rg_separable_f64(const double* x, double* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
+                     const rg_band_t* rows, const rg_band_t* cols, const double* pole,
+                     const rg_row_ring_t* ring, void* stream) {
+  return rg::conservative_launch<double>(x, y, batch, xbs, xrs, ybs, rows, cols, 0, 0.0, pole, ring,
+                                         static_cast<cudaStream_t>(stream));
+}
+
+int rg_separable_f32(const float* x, float* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
+                     const rg_band_t* rows, const rg_band_t* cols, const float* pole,
+                     const rg_row_ring_t* ring, void* stream) {
+  return rg::conservative_launch<float>(x, y, batch, xbs, xrs, ybs, rows, cols, 0, 0.0f, pole, ring,
+                                        static_cast<cudaStream_t>(stream));
+}
+
 size_t rg_conservative_host_workspace(int64_t chunk_batch, int32_t H, int32_t W, int32_t Ho,
                                       int32_t Wo, int32_t elem_size) {
   if (chunk_batch <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || elem_size <= 0) return 0;

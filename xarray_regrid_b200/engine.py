@@ -115,40 +115,24 @@ def _as_batch(x: torch.Tensor, dtype: torch.dtype):
     return x3, lead
 
 
-class ConservativePlan:
-    """Device-resident tables for ``ds.regrid.conservative`` on a fixed pair of grids.
+class BandOp:
+    """Two per-axis bands resident on the device + the launch of the separable band kernels.
 
-    Mirrors what ``conservative_regrid_dataset`` prepares before ``apply_weights``
-    (methods/conservative.py:119-137) and what ``format_for_regrid`` (utils.py:243-286)
-    would do to the data, as index tables.  Build once, apply to any number of stacks.
+    ``run`` computes ``y[b,k,l] = sum_t sum_c wr[t,k] wc[c,l] x[b, ri[t,k], ci[c,l]]`` with the
+    conservative NaN bookkeeping (``skipna``) or plain NaN propagation; it is the common back end of the
+    conservative, linear and cubic regridders.
     """
 
-    def __init__(self, rows: AxisSpec, cols: AxisSpec | None, *, spherical_rows: bool | None = None,
-                 device=None):
+    def __init__(self, rows_band: tables.Band, cols_band: tables.Band | None, device):
         self.device = _require_cuda(device)
-        self.rows_spec, self.cols_spec = rows, cols
-        if rows.kind == "lon" or (cols is not None and cols.kind == "lat"):
-            raise ValueError("layout must be [..., lat, lon]: transpose the data first")
-        rows_axis = tables.format_lat_axis(rows.src) if rows.kind == "lat" else tables.plain_axis(rows.src)
-        if spherical_rows is None:
-            spherical_rows = rows.kind == "lat"
-        self.rows_band = tables.conservative_band(rows_axis, rows.tgt, spherical=spherical_rows)
-        if cols is None:
-            self.cols_band = None
-        else:
-            cols_axis = (
-                tables.format_lon_axis(cols.src, cols.tgt) if cols.kind == "lon"
-                else tables.plain_axis(cols.src)
-            )
-            self.cols_band = tables.conservative_band(cols_axis, cols.tgt, spherical=False)
-        self.pole_rows = bool(self.rows_band.meta.get("pole_rows")) and bool(
-            (self.rows_band.idx >= self.rows_band.n_src).any()
+        self.rows_band, self.cols_band = rows_band, cols_band
+        self.pole_rows = bool(rows_band.meta.get("pole_rows")) and bool(
+            (rows_band.idx >= rows_band.n_src).any()
         )
         self._dev: dict = {}
         self._rings: dict = {}
         self.use_ring = True  # tests flip this to exercise the generic kernel
 
-    # ------------------------------------------------------------------------------
     def _ring(self, batch: int, n_cols: int, dtype: torch.dtype):
         """Row-ring schedule sized so that (slabs x runs) fills the SMs about twice over."""
         if not self.use_ring or self.pole_rows:
@@ -174,17 +158,10 @@ class ConservativePlan:
     def _out_hw(self, n_cols: int):
         return (self.rows_band.n_out, n_cols if self.cols_band is None else self.cols_band.n_out)
 
-    def __call__(self, x: torch.Tensor, skipna: bool = True, nan_threshold: float = 1.0,
-                 out: torch.Tensor | None = None) -> torch.Tensor:
-        if not 0.0 <= nan_threshold <= 1.0:
-            raise ValueError("nan_threshold must be between [0, 1]]")
-        if not x.is_cuda:
-            raise ValueError("device path takes CUDA tensors; use apply_host() for host buffers")
-        dtype = _result_dtype(x)
-        x3, lead = _as_batch(x, dtype)
+    def run(self, x3: torch.Tensor, skipna: bool, thr: float, out: torch.Tensor | None = None) -> torch.Tensor:
+        """``x3``: CUDA ``[B, H, W]`` float32/float64 with unit column stride -> ``[B, Ho, Wo]``."""
+        dtype = x3.dtype
         B, H, W = x3.shape
-        if B == 0:
-            return torch.empty(tuple(x.shape[:-2]) + self._out_hw(W), dtype=dtype, device=x.device)
         rows, cols = self._bands(dtype, W)
         if H != rows.host.n_src or W != cols.host.n_src:
             raise ValueError(
@@ -197,6 +174,8 @@ class ConservativePlan:
             y = out.view(B, Ho, Wo)
             if y.dtype != dtype or not y.is_contiguous():
                 raise ValueError("out must be a contiguous tensor of the result dtype")
+        if B == 0:
+            return y
         stream = _stream_ptr(x3.device)
         pole = None
         if self.pole_rows:
@@ -205,7 +184,6 @@ class ConservativePlan:
             check(fn(x3.data_ptr(), pole.data_ptr(), B, H, W, x3.stride(0), x3.stride(1), stream),
                   "rg_row_nanmean")
         fn = lib.rg_conservative_f64 if dtype == torch.float64 else lib.rg_conservative_f32
-        thr = tables.valid_threshold(nan_threshold)
         ring = self._ring(B, W, dtype)
         check(
             fn(x3.data_ptr(), y.data_ptr(), B, x3.stride(0) if B > 1 else H * x3.stride(1),
@@ -213,7 +191,47 @@ class ConservativePlan:
                None if pole is None else pole.data_ptr(), None if ring is None else ring.ref, stream),
             "rg_conservative",
         )
-        return y.view(tuple(lead) + (Ho, Wo))
+        return y
+
+
+def _axis(spec: AxisSpec | None, is_rows: bool):
+    if spec is None:
+        return None
+    if is_rows and spec.kind == "lon" or (not is_rows and spec.kind == "lat"):
+        raise ValueError("layout must be [..., lat, lon]: transpose the data first")
+    if spec.kind == "lat":
+        return tables.format_lat_axis(spec.src)
+    if spec.kind == "lon":
+        return tables.format_lon_axis(spec.src, spec.tgt)
+    return tables.plain_axis(spec.src)
+
+
+class ConservativePlan(BandOp):
+    """Device-resident tables for ``ds.regrid.conservative`` on a fixed pair of grids.
+
+    Mirrors what ``conservative_regrid_dataset`` prepares before ``apply_weights``
+    (methods/conservative.py:119-137) and what ``format_for_regrid`` (utils.py:243-286)
+    would do to the data, as index tables.  Build once, apply to any number of stacks.
+    """
+
+    def __init__(self, rows: AxisSpec, cols: AxisSpec | None, *, spherical_rows: bool | None = None,
+                 device=None):
+        self.rows_spec, self.cols_spec = rows, cols
+        if spherical_rows is None:
+            spherical_rows = rows.kind == "lat"
+        rows_band = tables.conservative_band(_axis(rows, True), rows.tgt, spherical=spherical_rows)
+        cols_band = None if cols is None else tables.conservative_band(_axis(cols, False), cols.tgt)
+        super().__init__(rows_band, cols_band, device)
+
+    def __call__(self, x: torch.Tensor, skipna: bool = True, nan_threshold: float = 1.0,
+                 out: torch.Tensor | None = None) -> torch.Tensor:
+        if not 0.0 <= nan_threshold <= 1.0:
+            raise ValueError("nan_threshold must be between [0, 1]]")
+        if not x.is_cuda:
+            raise ValueError("device path takes CUDA tensors; use apply_host() for host buffers")
+        x3, lead = _as_batch(x, _result_dtype(x))
+        y = self.run(x3, skipna, tables.valid_threshold(nan_threshold), out)
+        return y.view(tuple(lead) + tuple(y.shape[-2:]))
 
     # ------------------------------------------------------------------------------
     def apply_host(self, x_host: torch.Tensor, skipna: bool = True, nan_threshold: float = 1.0,
@@ -247,6 +265,131 @@ class ConservativePlan:
                 "rg_conservative_host",
             )
         return out_host.view(tuple(lead) + (Ho, Wo))
+
+
+_TYPE_CODE = {
+    torch.uint8: 0, torch.int8: 1, torch.int16: 2, torch.int32: 3, torch.int64: 4,
+    torch.float32: 5, torch.float64: 6,
+}
+
+
+class InterpPlan:
+    """Device-resident tables for ``ds.regrid.linear / nearest / cubic`` on a fixed pair of grids.
+
+    The reference does ``data.interp(coords, method)`` (methods/interp.py:43-46), which xarray turns into
+    one scipy ``interp1d`` per axis.  Here every method is a separable band:
+
+    * linear  -> 2-tap bands, one fused pass;
+    * nearest -> an index gather (integers stay exact; no arithmetic);
+    * cubic   -> prefilter bands on the source grid (A^-1 of the not-a-knot collocation system), then 4-tap
+      B-spline bands onto the target grid, plus scipy's "any NaN -> everything NaN" rule.
+
+    Result dtype follows the reference by default (``out_dtype="reference"``): float64 for linear / cubic
+    and for nearest on integer data, the input's dtype for nearest on floats.  ``out_dtype="same"`` keeps
+    float32 for linear and the integer dtype for nearest (``fill`` marks cells outside the source range).
+    """
+
+    def __init__(self, rows: AxisSpec, cols: AxisSpec | None, method: str, *, device=None):
+        if method not in ("linear", "nearest", "cubic"):
+            raise ValueError(f"unknown interpolation method {method!r}")
+        self.method = method
+        self.device = _require_cuda(device)
+        rows_axis, cols_axis = _axis(rows, True), _axis(cols, False)
+        self.rows_axis, self.cols_axis = rows_axis, cols_axis
+        if method == "linear":
+            self.op = BandOp(tables.linear_band(rows_axis, rows.tgt),
+                             None if cols is None else tables.linear_band(cols_axis, cols.tgt), self.device)
+        elif method == "nearest":
+            self.op = BandOp(tables.nearest_band(rows_axis, rows.tgt),
+                             None if cols is None else tables.nearest_band(cols_axis, cols.tgt), self.device)
+            self._gather: dict = {}
+        else:
+            r_pre, r_ev = tables.cubic_bands(rows_axis, rows.tgt)
+            c_pre, c_ev = (None, None) if cols is None else tables.cubic_bands(cols_axis, cols.tgt)
+            self.pre = BandOp(r_pre, c_pre, self.device)
+            self.op = BandOp(r_ev, c_ev, self.device)
+            self.chunk = 2048  # slabs per pass: bounds the fp64 coefficient buffer
+            # xr.interp interpolates one axis after the other; a row target outside the source range
+            # leaves NaN rows, and scipy's cubic turns ANY NaN in its input into an all-NaN result, so
+            # the second (column) pass blanks everything.  (The reference's axis order is the iteration
+            # order of a Python set, interp.py:39; the engine and the oracle fix it to rows, then cols.)
+            self.all_nan = cols is not None and not bool(r_ev.cover.all())
+
+    # nearest on integers (or out_dtype="same"): pure gather kernel
+    def _gather_tables(self, n_cols: int):
+        if n_cols not in self._gather:
+            def up(a, dt):
+                return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)
+            rb = self.op.rows_band
+            cb = self.op.cols_band if self.op.cols_band is not None else tables.identity_band(n_cols)
+            self._gather[n_cols] = (up(rb.idx[0], np.int32), up(rb.cover, np.uint8),
+                                    up(cb.idx[0], np.int32), up(cb.cover, np.uint8), rb.n_src, cb.n_src)
+        return self._gather[n_cols]
+
+    def _nearest_gather(self, x: torch.Tensor, out_dtype: torch.dtype, fill: float) -> torch.Tensor:
+        lead = x.shape[:-2]
+        x3 = x.reshape((-1,) + tuple(x.shape[-2:]))
+        if x3.stride(2) != 1:
+            x3 = x3.contiguous()
+        B, H, W = x3.shape
+        ri, rok, ci, cok, n_rows, n_cols = self._gather_tables(W)
+        if H != n_rows or W != n_cols:
+            raise ValueError(f"data is [{H}, {W}] but the plan was built for [{n_rows}, {n_cols}]")
+        Ho, Wo = ri.numel(), ci.numel()
+        y = torch.empty((B, Ho, Wo), dtype=out_dtype, device=x3.device)
+        if B:
+            check(
+                lib.rg_nearest(x3.data_ptr(), y.data_ptr(), _TYPE_CODE[x3.dtype], _TYPE_CODE[out_dtype], B,
+                               x3.stride(0) if B > 1 else H * x3.stride(1), x3.stride(1), Ho * Wo, Ho, Wo,
+                               ri.data_ptr(), rok.data_ptr(), ci.data_ptr(), cok.data_ptr(), float(fill),
+                               _stream_ptr(x3.device)),
+                "rg_nearest",
+            )
+        return y.view(tuple(lead) + (Ho, Wo))
+
+    def __call__(self, x: torch.Tensor, out_dtype: str = "reference", fill: float = float("nan")) -> torch.Tensor:
+        if not x.is_cuda:
+            raise ValueError("InterpPlan takes CUDA tensors")
+        if out_dtype not in ("reference", "same"):
+            raise ValueError("out_dtype must be 'reference' or 'same'")
+        is_float = x.dtype in (torch.float32, torch.float64)
+        if self.method == "nearest":
+            if x.dtype not in _TYPE_CODE:
+                x = x.to(torch.float32 if x.dtype in (torch.float16, torch.bfloat16) else torch.int32)
+                is_float = x.dtype == torch.float32
+            if self.op.pole_rows:  # a synthetic pole row can be the nearest neighbour: needs the mean
+                x3, lead = _as_batch(x, x.dtype if is_float else torch.float64)
+                y = self.op.run(x3, False, 0.0)
+                return y.view(tuple(lead) + tuple(y.shape[-2:]))
+            target = x.dtype if (is_float or out_dtype == "same") else torch.float64
+            return self._nearest_gather(x, target, fill)
+
+        work = torch.float64
+        if self.method == "linear" and out_dtype == "same" and x.dtype in (torch.float32, torch.float16, torch.bfloat16):
+            work = torch.float32
+        x3, lead = _as_batch(x, work)
+        if self.method == "linear":
+            y = self.op.run(x3, False, 0.0)
+            return y.view(tuple(lead) + tuple(y.shape[-2:]))
+
+        # cubic: NaN flag -> prefilter (source grid) -> evaluate (target grid) -> poison
+        B, H, W = x3.shape
+        Ho, Wo = self.op._out_hw(self.pre._out_hw(W)[1])
+        if self.all_nan:
+            return torch.full(tuple(lead) + (Ho, Wo), float("nan"), dtype=work, device=x3.device)
+        y = torch.empty((B, Ho, Wo), dtype=work, device=x3.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=x3.device)
+        stream = _stream_ptr(x3.device)
+        if B:
+            check(lib.rg_nan_flag_f64(x3.data_ptr(), B, H, W, x3.stride(0) if B > 1 else H * x3.stride(1),
+                                      x3.stride(1), flag.data_ptr(), stream), "rg_nan_flag")
+        for s0 in range(0, B, self.chunk):
+            xs = x3[s0:s0 + self.chunk]
+            coeff = self.pre.run(xs, False, 0.0)
+            self.op.run(coeff, False, 0.0, out=y[s0:s0 + self.chunk])
+        if B:
+            check(lib.rg_poison_if_f64(y.data_ptr(), y.numel(), flag.data_ptr(), stream), "rg_poison_if")
+        return y.view(tuple(lead) + (Ho, Wo))
 
 
 def sm_count() -> int:

@@ -443,3 +443,105 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
             return None
         ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = column_strips(cols, vec)
     return ring
+
+
+# ------------------------------------------------------------ interpolation bands (xr.interp)
+def _restore_not_needed(n_out):
+    return None
+
+
+def linear_band(axis: FormattedAxis, tgt) -> Band:
+    """2-tap band equal to scipy ``interp1d(kind="linear")`` as xarray calls it
+    (scipy/interpolate/_interpolate.py ``_call_linear``; reference methods/interp.py:43-46).
+
+    ``m = searchsorted(x, t).clip(1, n-1)``; weights ``(t - x_lo)/(x_hi - x_lo)`` and
+    ``(x_hi - t)/(x_hi - x_lo)``; targets outside ``[x[0], x[-1]]`` are NaN.  Both taps are ALWAYS
+    kept (even at weight 0) because the reference's ``w_hi*y_hi + w_lo*y_lo`` lets a NaN tap poison the
+    result at weight 0.  Targets keep their own order (no sort needed for interpolation).
+    """
+    x = np.asarray(axis.values, dtype=np.float64)
+    t = np.asarray(tgt)
+    n = x.size
+    if n < 2:
+        raise ValueError("x and y arrays must have at least 2 entries")
+    m = np.searchsorted(x, t).clip(1, n - 1).astype(int)
+    lo, hi = m - 1, m
+    x_lo, x_hi = x[lo], x[hi]
+    w_hi = (t - x_lo) / (x_hi - x_lo)
+    w_lo = (x_hi - t) / (x_hi - x_lo)
+    cover = ~((t < x[0]) | (t > x[-1]))
+    idx = np.stack([axis.source[lo], axis.source[hi]]).astype(np.int32)
+    w = np.stack([w_lo, w_hi]).astype(np.float64)
+    return Band(idx, w, np.full(t.size, 2, np.int32), cover.astype(np.uint8), axis.n_src, None,
+                {"pole_rows": axis.has_pole_rows, "method": "linear"})
+
+
+def nearest_index(axis: FormattedAxis, tgt):
+    """Source index and in-range mask of scipy ``interp1d(kind="nearest")``
+    (``_interpolate.py`` ``_call_nearest``): ``searchsorted(x[1:]/2 + x[:-1]/2, t, side="left")``,
+    i.e. exact midpoints go to the LOWER neighbour; outside ``[x[0], x[-1]]`` -> NaN."""
+    x = np.asarray(axis.values)
+    t = np.asarray(tgt)
+    if x.size < 1:
+        raise ValueError("x and y arrays must have at least 1 entries")
+    x_bds = x / 2.0
+    x_bds = x_bds[1:] + x_bds[:-1]
+    i = np.searchsorted(x_bds, t, side="left").clip(0, x.size - 1).astype(np.intp)
+    cover = ~((t < x[0]) | (t > x[-1]))
+    return axis.source[i].astype(np.int32), cover.astype(np.uint8)
+
+
+def nearest_band(axis: FormattedAxis, tgt) -> Band:
+    idx, cover = nearest_index(axis, tgt)
+    return Band(idx[None, :], np.ones((1, idx.size)), np.ones(idx.size, np.int32), cover, axis.n_src,
+                None, {"pole_rows": axis.has_pole_rows, "method": "nearest"})
+
+
+def cubic_bands(axis: FormattedAxis, tgt, rel_cut: float = 1e-18):
+    """Prefilter + evaluation bands equal to scipy ``interp1d(kind="cubic")`` =
+    ``make_interp_spline(x, y, k=3)`` (global not-a-knot spline) followed by B-spline evaluation.
+
+    Both steps are linear in ``y``: ``c = A^-1 y`` (A = collocation matrix incl. the not-a-knot rows) and
+    ``out = E c`` (E = 4 non-zero B-spline basis values per target).  ``A^-1`` is computed with scipy's
+    own routine applied to the identity and cut where its entries fall below ``rel_cut`` of the row
+    maximum (they decay by ~0.27 per node, so ~ +-31 taps survive at 1e-18 -- far below fp64 rounding).
+
+    Returns ``(prefilter, evaluate)``: ``prefilter`` maps the ORIGINAL source axis to the formatted axis
+    (n_fmt outputs), ``evaluate`` maps the formatted axis to the targets.
+    """
+    from scipy.interpolate import BSpline, make_interp_spline
+
+    x = np.asarray(axis.values, dtype=np.float64)
+    t = np.asarray(tgt, dtype=np.float64)
+    n = x.size
+    if n < 4:
+        raise ValueError("x and y arrays must have at least 4 entries")
+    spl = make_interp_spline(x, np.eye(n), k=3, check_finite=False)
+    minv = np.asarray(spl.c)  # [n coefficients, n data points]
+    keep = np.abs(minv) >= rel_cut * np.abs(minv).max(axis=1, keepdims=True)
+    cnt = keep.sum(axis=1).astype(np.int32)
+    k_max = int(cnt.max())
+    order = np.argsort(~keep, axis=1, kind="stable")[:, :k_max]  # kept columns first, ascending
+    w = np.take_along_axis(minv, order, axis=1)
+    dead = np.arange(k_max)[None, :] >= cnt[:, None]
+    w = np.where(dead, 0.0, w)
+    src = axis.source[np.where(dead, order[:, :1], order)]
+    pre = Band(np.ascontiguousarray(src.T.astype(np.int32)), np.ascontiguousarray(w.T),
+               cnt, np.ones(n, np.uint8), axis.n_src, None,
+               {"pole_rows": axis.has_pole_rows, "method": "cubic-prefilter"})
+
+    cover = ~((t < x[0]) | (t > x[-1]))
+    tc = np.clip(t, x[0], x[-1])
+    dm = BSpline.design_matrix(tc, spl.t, 3).tocsr()
+    e_idx = np.zeros((4, t.size), np.int32)
+    e_w = np.zeros((4, t.size))
+    for o in range(t.size):
+        a, b = dm.indptr[o], dm.indptr[o + 1]
+        cols, vals = dm.indices[a:b], dm.data[a:b]
+        k = cols.size
+        e_idx[:k, o] = cols
+        e_w[:k, o] = vals
+        e_idx[k:, o] = cols[0]
+    ev = Band(e_idx, e_w, np.full(t.size, 4, np.int32), cover.astype(np.uint8), n, None,
+              {"pole_rows": False, "method": "cubic-evaluate"})
+    return pre, ev
