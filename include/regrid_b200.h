@@ -244,6 +244,73 @@ int rg_nan_flag_f32(const float* x, int64_t batch, int32_t H, int32_t W, int64_t
 int rg_poison_if_f64(double* y, int64_t n, const int32_t* flag, void* stream);
 int rg_poison_if_f32(float* y, int64_t n, const int32_t* flag, void* stream);
 
+/*
+ * Per-axis bin table of the group-by regridders.  Bin membership is decided on the host with the
+ * reference's expressions (methods/_shared.py:12-18: closed-left bins on
+ * `append(t, t[-1] + step) - step / 2`; _shared.py:92-108 trimming), on the source axis sorted ascending
+ * and, for longitude, shifted / wrap-padded by format_for_regrid(stats=True) (utils.py:258-261, 341-390).
+ * A bin is therefore a contiguous range of "formatted positions":
+ *   start[o], count[o]   the positions of target o (bins are visited in ascending order of o)
+ *   cover[o]             target centre inside the (trimmed) source range (_shared.py:56-59), else fill
+ *   out_index[o]         index of target o in the output (the target's own order: reindex_like)
+ *   source index of position p = (src_offset + src_step * p) mod n_src,  src_step = +1 or -1
+ */
+typedef struct rg_bins {
+  const int32_t* start;     /* device, [n_out] */
+  const int32_t* count;     /* device, [n_out] */
+  const uint8_t* cover;     /* device, [n_out] */
+  const int32_t* out_index; /* device, [n_out] */
+  int32_t n_out;
+  int32_t n_src;
+  int32_t src_offset;
+  int32_t src_step;
+} rg_bins_t;
+
+/*
+ * most_common / least_common: for every target cell count the occurrences of each label of `values`
+ * among the source cells of its bin and return the label with the largest (anti_mode: smallest) count.
+ * Labels that do not occur count as -1 (the reference passes fill_value=-1 to flox), ties go to the
+ * label that comes first in `values`, labels not listed in `values` are ignored; cells that are not
+ * covered get `fill`.  Replaces the flox count + idxmax/idxmin of methods/flox_reduce.py:174-183 and
+ * the masking of methods/_shared.py:41-73.
+ *   values         device [n_values], element type in_type, in the caller's order
+ *   dense != 0     values == 0..n_values-1: a label is its own index (values_sorted / value_rank unused)
+ *   values_sorted  device [n_values] ascending, value_rank[i] = position of values_sorted[i] in `values`
+ *   cols_per_chunk target columns staged per CTA; tile_elems >= rows-per-bin * source columns of any chunk
+ *   in_type        RG_U8 / RG_I8 / RG_I16 / RG_I32 / RG_I64; out_type = in_type or RG_F64 (NaN fill)
+ */
+int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t batch,
+            int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
+            const rg_bins_t* rows, const rg_bins_t* cols, int32_t cols_per_chunk, int32_t tile_elems,
+            const void* values_sorted, const int32_t* value_rank, const void* values, int32_t n_values,
+            int32_t dense, int32_t anti_mode, double fill, void* stream);
+
+/* Statistic codes of rg_stat_*. */
+#define RG_STAT_SUM 0
+#define RG_STAT_MEAN 1
+#define RG_STAT_VAR 2
+#define RG_STAT_STD 3
+#define RG_STAT_MIN 4
+#define RG_STAT_MAX 5
+#define RG_STAT_MEDIAN 6
+
+/*
+ * Zonal statistic per target cell over the source cells of its bin: sum, mean, var / std (population,
+ * ddof = 0, two passes), min, max, median.  skipna == 0: a NaN in the bin makes the result NaN;
+ * skipna != 0: NaNs are ignored (an all-NaN bin gives NaN, 0 for sum).  Cells that are not covered get
+ * `fill`.  Replaces flox.xarray.xarray_reduce(data, *coords, func=method, expected_groups=bounds,
+ * skipna=..., fill_value=...) of methods/flox_reduce.py:89-96.  sort_cap (median only) >= next power
+ * of two of the largest bin population.
+ */
+int rg_stat_f64(const double* x, double* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
+                int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
+                int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
+                double fill, void* stream);
+int rg_stat_f32(const float* x, float* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
+                int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
+                int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
+                double fill, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

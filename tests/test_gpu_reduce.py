@@ -1,0 +1,185 @@
+"""Parity of most_common / least_common / stat (CUDA, through the C ABI) against the oracle and the
+reference's known answers (tests/test_reduce.py).  Bit-exact for the label modes and min / max;
+1e-12 (fp64) / 1e-5 (fp32) relative for the floating-point statistics."""
+
+import warnings
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import reduce as orr  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xarray_regrid_b200 import engine
+
+    return engine
+
+
+LC = np.array(
+    [
+        [2, 2, 2, 2, 0, 0, 0, 0, 0, 0, 0],
+        [2, 2, 0, 2, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [3, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1],
+        [3, 3, 3, 3, 0, 0, 0, 0, 1, 1, 1],
+        [3, 3, 0, 3, 0, 0, 0, 0, 1, 1, 1],
+    ]
+)
+C11 = np.linspace(0, 40, num=11)
+T6 = np.arange(0.0, 41.0, 8.0)
+LABELS = np.array([0, 1, 2, 3])
+
+
+def _plan(engine, r_src, c_src, r_tgt, c_tgt, kinds=("other", "other")):
+    return engine.ReducePlan(engine.AxisSpec(r_src, r_tgt, kinds[0]), engine.AxisSpec(c_src, c_tgt, kinds[1]))
+
+
+def test_reference_known_answer_most_common(engine):
+    """reference tests/test_reduce.py:87-110 (ties -> label 0, uint8 preserved) through the CUDA path."""
+    expected = np.array(
+        [[2, 2, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0],
+         [0, 0, 0, 0, 0, 0], [3, 3, 0, 0, 0, 1]], dtype="uint8")
+    plan = _plan(engine, C11, C11, T6, T6)
+    y = plan.mode(torch.from_numpy(LC.astype("uint8")).cuda(), LABELS)
+    assert y.dtype == torch.uint8
+    np.testing.assert_array_equal(y.cpu().numpy(), expected)
+    yl = plan.mode(torch.from_numpy(LC.astype("uint8")).cuda(), LABELS, anti_mode=True)
+    np.testing.assert_array_equal(
+        yl.cpu().numpy(), orr.mode(LC.astype("uint8"), [C11, C11], [T6, T6], [0, 1], LABELS, anti_mode=True))
+
+
+def test_reference_known_answer_oversized_target(engine):
+    """reference tests/test_reduce.py:121-153: NaN ring, float result, warning."""
+    t8 = np.arange(-8.0, 49.0, 8.0)
+    plan = _plan(engine, C11, C11, t8, t8)
+    with pytest.warns(UserWarning, match="fill_value"):
+        y = plan.mode(torch.from_numpy(LC).cuda(), LABELS)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = orr.mode(LC, [C11, C11], [t8, t8], [0, 1], LABELS)
+    assert y.dtype == torch.float64 and np.isnan(want[0]).all()
+    np.testing.assert_array_equal(y.cpu().numpy(), want)
+    y = plan.mode(torch.from_numpy(LC).cuda(), LABELS, fill_value=-9)
+    assert y.dtype == torch.int64 and (y[0] == -9).all()
+
+
+@pytest.mark.parametrize("method,expected", [
+    ("min", [[2.0, 2.0, 0, 0, 0, 0], [0] * 6, [0] * 6, [0] * 6, [0] * 6, [3.0, 0, 0, 0, 0, 1.0]]),
+    ("var", [[0, 0, 1.0, 0, 0, 0], [1.0, 0.75, 0.75, 0, 0, 0], [0] * 6, [0] * 6,
+             [2.25, 0, 0, 0, 0, 0.25], [0, 1.6875, 2.25, 0, 0.25, 0]]),
+])
+def test_reference_known_answer_stats(engine, method, expected):
+    """reference tests/test_reduce.py:202-235 (min; population variance) and :238-260 (unsorted source)."""
+    plan = _plan(engine, C11, C11, T6, T6)
+    y = plan.stat(torch.from_numpy(LC.astype(float)).cuda(), method)
+    np.testing.assert_array_equal(y.cpu().numpy(), np.array(expected, dtype=float))
+    order = np.argsort(np.array([1, 3, 7, 0, 2, 8, 9, -1, 5, 11, 12]), kind="stable")
+    plan = _plan(engine, C11, C11[order], T6, T6)
+    y = plan.stat(torch.from_numpy(LC.astype(float)[:, order].copy()).cuda(), method)
+    np.testing.assert_array_equal(y.cpu().numpy(), np.array(expected, dtype=float))
+
+
+def _landcover(rng, shape, n_classes, block):
+    coarse = rng.integers(0, n_classes, size=(shape[0] // block + 1, shape[1] // block + 1))
+    x = np.kron(coarse, np.ones((block, block), dtype=np.int64))[: shape[0], : shape[1]]
+    noise = rng.random(shape) < 0.05
+    x[noise] = rng.integers(0, n_classes, size=int(noise.sum()))
+    return x
+
+
+@pytest.mark.parametrize("aligned", [True, False])
+def test_c5_most_common_uint8_32_classes(engine, aligned):
+    """BASELINE config 5 shape at 1/10 scale in longitude: 0.01 deg uint8 land cover, 32 classes -> 0.25 deg.
+    aligned=True: cell-aligned target (25 x 25 cells per bin); False: pole-centred target whose bin edges
+    coincide with source centres (membership decided by fp64 rounding -> host arithmetic must match)."""
+    rng = np.random.default_rng(13)
+    lat = np.round(np.arange(-9.995, 10, 0.01), 3)
+    lon = np.round(np.arange(0.005, 360, 0.01), 3)[:3600]
+    if aligned:
+        tlat, tlon = np.arange(-9.875, 10, 0.25), np.arange(0.125, 36, 0.25)
+    else:
+        tlat, tlon = np.arange(-10.0, 10.01, 0.25), np.arange(0.0, 36.01, 0.25)
+    x = _landcover(rng, (lat.size, lon.size), 32, 64).astype(np.uint8)
+    plan = _plan(engine, lat, lon, tlat, tlon, ("lat", "lon"))
+    values = np.arange(32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        y = plan.mode(torch.from_numpy(x).cuda(), values)
+        want = orr.regrid_latlon(x, lat, lon, tlat, tlon, "most_common", values=values)
+    np.testing.assert_array_equal(y.cpu().numpy(), want)
+    assert y.dtype == (torch.uint8 if aligned else torch.float64)
+
+
+def test_mode_sparse_labels_batch_and_ignored_values(engine):
+    """Non-dense `values` in a non-sorted order (ties go to the first listed), labels not listed are
+    ignored, leading batch dims, int32 data, reversed target."""
+    rng = np.random.default_rng(14)
+    lat, lon = np.arange(0.5, 40, 1.0), np.arange(0.5, 60, 1.0)
+    tlat, tlon = np.arange(2.0, 40, 4.0), np.arange(2.5, 60, 5.0)[::-1].copy()
+    labels = np.array([40, 10, 30, 20])
+    x = rng.choice(np.array([10, 20, 30, 40, 99]), size=(2, 3, lat.size, lon.size)).astype(np.int32)
+    plan = _plan(engine, lat, lon, tlat, tlon)
+    for anti in (False, True):
+        y = plan.mode(torch.from_numpy(x).cuda(), labels, anti_mode=anti)
+        want = orr.mode(x, [lat, lon], [tlat, tlon], [-2, -1], labels, anti_mode=anti)
+        assert y.shape == (2, 3, tlat.size, tlon.size)
+        np.testing.assert_array_equal(y.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+@pytest.mark.parametrize("skipna", [False, True])
+def test_stats_all_methods(engine, dtype, rtol, skipna):
+    """Every statistic on a float field with 2 % NaN (SURVEY 8d, config 5's stat variant, scaled)."""
+    rng = np.random.default_rng(17)
+    lat, lon = np.round(np.arange(-4.995, 5, 0.01), 3), np.round(np.arange(0.005, 20, 0.01), 3)
+    tlat, tlon = np.arange(-4.875, 5, 0.25), np.arange(0.125, 20, 0.25)
+    x = rng.normal(size=(2, lat.size, lon.size)).astype(dtype)
+    x[rng.random(x.shape) < 0.02] = np.nan
+    x[0, :30, :30] = np.nan  # a few all-NaN cells
+    plan = _plan(engine, lat, lon, tlat, tlon, ("lat", "lon"))
+    xt = torch.from_numpy(x).cuda()
+    for method in ["sum", "mean", "var", "std", "min", "max", "median"]:
+        y = plan.stat(xt, method, skipna=skipna).cpu().numpy()
+        want = orr.regrid_latlon(x, lat, lon, tlat, tlon, "stat", method=method, skipna=skipna)
+        assert y.dtype == dtype and want.dtype == dtype
+        np.testing.assert_array_equal(np.isnan(y), np.isnan(want), err_msg=method)
+        if method in ("min", "max", "median"):
+            np.testing.assert_array_equal(y, want, err_msg=method)
+        else:
+            np.testing.assert_allclose(y, want, rtol=rtol, atol=rtol * 10, err_msg=method)
+
+
+def test_stat_global_wrap_and_uncovered(engine):
+    """Global 1 deg cell-centred source -> 2 deg pole-centred target: longitude wrap padding is applied
+    (stats=True skips the pole rows, tests/test_format.py:182-218) and edge bins are half populated."""
+    rng = np.random.default_rng(18)
+    lat, lon = np.arange(-89.5, 90, 1.0), np.arange(0.5, 360, 1.0)
+    tlat, tlon = np.arange(-90.0, 91, 2.0), np.arange(0.0, 361, 2.0)
+    x = rng.random((3, lat.size, lon.size))
+    plan = _plan(engine, lat, lon, tlat, tlon, ("lat", "lon"))
+    for method in ("mean", "max", "sum"):
+        y = plan.stat(torch.from_numpy(x).cuda(), method).cpu().numpy()
+        want = orr.regrid_latlon(x, lat, lon, tlat, tlon, "stat", method=method)
+        np.testing.assert_array_equal(np.isnan(y), np.isnan(want))
+        np.testing.assert_allclose(y, want, rtol=1e-12)
+
+
+def test_errors(engine):
+    plan = _plan(engine, C11, C11, T6, T6)
+    with pytest.raises(ValueError):
+        plan.stat(torch.zeros((11, 11), device="cuda"), "mode")  # flox_reduce.py:70-73
+    with pytest.raises(ValueError):
+        plan.mode(torch.zeros((11, 11), device="cuda"), LABELS)  # flox_reduce.py:156-162

@@ -51,6 +51,19 @@ class rg_row_ring_t(C.Structure):  # noqa: N801 - mirrors the C name
     ]
 
 
+class rg_bins_t(C.Structure):  # noqa: N801 - mirrors the C name
+    _fields_ = [
+        ("start", C.c_void_p),
+        ("count", C.c_void_p),
+        ("cover", C.c_void_p),
+        ("out_index", C.c_void_p),
+        ("n_out", C.c_int32),
+        ("n_src", C.c_int32),
+        ("src_offset", C.c_int32),
+        ("src_step", C.c_int32),
+    ]
+
+
 def _load():
     if not LIB_PATH.exists():
         raise ImportError(
@@ -61,6 +74,7 @@ def _load():
     p, i32, i64, f32, f64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
     band = C.POINTER(rg_band_t)
     ring = C.POINTER(rg_row_ring_t)
+    bins = C.POINTER(rg_bins_t)
     sig = {
         "rg_abi_version": (C.c_int, []),
         "rg_error_string": (C.c_char_p, [C.c_int]),
@@ -76,6 +90,10 @@ def _load():
         "rg_nan_flag_f32": (C.c_int, [p, i64, i32, i32, i64, i64, p, p]),
         "rg_poison_if_f64": (C.c_int, [p, i64, p, p]),
         "rg_poison_if_f32": (C.c_int, [p, i64, p, p]),
+        "rg_mode": (C.c_int, [p, p, i32, i32, i64, i64, i64, i64, bins, bins, i32, i32, p, p, p, i32, i32, i32,
+                              f64, p]),
+        "rg_stat_f64": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, f64, p]),
+        "rg_stat_f32": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, f64, p]),
         "rg_conservative_host_workspace": (sz, [i64, i32, i32, i32, i32, i32]),
         "rg_conservative_host_f64": (C.c_int, [p, p, i64, i64, band, band, i32, f64, i32, ring, p, sz]),
         "rg_conservative_host_f32": (C.c_int, [p, p, i64, i64, band, band, i32, f32, i32, ring, p, sz]),

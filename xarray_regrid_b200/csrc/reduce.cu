@@ -1,0 +1,417 @@
+// Group-by regridders for sm_100a: most_common / least_common (label mode) and zonal statistics
+// (sum, mean, var, std, min, max, median) per target cell.
+//
+// Replaces flox.xarray.xarray_reduce(... expected_groups=<closed-left bins> ...) as called from
+// src/xarray_regrid/methods/flox_reduce.py:89-96 (statistics) and :174-183 (count per label, then
+// idxmax / idxmin).  Bin membership is decided on the HOST with the reference's own expressions
+// (np.digitize on `append(t, t[-1]+step) - step/2`, _shared.py:12-18), so a target cell is simply a
+// contiguous range of (sorted) source rows x a contiguous range of (sorted, possibly wrapped) source
+// columns -- the kernels never compare coordinates.
+//
+// One CTA stages the tile [rows of target row k] x [columns of a chunk of target cells] in shared
+// memory with coalesced loads, then one warp per target cell
+//   mode:   maps each element to its dense label index, finds equal labels inside the warp with
+//           match.any (no atomics: one elected lane per distinct label adds the popcount to a warp-
+//           private counter array), then arg-max / arg-min with ties to the first label;
+//   stats:  shuffle reductions (two-pass variance, exactly like np.var), bitonic sort for the median.
+//
+// Roofline: HBM.  Algorithmic bytes = source cells * sizeof(T) + target cells * sizeof(Tout).
+
+#include "common.cuh"
+
+namespace rg {
+
+struct Bins {
+  const int32_t* __restrict__ start;  // [n_out] first formatted source position of the bin
+  const int32_t* __restrict__ count;  // [n_out] number of positions
+  const uint8_t* __restrict__ cover;  // [n_out]
+  const int32_t* __restrict__ out_index;  // [n_out] where the bin goes in the output
+  int n_out, n_src, src_offset, src_step;  // source index = (offset + step * position) mod n_src
+};
+
+inline int make_bins(const rg_bins_t* b, Bins* out) {
+  if (!b || !b->start || !b->count || !b->cover || !b->out_index) return RG_ERR_NULL;
+  if (b->n_out <= 0 || b->n_src <= 0 || (b->src_step != 1 && b->src_step != -1)) return RG_ERR_SHAPE;
+  *out = Bins{b->start, b->count, b->cover, b->out_index, b->n_out, b->n_src, b->src_offset, b->src_step};
+  return RG_OK;
+}
+
+__device__ __forceinline__ int src_index(const Bins& a, int pos) {
+  int i = a.src_offset + a.src_step * pos;
+  i %= a.n_src;
+  return i < 0 ? i + a.n_src : i;
+}
+
+constexpr int kRedThreads = 256;
+constexpr int kRedWarps = kRedThreads / 32;
+
+enum { OP_SUM = 0, OP_MEAN = 1, OP_VAR = 2, OP_STD = 3, OP_MIN = 4, OP_MAX = 5, OP_MEDIAN = 6 };
+
+// ------------------------------------------------------------------ tile staging (all ops)
+// tile[r * ncol + c] = x[b, src_row(r0 + r), src_col(p0 + c)]
+template <typename T>
+__device__ __forceinline__ void load_tile(T* tile, const T* __restrict__ xb, long long xrs, const Bins& rows,
+                                          const Bins& cols, int r0, int nr, int p0, int ncol) {
+  for (int r = threadIdx.x >> 5; r < nr; r += kRedWarps) {
+    const T* row = xb + static_cast<long long>(src_index(rows, r0 + r)) * xrs;
+    T* trow = tile + r * ncol;
+    for (int c = threadIdx.x & 31; c < ncol; c += 32) trow[c] = __ldg(row + src_index(cols, p0 + c));
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------- mode
+// label -> dense index in `values`: identity with bound (dense 0..n-1 labels), else binary search.
+template <typename T>
+__device__ __forceinline__ int label_index(T v, const T* __restrict__ values, int n_values, int dense) {
+  if (dense) return (v >= T(0) && static_cast<long long>(v) < n_values) ? static_cast<int>(v) : -1;
+  int lo = 0, hi = n_values - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const T m = values[mid];
+    if (m == v) return mid;
+    if (m < v) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kRedThreads)
+mode_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long batch, long long xbs, long long xrs,
+            long long ybs, Bins rows, Bins cols, int cols_per_chunk, int n_chunks,
+            const Tin* __restrict__ values_sorted, const int32_t* __restrict__ value_rank,
+            const Tin* __restrict__ values, int n_values, int dense, int anti, Tout fill, int tile_elems) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Tin* tile = reinterpret_cast<Tin*>(smem);
+  int32_t* counts = reinterpret_cast<int32_t*>(smem + (static_cast<size_t>(tile_elems) * sizeof(Tin) + 15) / 16 * 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int32_t* cnt = counts + warp * n_values;
+  const long long tasks = batch * rows.n_out * n_chunks;
+  const int Wo = cols.n_out;
+
+  for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int chunk = static_cast<int>(task % n_chunks);
+    const int k = static_cast<int>((task / n_chunks) % rows.n_out);
+    const long long b = task / (static_cast<long long>(n_chunks) * rows.n_out);
+    const int l0 = chunk * cols_per_chunk;
+    const int l1 = min(l0 + cols_per_chunk, Wo);
+    Tout* yrow = y + b * ybs + static_cast<long long>(rows.out_index[k]) * Wo;
+    const bool row_ok = rows.cover[k] != 0;
+    const int r0 = rows.start[k], nr = row_ok ? rows.count[k] : 0;
+    const int p0 = cols.start[l0];
+    const int ncol = cols.start[l1 - 1] + cols.count[l1 - 1] - p0;
+    const bool fits = static_cast<long long>(nr) * ncol <= tile_elems;  // host contract; never overrun
+    if (fits && nr > 0 && ncol > 0) load_tile(tile, x + b * xbs, xrs, rows, cols, r0, nr, p0, ncol);
+    __syncthreads();
+
+    for (int l = l0 + warp; l < l1; l += kRedWarps) {
+      Tout out = fill;
+      if (fits && row_ok && cols.cover[l]) {
+        for (int i = lane; i < n_values; i += 32) cnt[i] = 0;
+        __syncwarp();
+        const int c0 = cols.start[l] - p0, nc = cols.count[l];
+        for (int r = 0; r < nr; ++r) {
+          const Tin* trow = tile + r * ncol + c0;
+          for (int cb = 0; cb < nc; cb += 32) {
+            const int c = cb + lane;
+            int d = -1;
+            if (c < nc) {
+              d = label_index(trow[c], values_sorted, n_values, dense);
+              if (d >= 0 && !dense) d = value_rank[d];  // position in the caller's `values` order
+            }
+            const unsigned active = __ballot_sync(0xffffffffu, d >= 0);
+            if (d >= 0) {
+              const unsigned same = __match_any_sync(active, d);
+              if ((__ffs(same) - 1) == lane) cnt[d] += __popc(same);  // one elected lane per label
+            }
+            __syncwarp();
+          }
+        }
+        // arg-max (arg-min) over labels; empty labels count as -1 (flox fill_value=-1), ties -> first
+        int best_i = 0x7fffffff;
+        long long best_key = anti ? 0x7fffffffffffffffLL : -0x7fffffffffffffffLL;
+        for (int i = lane; i < n_values; i += 32) {
+          const int cval = cnt[i] > 0 ? cnt[i] : -1;
+          const bool better = anti ? (cval < best_key) : (cval > best_key);
+          if (better) { best_key = cval; best_i = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const long long ok = __shfl_xor_sync(0xffffffffu, best_key, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+          const bool better = anti ? (ok < best_key) : (ok > best_key);
+          if (better || (ok == best_key && oi < best_i)) { best_key = ok; best_i = oi; }
+        }
+        out = static_cast<Tout>(values[best_i]);
+        __syncwarp();
+      }
+      if (lane == 0) yrow[cols.out_index[l]] = out;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ stats
+template <typename T>
+__device__ __forceinline__ void bitonic_sort_warp(T* a, int n_pow2, int lane) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n_pow2; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const T x0 = a[i], x1 = a[ixj];
+          const bool up = (i & k) == 0;
+          if ((x0 > x1) == up) { a[i] = x1; a[ixj] = x0; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads)
+stat_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
+            long long ybs, Bins rows, Bins cols, int cols_per_chunk, int n_chunks, int op, int skipna,
+            T fill, int tile_elems, int sort_cap) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  T* tile = reinterpret_cast<T*>(smem);
+  T* scratch = tile + (tile_elems + 3) / 4 * 4;  // [kRedWarps * sort_cap], median only
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tasks = batch * rows.n_out * n_chunks;
+  const int Wo = cols.n_out;
+  const T nan = quiet_nan<T>();
+
+  for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int chunk = static_cast<int>(task % n_chunks);
+    const int k = static_cast<int>((task / n_chunks) % rows.n_out);
+    const long long b = task / (static_cast<long long>(n_chunks) * rows.n_out);
+    const int l0 = chunk * cols_per_chunk;
+    const int l1 = min(l0 + cols_per_chunk, Wo);
+    T* yrow = y + b * ybs + static_cast<long long>(rows.out_index[k]) * Wo;
+    const bool row_ok = rows.cover[k] != 0;
+    const int r0 = rows.start[k], nr = row_ok ? rows.count[k] : 0;
+    const int p0 = cols.start[l0];
+    const int ncol = cols.start[l1 - 1] + cols.count[l1 - 1] - p0;
+    const bool fits = static_cast<long long>(nr) * ncol <= tile_elems;  // host contract; never overrun
+    if (fits && nr > 0 && ncol > 0) load_tile(tile, x + b * xbs, xrs, rows, cols, r0, nr, p0, ncol);
+    __syncthreads();
+
+    for (int l = l0 + warp; l < l1; l += kRedWarps) {
+      T out = fill;
+      if (fits && row_ok && cols.cover[l]) {
+        const int c0 = cols.start[l] - p0, nc = cols.count[l];
+        // pass 1: count, NaN count, sum, min, max
+        double sum = 0.0;
+        int n = 0, n_nan = 0;
+        T vmin = CUDART_INF, vmax = -CUDART_INF;
+        for (int r = 0; r < nr; ++r) {
+          const T* trow = tile + r * ncol + c0;
+          for (int c = lane; c < nc; c += 32) {
+            const T v = trow[c];
+            if (v == v) {
+              sum += static_cast<double>(v);
+              ++n;
+              vmin = v < vmin ? v : vmin;
+              vmax = v > vmax ? v : vmax;
+            } else {
+              ++n_nan;
+            }
+          }
+        }
+        sum = warp_sum(sum);
+        n = warp_sum(n);
+        n_nan = warp_sum(n_nan);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const T a = __shfl_xor_sync(0xffffffffu, vmin, o), c = __shfl_xor_sync(0xffffffffu, vmax, o);
+          vmin = a < vmin ? a : vmin;
+          vmax = c > vmax ? c : vmax;
+        }
+        const bool poisoned = !skipna && n_nan > 0;
+        if (poisoned) {
+          out = nan;
+        } else if (n == 0) {
+          out = (op == OP_SUM) ? T(0) : nan;
+        } else if (op == OP_SUM) {
+          out = static_cast<T>(sum);
+        } else if (op == OP_MEAN) {
+          out = static_cast<T>(sum / n);
+        } else if (op == OP_MIN) {
+          out = vmin;
+        } else if (op == OP_MAX) {
+          out = vmax;
+        } else if (op == OP_VAR || op == OP_STD) {
+          const double mean = sum / n;  // two passes, like np.var (ddof = 0)
+          double m2 = 0.0;
+          for (int r = 0; r < nr; ++r) {
+            const T* trow = tile + r * ncol + c0;
+            for (int c = lane; c < nc; c += 32) {
+              const T v = trow[c];
+              if (v == v) { const double d = static_cast<double>(v) - mean; m2 += d * d; }
+            }
+          }
+          m2 = warp_sum(m2) / n;
+          out = static_cast<T>(op == OP_STD ? sqrt(m2) : m2);
+        } else {  // OP_MEDIAN: gather the valid values, sort, average the two middle ones
+          T* s = scratch + warp * sort_cap;
+          int n_pow2 = 1;
+          while (n_pow2 < n) n_pow2 <<= 1;
+          // stable compaction is not needed for a median: lanes claim slots with a warp prefix sum
+          int base = 0;
+          for (int r = 0; r < nr; ++r) {
+            const T* trow = tile + r * ncol + c0;
+            for (int cb = 0; cb < nc; cb += 32) {
+              const int c = cb + lane;
+              const T v = c < nc ? trow[c] : nan;
+              const bool ok = (v == v);
+              const unsigned m = __ballot_sync(0xffffffffu, ok);
+              if (ok) s[base + __popc(m & ((1u << lane) - 1u))] = v;
+              base += __popc(m);
+            }
+          }
+          for (int i = n + lane; i < n_pow2; i += 32) s[i] = CUDART_INF;
+          __syncwarp();
+          bitonic_sort_warp(s, n_pow2, lane);
+          const double lo = static_cast<double>(s[(n - 1) >> 1]), hi = static_cast<double>(s[n >> 1]);
+          out = static_cast<T>((lo + hi) / 2);
+          __syncwarp();
+        }
+      }
+      if (lane == 0) yrow[cols.out_index[l]] = out;
+    }
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------- launchers
+struct ChunkPlan {
+  int cols_per_chunk, n_chunks, tile_elems;
+};
+
+template <typename Tin, typename Tout>
+int mode_launch(const void* x, void* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
+                const rg_bins_t* rows_c, const rg_bins_t* cols_c, int32_t cols_per_chunk, int32_t tile_elems,
+                const void* values_sorted, const int32_t* value_rank, const void* values, int32_t n_values,
+                int32_t dense, int32_t anti, double fill, cudaStream_t stream) {
+  Bins rows, cols;
+  int rc = make_bins(rows_c, &rows);
+  if (rc != RG_OK) return rc;
+  rc = make_bins(cols_c, &cols);
+  if (rc != RG_OK) return rc;
+  DeviceInfo dev;
+  rc = device_info(&dev);
+  if (rc != RG_OK) return rc;
+  const size_t smem = (static_cast<size_t>(tile_elems) * sizeof(Tin) + 15) / 16 * 16 +
+                      static_cast<size_t>(kRedWarps) * n_values * sizeof(int32_t);
+  if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_SMEM;
+  auto kern = mode_kernel<Tin, Tout>;
+  if (smem > 48 * 1024)
+    RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int n_chunks = (cols.n_out + cols_per_chunk - 1) / cols_per_chunk;
+  const long long tasks = static_cast<long long>(batch) * rows.n_out * n_chunks;
+  int per_sm = 0;
+  RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRedThreads, smem));
+  if (per_sm < 1) return RG_ERR_SMEM;
+  long long grid = static_cast<long long>(dev.sm_count) * per_sm * 4;
+  if (grid > tasks) grid = tasks;
+  kern<<<static_cast<unsigned>(grid), kRedThreads, smem, stream>>>(
+      static_cast<const Tin*>(x), static_cast<Tout*>(y), batch, xbs, xrs, ybs, rows, cols, cols_per_chunk,
+      n_chunks, static_cast<const Tin*>(values_sorted), value_rank, static_cast<const Tin*>(values), n_values,
+      dense, anti, static_cast<Tout>(fill), tile_elems);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T>
+int stat_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
+                const rg_bins_t* rows_c, const rg_bins_t* cols_c, int32_t cols_per_chunk, int32_t tile_elems,
+                int32_t op, int32_t skipna, int32_t sort_cap, double fill, cudaStream_t stream) {
+  if (!x || !y) return RG_ERR_NULL;
+  if (op < OP_SUM || op > OP_MEDIAN || cols_per_chunk <= 0 || tile_elems <= 0) return RG_ERR_SHAPE;
+  Bins rows, cols;
+  int rc = make_bins(rows_c, &rows);
+  if (rc != RG_OK) return rc;
+  rc = make_bins(cols_c, &cols);
+  if (rc != RG_OK) return rc;
+  if (batch <= 0) return batch == 0 ? RG_OK : RG_ERR_SHAPE;
+  DeviceInfo dev;
+  rc = device_info(&dev);
+  if (rc != RG_OK) return rc;
+  const size_t smem = (static_cast<size_t>((tile_elems + 3) / 4 * 4) +
+                       (op == OP_MEDIAN ? static_cast<size_t>(kRedWarps) * sort_cap : 0)) * sizeof(T);
+  if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_SMEM;
+  auto kern = stat_kernel<T>;
+  if (smem > 48 * 1024)
+    RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int n_chunks = (cols.n_out + cols_per_chunk - 1) / cols_per_chunk;
+  const long long tasks = static_cast<long long>(batch) * rows.n_out * n_chunks;
+  int per_sm = 0;
+  RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRedThreads, smem));
+  if (per_sm < 1) return RG_ERR_SMEM;
+  long long grid = static_cast<long long>(dev.sm_count) * per_sm * 4;
+  if (grid > tasks) grid = tasks;
+  kern<<<static_cast<unsigned>(grid), kRedThreads, smem, stream>>>(x, y, batch, xbs, xrs, ybs, rows, cols,
+                                                                  cols_per_chunk, n_chunks, op, skipna,
+                                                                  static_cast<T>(fill), tile_elems, sort_cap);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace rg
+
+extern "C" {
+
+int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t batch,
+            int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride, const rg_bins_t* rows,
+            const rg_bins_t* cols, int32_t cols_per_chunk, int32_t tile_elems, const void* values_sorted,
+            const int32_t* value_rank, const void* values, int32_t n_values, int32_t dense,
+            int32_t anti_mode, double fill, void* stream) {
+  if (!x || !y || !values || (!dense && (!values_sorted || !value_rank))) return RG_ERR_NULL;
+  if (n_values <= 0 || cols_per_chunk <= 0 || tile_elems <= 0 || batch < 0) return RG_ERR_SHAPE;
+  if (batch == 0) return RG_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define RG_MODE(CODE, TIN)                                                                                  \
+  if (in_type == CODE) {                                                                                    \
+    if (out_type == CODE)                                                                                   \
+      return rg::mode_launch<TIN, TIN>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows,     \
+                                       cols, cols_per_chunk, tile_elems, values_sorted, value_rank, values, \
+                                       n_values, dense, anti_mode, fill, s);                                \
+    if (out_type == RG_F64)                                                                                 \
+      return rg::mode_launch<TIN, double>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows,  \
+                                          cols, cols_per_chunk, tile_elems, values_sorted, value_rank,      \
+                                          values, n_values, dense, anti_mode, fill, s);                     \
+    return RG_ERR_UNSUPPORTED;                                                                              \
+  }
+  RG_MODE(RG_U8, uint8_t)
+  RG_MODE(RG_I8, int8_t)
+  RG_MODE(RG_I16, int16_t)
+  RG_MODE(RG_I32, int32_t)
+  RG_MODE(RG_I64, long long)
+#undef RG_MODE
+  return RG_ERR_UNSUPPORTED;
+}
+
+int rg_stat_f64(const double* x, double* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
+                int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
+                int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
+                double fill, void* stream) {
+  return rg::stat_launch<double>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows, cols,
+                                 cols_per_chunk, tile_elems, op, skipna, sort_cap, fill,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int rg_stat_f32(const float* x, float* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
+                int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
+                int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
+                double fill, void* stream) {
+  return rg::stat_launch<float>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows, cols,
+                                cols_per_chunk, tile_elems, op, skipna, sort_cap, fill,
+                                static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

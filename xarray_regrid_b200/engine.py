@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib, tables
-from ._lib import check, lib, rg_band_t, rg_row_ring_t
+from ._lib import check, lib, rg_band_t, rg_bins_t, rg_row_ring_t
 
 
 def _require_cuda(device=None) -> torch.device:
@@ -389,6 +389,148 @@ class InterpPlan:
             self.op.run(coeff, False, 0.0, out=y[s0:s0 + self.chunk])
         if B:
             check(lib.rg_poison_if_f64(y.data_ptr(), y.numel(), flag.data_ptr(), stream), "rg_poison_if")
+        return y.view(tuple(lead) + (Ho, Wo))
+
+
+class DeviceBins:
+    """A ``tables.Bins`` uploaded to the GPU, plus the ``rg_bins_t`` that points at it."""
+
+    def __init__(self, bins: tables.Bins, device: torch.device):
+        self.host = bins
+
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)
+
+        self.start, self.count = up(bins.start, np.int32), up(bins.count, np.int32)
+        self.cover, self.out_index = up(bins.cover, np.uint8), up(bins.out_index, np.int32)
+        self.gather = None if bins.gather is None else up(bins.gather, np.int64)
+        self.c = rg_bins_t(self.start.data_ptr(), self.count.data_ptr(), self.cover.data_ptr(),
+                           self.out_index.data_ptr(), bins.n_out, bins.n_src, bins.src_offset, bins.src_step)
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+
+_STAT_CODE = {"sum": 0, "mean": 1, "var": 2, "std": 3, "min": 4, "max": 5, "median": 6}
+VALID_STAT_METHODS = ["sum", "mean", "var", "std", "median", "max", "min"]
+
+
+class ReducePlan:
+    """Device-resident bin tables for ``da.regrid.most_common / least_common / stat``.
+
+    Mirrors what ``compute_mode`` / ``statistic_reduce`` (methods/flox_reduce.py:40-187) prepare before
+    calling flox -- sorted targets, closed-left interval bins, the trimmed source domain -- after
+    ``format_for_regrid(stats=True)`` (longitude shift / wrap padding only, no pole rows).
+    """
+
+    def __init__(self, rows: AxisSpec, cols: AxisSpec | None, *, device=None):
+        self.device = _require_cuda(device)
+        if rows.kind == "lon" or (cols is not None and cols.kind == "lat"):
+            raise ValueError("layout must be [..., lat, lon]: transpose the data first")
+        self.rows_bins = tables.bins_axis(tables.plain_axis(rows.src), rows.tgt)  # stats: no pole rows
+        if cols is None:
+            self.cols_bins = None
+        else:
+            cols_axis = (tables.format_lon_axis(cols.src, cols.tgt) if cols.kind == "lon"
+                         else tables.plain_axis(cols.src))
+            self.cols_bins = tables.bins_axis(cols_axis, cols.tgt)
+        self._dev: dict = {}
+
+    def _bins(self, n_cols: int):
+        if n_cols not in self._dev:
+            cols = self.cols_bins if self.cols_bins is not None else tables.identity_bins(n_cols)
+            self._dev[n_cols] = (DeviceBins(self.rows_bins, self.device), DeviceBins(cols, self.device))
+        return self._dev[n_cols]
+
+    @property
+    def fully_covered(self) -> bool:
+        return bool(self.rows_bins.cover.all()) and (self.cols_bins is None or bool(self.cols_bins.cover.all()))
+
+    def _prepare(self, x: torch.Tensor):
+        lead = x.shape[:-2]
+        x3 = x.reshape((-1,) + tuple(x.shape[-2:]))
+        rows, cols = self._bins(x3.shape[2])
+        # a source axis whose order is neither ascending, descending nor a rotation is sorted first
+        if rows.gather is not None:
+            x3 = x3.index_select(1, rows.gather)
+        if cols.gather is not None:
+            x3 = x3.index_select(2, cols.gather)
+        if x3.stride(2) != 1:
+            x3 = x3.contiguous()
+        if x3.shape[1] != rows.host.n_src or x3.shape[2] != cols.host.n_src:
+            raise ValueError(
+                f"data is {list(x3.shape[1:])} but the plan was built for [{rows.host.n_src}, {cols.host.n_src}]"
+            )
+        return x3, lead, rows, cols
+
+    def mode(self, x: torch.Tensor, values, fill_value=None, anti_mode: bool = False) -> torch.Tensor:
+        """``compute_mode`` (methods/flox_reduce.py:122-187)."""
+        if not x.is_cuda:
+            raise ValueError("ReducePlan takes CUDA tensors")
+        if x.dtype not in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+            raise ValueError(
+                "Your input data has to be of an integer datatype for this method.\n"
+                f"    instead, your data is of type '{x.dtype}'."
+            )
+        x3, lead, rows, cols = self._prepare(x)
+        np_dtype = np.dtype(str(x.dtype).replace("torch.", ""))
+        vals = np.asarray(values).astype(np_dtype)
+        dense = bool(np.array_equal(vals, np.arange(vals.size)))
+        order = np.argsort(vals, kind="stable")
+        v_dev = torch.from_numpy(np.ascontiguousarray(vals)).to(self.device)
+        vs_dev = torch.from_numpy(np.ascontiguousarray(vals[order])).to(self.device)
+        rank_dev = torch.from_numpy(order.astype(np.int32)).to(self.device)
+        if fill_value is None and not self.fully_covered:
+            import warnings
+
+            warnings.warn(
+                "No fill_value is provided; data will be cast to floating point dtype to be able to use "
+                "NaN for missing values.", stacklevel=1,
+            )
+            out_dtype, fill = torch.float64, float("nan")
+        else:
+            out_dtype, fill = x.dtype, 0.0 if fill_value is None else float(fill_value)
+        B, Ho, Wo = x3.shape[0], rows.host.n_out, cols.host.n_out
+        y = torch.empty((B, Ho, Wo), dtype=out_dtype, device=x3.device)
+        cpc, tile = tables.plan_chunks(rows.host, cols.host, x3.element_size(), 8 * vals.size * 4)
+        if B:
+            check(
+                lib.rg_mode(x3.data_ptr(), y.data_ptr(), _TYPE_CODE[x3.dtype], _TYPE_CODE[out_dtype], B,
+                            x3.stride(0) if B > 1 else x3.shape[1] * x3.stride(1), x3.stride(1), Ho * Wo,
+                            rows.ref, cols.ref, cpc, tile, vs_dev.data_ptr(), rank_dev.data_ptr(),
+                            v_dev.data_ptr(), int(vals.size), int(dense), int(bool(anti_mode)), fill,
+                            _stream_ptr(x3.device)),
+                "rg_mode",
+            )
+        return y.view(tuple(lead) + (Ho, Wo))
+
+    def stat(self, x: torch.Tensor, method: str, skipna: bool = False, fill_value=None) -> torch.Tensor:
+        """``statistic_reduce`` (methods/flox_reduce.py:40-100)."""
+        if method not in VALID_STAT_METHODS:
+            raise ValueError(f"Invalid method. Please choose from '{VALID_STAT_METHODS}'.")
+        if not x.is_cuda:
+            raise ValueError("ReducePlan takes CUDA tensors")
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.to(torch.float64)
+        x3, lead, rows, cols = self._prepare(x)
+        B, Ho, Wo = x3.shape[0], rows.host.n_out, cols.host.n_out
+        y = torch.empty((B, Ho, Wo), dtype=x3.dtype, device=x3.device)
+        sort_cap = 0
+        if method == "median":
+            biggest = int(rows.host.count.max()) * int(cols.host.count.max())
+            sort_cap = 1 << max(biggest - 1, 0).bit_length()
+        cpc, tile = tables.plan_chunks(rows.host, cols.host, x3.element_size(),
+                                       8 * sort_cap * x3.element_size())
+        fn = lib.rg_stat_f64 if x3.dtype == torch.float64 else lib.rg_stat_f32
+        fill = float("nan") if fill_value is None else float(fill_value)
+        if B:
+            check(
+                fn(x3.data_ptr(), y.data_ptr(), B, x3.stride(0) if B > 1 else x3.shape[1] * x3.stride(1),
+                   x3.stride(1), Ho * Wo, rows.ref, cols.ref, cpc, tile, _STAT_CODE[method],
+                   int(bool(skipna)), sort_cap, fill, _stream_ptr(x3.device)),
+                "rg_stat",
+            )
         return y.view(tuple(lead) + (Ho, Wo))
 
 

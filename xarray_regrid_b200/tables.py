@@ -545,3 +545,103 @@ def cubic_bands(axis: FormattedAxis, tgt, rel_cut: float = 1e-18):
     ev = Band(e_idx, e_w, np.full(t.size, 4, np.int32), cover.astype(np.uint8), n, None,
               {"pole_rows": False, "method": "cubic-evaluate"})
     return pre, ev
+
+
+# ------------------------------------------------------------- group-by bins (most_common / stat)
+@dataclass
+class Bins:
+    """Closed-left target bins over one (formatted, ascending) source axis: ``rg_bins_t``."""
+
+    start: np.ndarray  # int32 [n_out] first formatted position of the bin (sorted-target order)
+    count: np.ndarray  # int32 [n_out]
+    cover: np.ndarray  # uint8 [n_out]
+    out_index: np.ndarray  # int32 [n_out] index of the bin's target in the target's own order
+    n_src: int
+    src_offset: int
+    src_step: int
+    gather: np.ndarray | None = None  # set when the source order is not affine: materialise x[gather] first
+
+    @property
+    def n_out(self) -> int:
+        return int(self.start.size)
+
+
+def bin_breaks(tgt_sorted):
+    """methods/_shared.py:12-18: ``append(t, t[-1] + step) - step / 2`` with the MEDIAN step."""
+    step = np.median(np.diff(tgt_sorted, n=1))
+    return np.append(tgt_sorted, tgt_sorted[-1] + step) - step / 2
+
+
+def bins_axis(axis: FormattedAxis, tgt) -> Bins:
+    """Bin table of one axis, following ``construct_intervals`` (_shared.py:12-18),
+    ``reduce_data_to_new_domain`` (_shared.py:92-108) and the coverage rule of
+    ``restore_properties`` (_shared.py:56-59)."""
+    tgt = np.asarray(tgt)
+    if tgt.size < 2:
+        raise ValueError("the group-by regridders need at least two target points per axis")
+    t_order = monotonic_order(tgt)
+    tgt_sorted = tgt if t_order is None else tgt[t_order]
+    if tgt_sorted.size != tgt.size:
+        raise NotImplementedError("duplicate target coordinates")
+    out_index = np.arange(tgt.size) if t_order is None else t_order
+
+    src = np.asarray(axis.values)
+    res = np.median(np.diff(tgt_sorted, 1))
+    keep = (src >= tgt_sorted.min() - res) & (src <= tgt_sorted.max() + res)
+    breaks = bin_breaks(tgt_sorted)
+    n_out = tgt_sorted.size
+    code = np.digitize(src, breaks, right=False) - 1  # closed-left membership
+    code = np.where(src < breaks[0], -1, np.where(~(src < breaks[-1]), n_out, code))
+    code = np.where(keep | (code < 0) | (code >= n_out), code, np.where(src < tgt_sorted.min(), -1, n_out))
+    start = np.searchsorted(code, np.arange(n_out), side="left")
+    stop = np.searchsorted(code, np.arange(n_out), side="right")
+    kept = src[keep]
+    if kept.size:
+        cover = (tgt_sorted <= kept.max()) & (tgt_sorted >= kept.min())
+    else:
+        cover = np.zeros(n_out, bool)
+
+    # source order as an affine map of the formatted position (ascending, descending, rotated/wrapped)
+    source = axis.source.astype(np.int64)
+    n_src = axis.n_src
+    gather = None
+    offset, step = 0, 1
+    if source.size:
+        ok = False
+        for s in (1, -1):
+            if np.array_equal(source, (source[0] + s * np.arange(source.size)) % n_src):
+                offset, step, ok = int(source[0]), s, True
+                break
+        if not ok:
+            gather, n_src = source, int(source.size)
+    return Bins(start.astype(np.int32), (stop - start).astype(np.int32), cover.astype(np.uint8),
+                out_index.astype(np.int32), n_src, offset, step, gather)
+
+
+def identity_bins(n: int) -> Bins:
+    """Every source index is its own bin (axis that is not regridded)."""
+    return Bins(np.arange(n, dtype=np.int32), np.ones(n, np.int32), np.ones(n, np.uint8),
+                np.arange(n, dtype=np.int32), n, 0, 1)
+
+
+def plan_chunks(rows: Bins, cols: Bins, elem_size: int, extra_bytes_per_cta: int = 0,
+                budget_bytes: int = 72 * 1024, hard_limit: int = 200 * 1024):
+    """Target columns per CTA and the tile capacity (elements) the stat / mode kernels need."""
+    max_rows = int(rows.count[rows.cover > 0].max()) if (rows.cover > 0).any() else 1
+    max_rows = max(max_rows, 1)
+    ends = cols.start.astype(np.int64) + cols.count
+    best = None
+    for c in (64, 48, 32, 24, 16, 12, 8, 6, 4, 3, 2, 1):
+        l0 = np.arange(0, cols.n_out, c)
+        l1 = np.minimum(l0 + c, cols.n_out) - 1
+        span = int((ends[l1] - cols.start[l0]).max())
+        tile = max(max_rows * max(span, 1), 1)
+        total = tile * elem_size + extra_bytes_per_cta
+        if total <= budget_bytes or (c == 1 and total <= hard_limit):
+            best = (c, tile)
+            break
+    if best is None:
+        raise NotImplementedError(
+            "a single target cell does not fit in shared memory (bins of more than ~200 KB of source data)"
+        )
+    return best
