@@ -123,46 +123,51 @@ class BandOp:
     conservative, linear and cubic regridders.
     """
 
-    def __init__(self, rows_band: tables.Band, cols_band: tables.Band | None, device):
+    def __init__(self, rows_band: tables.Band | None, cols_band: tables.Band | None, device):
         self.device = _require_cuda(device)
-        self.rows_band, self.cols_band = rows_band, cols_band
-        self.pole_rows = bool(rows_band.meta.get("pole_rows")) and bool(
+        self.rows_band, self.cols_band = rows_band, cols_band  # None = axis is not regridded (identity)
+        self.pole_rows = rows_band is not None and bool(rows_band.meta.get("pole_rows")) and bool(
             (rows_band.idx >= rows_band.n_src).any()
         )
         self._dev: dict = {}
         self._rings: dict = {}
         self.use_ring = True  # tests flip this to exercise the generic kernel
 
-    def _ring(self, batch: int, n_cols: int, dtype: torch.dtype):
+    def _host_bands(self, n_rows: int, n_cols: int):
+        rows = self.rows_band if self.rows_band is not None else tables.identity_band(n_rows)
+        cols = self.cols_band if self.cols_band is not None else tables.identity_band(n_cols)
+        return rows, cols
+
+    def _ring(self, batch: int, n_rows: int, n_cols: int, dtype: torch.dtype):
         """Row-ring schedule sized so that (slabs x runs) fills the SMs about twice over."""
         if not self.use_ring or self.pole_rows:
             return None
+        rows, cols = self._host_bands(n_rows, n_cols)
         sms = max(sm_count(), 1)
-        n_runs = int(min(self.rows_band.n_out, max(1, -(-2 * sms // max(batch, 1)))))
+        n_runs = int(min(rows.n_out, max(1, -(-2 * sms // max(batch, 1)))))
         vec = 2 if dtype == torch.float64 else 4
-        key = (n_runs, n_cols, vec)
+        key = (n_runs, n_rows, n_cols, vec)
         if key not in self._rings:
-            cols = self.cols_band if self.cols_band is not None else tables.identity_band(n_cols)
-            host = tables.row_ring_schedule(self.rows_band, n_runs, cols, vec)
-            self._rings[key] = None if host is None else DeviceRing(host, self.rows_band, dtype, self.device)
+            host = tables.row_ring_schedule(rows, n_runs, cols, vec)
+            self._rings[key] = None if host is None else DeviceRing(host, rows, dtype, self.device)
         return self._rings[key]
 
-    def _bands(self, dtype: torch.dtype, n_cols: int):
-        key = (dtype, n_cols)
+    def _bands(self, dtype: torch.dtype, n_rows: int, n_cols: int):
+        key = (dtype, n_rows, n_cols)
         if key not in self._dev:
-            cols = self.cols_band if self.cols_band is not None else tables.identity_band(n_cols)
-            self._dev[key] = (DeviceBand(self.rows_band, dtype, self.device),
-                              DeviceBand(cols, dtype, self.device))
+            rows, cols = self._host_bands(n_rows, n_cols)
+            self._dev[key] = (DeviceBand(rows, dtype, self.device), DeviceBand(cols, dtype, self.device))
         return self._dev[key]
 
-    def _out_hw(self, n_cols: int):
-        return (self.rows_band.n_out, n_cols if self.cols_band is None else self.cols_band.n_out)
+    def _out_hw(self, n_cols: int, n_rows: int | None = None):
+        return (n_rows if self.rows_band is None else self.rows_band.n_out,
+                n_cols if self.cols_band is None else self.cols_band.n_out)
 
     def run(self, x3: torch.Tensor, skipna: bool, thr: float, out: torch.Tensor | None = None) -> torch.Tensor:
         """``x3``: CUDA ``[B, H, W]`` float32/float64 with unit column stride -> ``[B, Ho, Wo]``."""
         dtype = x3.dtype
         B, H, W = x3.shape
-        rows, cols = self._bands(dtype, W)
+        rows, cols = self._bands(dtype, H, W)
         if H != rows.host.n_src or W != cols.host.n_src:
             raise ValueError(
                 f"data is [{H}, {W}] but the plan was built for [{rows.host.n_src}, {cols.host.n_src}]"
@@ -184,7 +189,7 @@ class BandOp:
             check(fn(x3.data_ptr(), pole.data_ptr(), B, H, W, x3.stride(0), x3.stride(1), stream),
                   "rg_row_nanmean")
         fn = lib.rg_conservative_f64 if dtype == torch.float64 else lib.rg_conservative_f32
-        ring = self._ring(B, W, dtype)
+        ring = self._ring(B, H, W, dtype)
         check(
             fn(x3.data_ptr(), y.data_ptr(), B, x3.stride(0) if B > 1 else H * x3.stride(1),
                x3.stride(1), Ho * Wo, rows.ref, cols.ref, int(bool(skipna)), thr,
@@ -214,12 +219,15 @@ class ConservativePlan(BandOp):
     would do to the data, as index tables.  Build once, apply to any number of stacks.
     """
 
-    def __init__(self, rows: AxisSpec, cols: AxisSpec | None, *, spherical_rows: bool | None = None,
+    def __init__(self, rows: AxisSpec | None, cols: AxisSpec | None, *, spherical_rows: bool | None = None,
                  device=None):
         self.rows_spec, self.cols_spec = rows, cols
+        if rows is None and cols is None:
+            raise ValueError("at least one axis must be regridded")
         if spherical_rows is None:
-            spherical_rows = rows.kind == "lat"
-        rows_band = tables.conservative_band(_axis(rows, True), rows.tgt, spherical=spherical_rows)
+            spherical_rows = rows is not None and rows.kind == "lat"
+        rows_band = None if rows is None else tables.conservative_band(_axis(rows, True), rows.tgt,
+                                                                      spherical=spherical_rows)
         cols_band = None if cols is None else tables.conservative_band(_axis(cols, False), cols.tgt)
         super().__init__(rows_band, cols_band, device)
 
@@ -248,7 +256,7 @@ class ConservativePlan(BandOp):
         lead = x_host.shape[:-2]
         B, H, W = x3.shape
         with torch.cuda.device(self.device):
-            rows, cols = self._bands(dtype, W)
+            rows, cols = self._bands(dtype, H, W)
             Ho, Wo = rows.host.n_out, cols.host.n_out
             if out_host is None:
                 out_host = torch.empty((B, Ho, Wo), dtype=dtype, pin_memory=x3.is_pinned())
@@ -256,7 +264,7 @@ class ConservativePlan(BandOp):
             if workspace is None or workspace.numel() * workspace.element_size() < need:
                 workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
             fn = lib.rg_conservative_host_f64 if dtype == torch.float64 else lib.rg_conservative_host_f32
-            ring = self._ring(min(chunk_batch, B), W, dtype)
+            ring = self._ring(min(chunk_batch, B), H, W, dtype)
             check(
                 fn(x3.data_ptr(), out_host.data_ptr(), B, chunk_batch, rows.ref, cols.ref,
                    int(bool(skipna)), tables.valid_threshold(nan_threshold), int(self.pole_rows),
@@ -289,22 +297,24 @@ class InterpPlan:
     float32 for linear and the integer dtype for nearest (``fill`` marks cells outside the source range).
     """
 
-    def __init__(self, rows: AxisSpec, cols: AxisSpec | None, method: str, *, device=None):
+    def __init__(self, rows: AxisSpec | None, cols: AxisSpec | None, method: str, *, device=None):
         if method not in ("linear", "nearest", "cubic"):
             raise ValueError(f"unknown interpolation method {method!r}")
+        if rows is None and cols is None:
+            raise ValueError("at least one axis must be regridded")
         self.method = method
         self.device = _require_cuda(device)
         rows_axis, cols_axis = _axis(rows, True), _axis(cols, False)
         self.rows_axis, self.cols_axis = rows_axis, cols_axis
         if method == "linear":
-            self.op = BandOp(tables.linear_band(rows_axis, rows.tgt),
+            self.op = BandOp(None if rows is None else tables.linear_band(rows_axis, rows.tgt),
                              None if cols is None else tables.linear_band(cols_axis, cols.tgt), self.device)
         elif method == "nearest":
-            self.op = BandOp(tables.nearest_band(rows_axis, rows.tgt),
+            self.op = BandOp(None if rows is None else tables.nearest_band(rows_axis, rows.tgt),
                              None if cols is None else tables.nearest_band(cols_axis, cols.tgt), self.device)
             self._gather: dict = {}
         else:
-            r_pre, r_ev = tables.cubic_bands(rows_axis, rows.tgt)
+            r_pre, r_ev = (None, None) if rows is None else tables.cubic_bands(rows_axis, rows.tgt)
             c_pre, c_ev = (None, None) if cols is None else tables.cubic_bands(cols_axis, cols.tgt)
             self.pre = BandOp(r_pre, c_pre, self.device)
             self.op = BandOp(r_ev, c_ev, self.device)
@@ -313,18 +323,18 @@ class InterpPlan:
             # leaves NaN rows, and scipy's cubic turns ANY NaN in its input into an all-NaN result, so
             # the second (column) pass blanks everything.  (The reference's axis order is the iteration
             # order of a Python set, interp.py:39; the engine and the oracle fix it to rows, then cols.)
-            self.all_nan = cols is not None and not bool(r_ev.cover.all())
+            self.all_nan = rows is not None and cols is not None and not bool(r_ev.cover.all())
 
     # nearest on integers (or out_dtype="same"): pure gather kernel
-    def _gather_tables(self, n_cols: int):
-        if n_cols not in self._gather:
+    def _gather_tables(self, n_rows: int, n_cols: int):
+        if (n_rows, n_cols) not in self._gather:
             def up(a, dt):
                 return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)
-            rb = self.op.rows_band
-            cb = self.op.cols_band if self.op.cols_band is not None else tables.identity_band(n_cols)
-            self._gather[n_cols] = (up(rb.idx[0], np.int32), up(rb.cover, np.uint8),
-                                    up(cb.idx[0], np.int32), up(cb.cover, np.uint8), rb.n_src, cb.n_src)
-        return self._gather[n_cols]
+            rb, cb = self.op._host_bands(n_rows, n_cols)
+            self._gather[(n_rows, n_cols)] = (up(rb.idx[0], np.int32), up(rb.cover, np.uint8),
+                                              up(cb.idx[0], np.int32), up(cb.cover, np.uint8),
+                                              rb.n_src, cb.n_src)
+        return self._gather[(n_rows, n_cols)]
 
     def _nearest_gather(self, x: torch.Tensor, out_dtype: torch.dtype, fill: float) -> torch.Tensor:
         lead = x.shape[:-2]
@@ -332,7 +342,7 @@ class InterpPlan:
         if x3.stride(2) != 1:
             x3 = x3.contiguous()
         B, H, W = x3.shape
-        ri, rok, ci, cok, n_rows, n_cols = self._gather_tables(W)
+        ri, rok, ci, cok, n_rows, n_cols = self._gather_tables(H, W)
         if H != n_rows or W != n_cols:
             raise ValueError(f"data is [{H}, {W}] but the plan was built for [{n_rows}, {n_cols}]")
         Ho, Wo = ri.numel(), ci.numel()
@@ -374,7 +384,8 @@ class InterpPlan:
 
         # cubic: NaN flag -> prefilter (source grid) -> evaluate (target grid) -> poison
         B, H, W = x3.shape
-        Ho, Wo = self.op._out_hw(self.pre._out_hw(W)[1])
+        Hf, Wf = self.pre._out_hw(W, H)
+        Ho, Wo = self.op._out_hw(Wf, Hf)
         if self.all_nan:
             return torch.full(tuple(lead) + (Ho, Wo), float("nan"), dtype=work, device=x3.device)
         y = torch.empty((B, Ho, Wo), dtype=work, device=x3.device)
@@ -424,11 +435,14 @@ class ReducePlan:
     ``format_for_regrid(stats=True)`` (longitude shift / wrap padding only, no pole rows).
     """
 
-    def __init__(self, rows: AxisSpec, cols: AxisSpec | None, *, device=None):
+    def __init__(self, rows: AxisSpec | None, cols: AxisSpec | None, *, device=None):
         self.device = _require_cuda(device)
-        if rows.kind == "lon" or (cols is not None and cols.kind == "lat"):
+        if rows is None and cols is None:
+            raise ValueError("at least one axis must be regridded")
+        if (rows is not None and rows.kind == "lon") or (cols is not None and cols.kind == "lat"):
             raise ValueError("layout must be [..., lat, lon]: transpose the data first")
-        self.rows_bins = tables.bins_axis(tables.plain_axis(rows.src), rows.tgt)  # stats: no pole rows
+        # stats=True formatting: no pole rows (utils.py:258-261)
+        self.rows_bins = None if rows is None else tables.bins_axis(tables.plain_axis(rows.src), rows.tgt)
         if cols is None:
             self.cols_bins = None
         else:
@@ -437,20 +451,22 @@ class ReducePlan:
             self.cols_bins = tables.bins_axis(cols_axis, cols.tgt)
         self._dev: dict = {}
 
-    def _bins(self, n_cols: int):
-        if n_cols not in self._dev:
+    def _bins(self, n_rows: int, n_cols: int):
+        if (n_rows, n_cols) not in self._dev:
+            rows = self.rows_bins if self.rows_bins is not None else tables.identity_bins(n_rows)
             cols = self.cols_bins if self.cols_bins is not None else tables.identity_bins(n_cols)
-            self._dev[n_cols] = (DeviceBins(self.rows_bins, self.device), DeviceBins(cols, self.device))
-        return self._dev[n_cols]
+            self._dev[(n_rows, n_cols)] = (DeviceBins(rows, self.device), DeviceBins(cols, self.device))
+        return self._dev[(n_rows, n_cols)]
 
     @property
     def fully_covered(self) -> bool:
-        return bool(self.rows_bins.cover.all()) and (self.cols_bins is None or bool(self.cols_bins.cover.all()))
+        return (self.rows_bins is None or bool(self.rows_bins.cover.all())) and (
+            self.cols_bins is None or bool(self.cols_bins.cover.all()))
 
     def _prepare(self, x: torch.Tensor):
         lead = x.shape[:-2]
         x3 = x.reshape((-1,) + tuple(x.shape[-2:]))
-        rows, cols = self._bins(x3.shape[2])
+        rows, cols = self._bins(x3.shape[1], x3.shape[2])
         # a source axis whose order is neither ascending, descending nor a rotation is sorted first
         if rows.gather is not None:
             x3 = x3.index_select(1, rows.gather)

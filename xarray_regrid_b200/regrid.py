@@ -1,0 +1,315 @@
+"""The ``.regrid`` accessor: same methods, arguments and errors as the reference's ``Regridder``
+(src/xarray_regrid/regrid.py:11-315), executed by the CUDA engine.
+
+Works on ``labelled.DataArray`` / ``labelled.Dataset`` everywhere, and -- when xarray is importable --
+is registered as the ``regrid`` accessor of ``xarray.DataArray`` / ``xarray.Dataset`` exactly like the
+reference does (regrid.py:11-12), converting through ``labelled.from_xarray`` / ``to_xarray``.
+
+What stays on the host is label bookkeeping only: which coordinates are regridded, their names
+(lat / lon formatting), dimension order, attributes.  Arrays that arrive as numpy are moved to the GPU,
+regridded and returned as numpy; CUDA tensors stay on the device.
+"""
+
+from __future__ import annotations
+
+import importlib.util
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import engine, tables
+from .labelled import DataArray, Dataset
+
+_PLAN_CACHE: "OrderedDict[tuple, object]" = OrderedDict()
+_PLAN_CACHE_SIZE = 16
+
+
+def _kind(name) -> str:
+    n = str(name).lower()
+    if n in tables.LAT_NAMES:
+        return "lat"
+    if n in tables.LON_NAMES:
+        return "lon"
+    return "other"
+
+
+def _key(*parts) -> tuple:
+    out = []
+    for p in parts:
+        if isinstance(p, np.ndarray):
+            out.append((p.dtype.str, p.shape, p.tobytes()))
+        else:
+            out.append(p)
+    return tuple(out)
+
+
+def _cached(key, build):
+    if key in _PLAN_CACHE:
+        _PLAN_CACHE.move_to_end(key)
+        return _PLAN_CACHE[key]
+    plan = build()
+    _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def validate_input(data, ds_target_grid: Dataset, time_dim):
+    """regrid.py:289-315: drop the time coordinate from the target; require shared dims and coords."""
+    if time_dim is not None and time_dim in ds_target_grid.coords:
+        coords = {k: v for k, v in ds_target_grid.coords.items() if k != time_dim}
+        ds_target_grid = Dataset({}, coords, dict(ds_target_grid.attrs),
+                                 {k: v for k, v in ds_target_grid.coord_attrs.items() if k != time_dim})
+    data_dims = set(data.dims)
+    if len(data_dims.intersection(set(ds_target_grid.dims))) == 0:
+        raise ValueError(
+            "None of the target dims are in the data:\n"
+            " regridding is not possible.\n"
+            f"Target dims: {list(ds_target_grid.dims)}\n"
+            f"Source dims: {list(data.dims)}"
+        )
+    if len(set(data.coords).intersection(set(ds_target_grid.coords))) == 0:
+        raise ValueError(
+            "None of the target coords are in the data:\n"
+            " regridding is not possible.\n"
+            f"Target coords: {list(ds_target_grid.coords)}\n"
+            f"Dataset coords: {list(data.coords)}"
+        )
+    return ds_target_grid
+
+
+def _layout(da: DataArray, names, prefer_rows=None):
+    """Pick (rows, cols) among the regridded coordinate names.  A latitude-named coordinate is always
+    rows and a longitude-named one always cols (the kernels' pole / wrap handling is tied to that
+    layout); other coordinates fill the free slots in the data's dim order (``prefer_rows`` first)."""
+    names = [n for n in names if n in da.dims]
+    if not names:
+        return None
+    if len(names) > 2:
+        raise NotImplementedError("regridding over more than two dimensions at once is not supported")
+    rows = next((n for n in names if _kind(n) == "lat"), None)
+    cols = next((n for n in names if _kind(n) == "lon"), None)
+    rest = sorted((n for n in names if n not in (rows, cols)),
+                  key=lambda n: (n != prefer_rows, da.dims.index(n)))
+    for n in rest:
+        if rows is None:
+            rows = n
+        elif cols is None:
+            cols = n
+    return rows, cols
+
+
+def _to_device(data):
+    """numpy / CPU tensor -> CUDA tensor; remembers how to go back."""
+    if isinstance(data, torch.Tensor):
+        if data.is_cuda:
+            return data, "cuda"
+        return data.cuda(), "cpu-tensor"
+    arr = np.asarray(data)
+    if arr.dtype.byteorder not in ("=", "|"):
+        arr = arr.astype(arr.dtype.newbyteorder("="))
+    return torch.from_numpy(np.ascontiguousarray(arr)).cuda(), "numpy"
+
+
+def _from_device(y: torch.Tensor, how: str):
+    if how == "cuda":
+        return y
+    if how == "cpu-tensor":
+        return y.cpu()
+    return y.cpu().numpy()
+
+
+def _apply(da: DataArray, target: Dataset, names, run, coord_attrs_from: str, prefer_rows=None) -> DataArray:
+    """Shared driver: permute to ``[..., rows, cols]``, call ``run(x, rows_name, rows_spec, cols_spec)``,
+    permute back, relabel.  ``run`` receives CUDA data and the two ``engine.AxisSpec`` (or None)."""
+    lay = _layout(da, names, prefer_rows)
+    if lay is None:
+        return da
+    rows, cols = lay
+    batch = [d for d in da.dims if d not in (rows, cols)]
+    pad = None
+    if cols is None and batch:  # one regridded axis (rows): let the last batch dim ride along as columns
+        order = batch[:-1] + [rows, batch[-1]]
+    elif cols is None:  # 1-D data: add a singleton column axis
+        order, pad = [rows], -1
+    elif rows is None:  # one regridded axis (cols): singleton row axis, every slab is one row
+        order, pad = batch + [cols], -2
+    else:
+        order = batch + [rows, cols]
+    x, how = _to_device(da.data)
+    x = x.permute([da.dims.index(d) for d in order])
+    if pad is not None:
+        x = x.unsqueeze(pad)
+    spec = {n: engine.AxisSpec(np.asarray(da.coords[n]), np.asarray(target.coords[n]), _kind(n))
+            for n in (rows, cols) if n is not None}
+    y = run(x, rows, spec.get(rows), spec.get(cols))
+    if pad is not None:
+        y = y.squeeze(pad)
+    y = y.permute([order.index(d) for d in da.dims])
+    coords = dict(da.coords)
+    cattrs = dict(da.coord_attrs)
+    for n in (rows, cols):
+        if n is not None:
+            coords[n] = np.asarray(target.coords[n])
+            if coord_attrs_from == "target":
+                cattrs[n] = dict(target.coord_attrs.get(n, {}))
+    return DataArray(_from_device(y.contiguous(), how), da.dims, coords, dict(da.attrs), cattrs, da.name)
+
+
+def _map(obj, fn):
+    """Apply ``fn`` to a DataArray or to every data variable of a Dataset (utils.py:201-224)."""
+    if isinstance(obj, DataArray):
+        return fn(obj)
+    out = {k: fn(v) for k, v in obj.data_vars.items()}
+    coords = dict(obj.coords)
+    cattrs = dict(obj.coord_attrs)
+    for v in out.values():
+        coords.update(v.coords)
+        for k, a in v.coord_attrs.items():
+            cattrs[k] = a
+    return Dataset(out, coords, dict(obj.attrs), cattrs)
+
+
+class Regridder:
+    """Regridding labelled datasets and dataarrays (mirror of regrid.py:13-270).
+
+    Available methods: linear, nearest, cubic, conservative, most_common, least_common, stat.
+    """
+
+    def __init__(self, obj):
+        self._obj = obj
+
+    # ---------------------------------------------------------------- interpolation (regrid.py:28-83)
+    def _interp(self, ds_target_grid, time_dim, method):
+        target = validate_input(self._obj, ds_target_grid, time_dim)
+        names = [c for c in target.coords if c in self._obj.coords]
+
+        def one(da):
+            def run(x, rows_name, rs, cs):
+                key = _key("interp", method, None if rs is None else rs.src, None if rs is None else rs.tgt,
+                           None if rs is None else rs.kind, None if cs is None else cs.src,
+                           None if cs is None else cs.tgt, None if cs is None else cs.kind, str(x.device))
+                plan = _cached(key, lambda: engine.InterpPlan(rs, cs, method, device=x.device))
+                return plan(x)
+
+            return _apply(da, target, names, run, "data")
+
+        return _map(self._obj, one)
+
+    def linear(self, ds_target_grid, time_dim="time"):
+        """Regrid to the coords of the target dataset with linear interpolation."""
+        return self._interp(ds_target_grid, time_dim, "linear")
+
+    def nearest(self, ds_target_grid, time_dim="time"):
+        """Regrid to the coords of the target with nearest-neighbor interpolation."""
+        return self._interp(ds_target_grid, time_dim, "nearest")
+
+    def cubic(self, ds_target_grid, time_dim="time"):
+        """Regrid to the coords of the target dataset with cubic interpolation."""
+        return self._interp(ds_target_grid, time_dim, "cubic")
+
+    # ------------------------------------------------------------------ conservative (regrid.py:85-131)
+    def conservative(self, ds_target_grid, latitude_coord=None, time_dim="time", skipna=True,
+                     nan_threshold=1.0, output_chunks=None):
+        """Regrid to the coords of the target dataset with a conservative scheme.
+
+        ``output_chunks`` is accepted for signature compatibility; the engine has no dask graph."""
+        if not 0.0 <= nan_threshold <= 1.0:
+            raise ValueError("nan_threshold must be between [0, 1]]")
+        target = validate_input(self._obj, ds_target_grid, time_dim)
+        if latitude_coord is None:  # conservative.py:75-79
+            for c in self._obj.coords:
+                if str(c).lower() in tables.LAT_NAMES:
+                    latitude_coord = c
+                    break
+        names = [c for c in target.coords if c in self._obj.coords]
+
+        def one(da):
+            def run(x, rows_name, rs, cs):
+                spherical = rows_name is not None and rows_name == latitude_coord
+                if latitude_coord in names and latitude_coord in da.dims and not spherical:
+                    raise NotImplementedError("the latitude coordinate must be the row axis of the kernel")
+                key = _key("conservative", spherical, None if rs is None else rs.src,
+                           None if rs is None else rs.tgt, None if rs is None else rs.kind,
+                           None if cs is None else cs.src, None if cs is None else cs.tgt,
+                           None if cs is None else cs.kind, str(x.device))
+                plan = _cached(key, lambda: engine.ConservativePlan(rs, cs, spherical_rows=spherical,
+                                                                    device=x.device))
+                return plan(x, skipna=skipna, nan_threshold=nan_threshold)
+
+            return _apply(da, target, names, run, "data", prefer_rows=latitude_coord)
+
+        return _map(self._obj, one)
+
+    # ------------------------------------------------------- most / least common (regrid.py:133-235)
+    def _mode(self, ds_target_grid, values, time_dim, fill_value, anti_mode, what):
+        target = validate_input(self._obj, ds_target_grid, time_dim)
+        if isinstance(self._obj, Dataset):
+            raise ValueError(
+                f"The '{what} common value' regridder is not implemented for\n"
+                "xarray.Dataset, as it requires specifying the expected labels.\n"
+                "Please select only a single variable (as DataArray),\n"
+                " and regrid it separately."
+            )
+        names = [c for c in target.coords if c in self._obj.coords and c != time_dim]
+
+        def run(x, rows_name, rs, cs):
+            key = _key("reduce", None if rs is None else rs.src, None if rs is None else rs.tgt,
+                       None if rs is None else rs.kind, None if cs is None else cs.src,
+                       None if cs is None else cs.tgt, None if cs is None else cs.kind, str(x.device))
+            plan = _cached(key, lambda: engine.ReducePlan(rs, cs, device=x.device))
+            return plan.mode(x, values, fill_value=fill_value, anti_mode=anti_mode)
+
+        return _apply(self._obj, target, names, run, "target")
+
+    def most_common(self, ds_target_grid, values, time_dim="time", fill_value=None):
+        """Regrid by taking the most common value within the new grid cells (ties: first of ``values``)."""
+        return self._mode(ds_target_grid, values, time_dim, fill_value, False, "most")
+
+    def least_common(self, ds_target_grid, values, time_dim="time", fill_value=None):
+        """Regrid by taking the least common value within the new grid cells."""
+        return self._mode(ds_target_grid, values, time_dim, fill_value, True, "least")
+
+    # ----------------------------------------------------------------------- stat (regrid.py:237-270)
+    def stat(self, ds_target_grid, method, time_dim="time", skipna=False, fill_value=None):
+        """Zonal statistics: "sum", "mean", "var", "std", "median", "min" or "max" per target cell."""
+        target = validate_input(self._obj, ds_target_grid, time_dim)
+        if method not in engine.VALID_STAT_METHODS:
+            raise ValueError(f"Invalid method. Please choose from '{engine.VALID_STAT_METHODS}'.")
+        names = [c for c in target.coords if c in self._obj.coords and c != time_dim]
+
+        def one(da):
+            def run(x, rows_name, rs, cs):
+                key = _key("reduce", None if rs is None else rs.src, None if rs is None else rs.tgt,
+                           None if rs is None else rs.kind, None if cs is None else cs.src,
+                           None if cs is None else cs.tgt, None if cs is None else cs.kind, str(x.device))
+                plan = _cached(key, lambda: engine.ReducePlan(rs, cs, device=x.device))
+                return plan.stat(x, method, skipna=skipna, fill_value=fill_value)
+
+            return _apply(da, target, names, run, "target")
+
+        return _map(self._obj, one)
+
+
+# ---------------------------------------------------------------------- xarray accessor registration
+if importlib.util.find_spec("xarray") is not None:  # pragma: no cover - xarray is absent in this image
+    import xarray as xr
+
+    from .labelled import from_xarray, to_xarray
+
+    @xr.register_dataarray_accessor("regrid")
+    @xr.register_dataset_accessor("regrid")
+    class _XarrayRegridder:
+        __doc__ = Regridder.__doc__
+
+        def __init__(self, xarray_obj):
+            self._x = xarray_obj
+
+        def __getattr__(self, name):
+            method = getattr(Regridder(from_xarray(self._x)), name)
+
+            def call(ds_target_grid, *args, **kwargs):
+                return to_xarray(method(from_xarray(ds_target_grid), *args, **kwargs))
+
+            return call
