@@ -71,6 +71,8 @@ typedef struct rg_band {
   int32_t n_out;
   int32_t k_max;
   int32_t n_src;
+  int32_t span; /* max over outputs of (largest - smallest tap index + 1); 0 = unknown.  Lets the
+                   library pick the shared-memory upsampling kernel for interpolation bands. */
 } rg_band_t;
 
 /*

@@ -28,6 +28,7 @@ class rg_band_t(C.Structure):  # noqa: N801 - mirrors the C name
         ("n_out", C.c_int32),
         ("k_max", C.c_int32),
         ("n_src", C.c_int32),
+        ("span", C.c_int32),
     ]
 
 

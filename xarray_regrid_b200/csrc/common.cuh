@@ -29,7 +29,7 @@ struct Band {
   const T* __restrict__ w;
   const int32_t* __restrict__ cnt;
   const uint8_t* __restrict__ cover;
-  int n_out, k_max, n_src;
+  int n_out, k_max, n_src, span;
 };
 
 template <typename T>
@@ -43,6 +43,7 @@ inline int make_band(const rg_band_t* b, Band<T>* out) {
   out->n_out = b->n_out;
   out->k_max = b->k_max;
   out->n_src = b->n_src;
+  out->span = b->span;
   return RG_OK;
 }
 

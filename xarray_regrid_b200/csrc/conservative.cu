@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "conservative_ring.cuh"
+#include "upsample.cuh"
 
 namespace rg {
 
@@ -206,6 +207,12 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   DeviceInfo dev;
   rc = device_info(&dev);
   if (rc != RG_OK) return rc;
+
+  // ---- interpolation onto a much finer grid (write-bound): shared-memory upsampling kernel
+  if (!skipna && !pole) {
+    rc = upsample_try_launch<T>(x, y, batch, xbs, xrs, ybs, rows, cols, rows.span, dev, stream);
+    if (rc != RG_ERR_UNSUPPORTED) return rc;
+  }
 
   // ---- fast path: TMA row-ring kernel (needs 16-byte aligned rows, no pole rows, <= 8 taps per
   //      axis, a ring that fits shared memory)

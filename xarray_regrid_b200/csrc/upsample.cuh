@@ -1,0 +1,252 @@
+// Separable small-band UPSAMPLING kernel (sm_100a): linear (2 x 2 taps) and cubic evaluation (4 x 4 taps)
+// onto a much finer grid, e.g. 1 deg -> 0.1 deg (config 3: 181 x 360 -> 1801 x 3600).
+//
+// The op is write-bound (100 output bytes per input byte), so the kernel is organised around the stores:
+//   * a CTA owns (slab b, band of R consecutive output rows) and ALL output columns;
+//   * every thread owns G groups of 4 consecutive output columns for the whole band and keeps their
+//     longitude taps (index + weight) in registers -- loaded once per CTA, the CTA is persistent;
+//   * the few source rows the band needs are staged in shared memory (sliding window, coalesced loads);
+//   * per output row: (A) one latitude-interpolated source row z[j] = sum_t wr[t] * xs[row_t][j] is
+//     built in shared memory (double buffered -> one barrier per output row), (B) each thread produces
+//     its outputs as sum_c wc[c] * z[idx[c]] and writes them with 16-byte streaming stores.
+// NaN propagates through every tap (weight 0 included), which is the interpolation semantics
+// (scipy interp1d: w_hi*y_hi + w_lo*y_lo).  Replaces data.interp(...) of methods/interp.py:43-46.
+//
+// Roofline: HBM (writes).  Algorithmic bytes per slab = (H*W + Ho*Wo) * sizeof(T).
+#pragma once
+
+#include "common.cuh"
+
+namespace rg {
+
+constexpr int kUpThreads = 256;
+constexpr int kUpRowCap = 16;      // source rows held in shared memory
+constexpr int kUpBandRows = 32;    // output rows per task
+constexpr int kUpRowsPerSync = 4;  // output rows produced per barrier
+
+template <typename T> struct Vec4;
+template <> struct alignas(16) Vec4<float> { float v[4]; };
+template <> struct alignas(16) Vec4<double> { double v[4]; };
+
+__device__ __forceinline__ void st_stream4(float* p, const Vec4<float>& a) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a.v[0]), "f"(a.v[1]), "f"(a.v[2]),
+               "f"(a.v[3])
+               : "memory");
+}
+__device__ __forceinline__ void st_stream4(double* p, const Vec4<double>& a) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a.v[0]), "d"(a.v[1]) : "memory");
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p + 2), "d"(a.v[2]), "d"(a.v[3]) : "memory");
+}
+
+// Rows [kb, kb + nk) of a band: latitude pass into the z buffers of parity BUF, one barrier, longitude
+// pass + stores.  BUF and the row slot are compile-time so that every z read is LDS [reg + immediate].
+template <typename T, int KR, int KC, int G, int ZW, int BUF>
+__device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, int nk, int W, int Wo,
+                                        const T* s_x, T* s_z, const int (*s_off)[KR], const T (*s_rw)[KR],
+                                        const int* s_state, const int (&ci)[G][4][KC], const T (&cw)[G][4][KC],
+                                        int tid, T nan) {
+  // ---- (A) latitude pass
+  for (int q = 0; q < nk; ++q) {
+    const int m = kb_local + q;
+    int off[KR];
+    T w[KR];
+#pragma unroll
+    for (int t = 0; t < KR; ++t) { off[t] = s_off[m][t]; w[t] = s_rw[m][t]; }
+    T* z = s_z + (BUF * kUpRowsPerSync + q) * ZW;
+    for (int j = tid; j < W; j += kUpThreads) {
+      T acc = T(0);
+#pragma unroll
+      for (int t = 0; t < KR; ++t) acc = fma(w[t], s_x[off[t] + j], acc);
+      z[j] = acc;
+    }
+  }
+  __syncthreads();
+  // ---- (B) longitude pass + 16-byte streaming stores
+#pragma unroll
+  for (int q = 0; q < kUpRowsPerSync; ++q) {
+    if (q < nk) {
+      T* yrow = y_band + static_cast<long long>(kb_local + q) * Wo;
+      const unsigned char* z = reinterpret_cast<const unsigned char*>(s_z + (BUF * kUpRowsPerSync + q) * ZW);
+      const int state = s_state[kb_local + q];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int l = (tid + g * kUpThreads) * 4;
+        if (l < Wo) {
+          Vec4<T> out;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            T acc = T(0);
+#pragma unroll
+            for (int c = 0; c < KC; ++c)
+              acc = fma(cw[g][e][c], *reinterpret_cast<const T*>(z + ci[g][e][c]), acc);
+            out.v[e] = acc;
+          }
+          if (state != 2) {  // uniform: uncovered latitude -> NaN row; covered without taps -> 0 (or NaN column)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) out.v[e] = (state == 0 || cw[g][e][0] != cw[g][e][0]) ? nan : T(0);
+          }
+          if (l + 4 <= Wo) {
+            st_stream4(yrow + l, out);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)  // unrolled + predicated: keeps `out` in registers
+              if (l + e < Wo) st_stream(yrow + l + e, out.v[e]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int KR, int KC, int G, int ZW>
+__global__ void __launch_bounds__(kUpThreads)
+upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
+                long long ybs, Band<T> rows, Band<T> cols, int band_rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int H = rows.n_src, W = cols.n_src, Ho = rows.n_out, Wo = cols.n_out;
+  T* s_z = reinterpret_cast<T*>(smem_raw);             // [2][kUpRowsPerSync][ZW] latitude-interpolated rows
+  T* s_x = s_z + 2 * kUpRowsPerSync * ZW;              // [kUpRowCap][W] staged source rows
+  // per-band row metadata, filled by warp 0 once per task
+  __shared__ int s_off[kUpBandRows][KR];  // element offset of tap t's row inside s_x
+  __shared__ T s_rw[kUpBandRows][KR];
+  __shared__ int s_state[kUpBandRows];    // 0: row not covered (NaN), 1: covered without taps (0), 2: normal
+  __shared__ int s_win0;
+
+  const int tid = threadIdx.x;
+  const T nan = quiet_nan<T>();
+
+  // ---- longitude taps of the columns this thread owns (registers, loaded once): byte offsets into a
+  //      z row and weights; a column outside the source range gets a NaN weight (NaN * z = NaN)
+  int ci[G][4][KC];
+  T cw[G][4][KC];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int l = (tid + g * kUpThreads) * 4 + e;
+      const bool in = l < Wo;
+      const int n = in ? cols.cnt[l] : 0;
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        const bool live = c < n && c < cols.k_max;
+        ci[g][e][c] = (live ? cols.idx[c * Wo + l] : (n > 0 ? cols.idx[l] : 0)) * static_cast<int>(sizeof(T));
+        cw[g][e][c] = live ? cols.w[c * Wo + l] : T(0);
+      }
+      if (in && !cols.cover[l]) cw[g][e][0] = nan;
+    }
+  }
+
+  const int n_bands = (Ho + band_rows - 1) / band_rows;
+  const long long tasks = batch * n_bands;
+  for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int band = static_cast<int>(task % n_bands);
+    const long long b = task / n_bands;
+    const T* xb = x + b * xbs;
+    const int k0 = band * band_rows, k1 = min(k0 + band_rows, Ho);
+
+    // ---- warp 0: row taps of the band -> shared memory; first source row of the band
+    if (tid < 32) {
+      const int k = k0 + tid;
+      int ri[KR];
+      T rw[KR];
+      int n = 0, rmin = H;
+      bool cov = false;
+      if (k < k1) {
+        cov = rows.cover[k] != 0;
+        n = cov ? rows.cnt[k] : 0;
+#pragma unroll
+        for (int t = 0; t < KR; ++t) {
+          const bool live = t < n && t < rows.k_max;
+          ri[t] = live ? rows.idx[t * Ho + k] : (n > 0 ? rows.idx[k] : 0);
+          rw[t] = live ? rows.w[t * Ho + k] : T(0);
+          if (n > 0) rmin = min(rmin, ri[t]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+      if (rmin >= H) rmin = 0;
+      if (k < k1) {
+#pragma unroll
+        for (int t = 0; t < KR; ++t) {
+          s_off[tid][t] = (n > 0 ? ri[t] - rmin : 0) * W;  // host contract (band span): < kUpRowCap rows
+          s_rw[tid][t] = rw[t];
+        }
+        s_state[tid] = !cov ? 0 : (n == 0 ? 1 : 2);
+      }
+      if (tid == 0) s_win0 = rmin;
+    }
+    __syncthreads();
+    // ---- stage the band's source rows (coalesced)
+    {
+      const int w0 = s_win0;
+      const int wn = min(kUpRowCap, H - w0);
+      for (int r = 0; r < wn; ++r) {
+        const T* src = xb + static_cast<long long>(w0 + r) * xrs;
+        for (int j = tid; j < W; j += kUpThreads) s_x[r * W + j] = __ldg(src + j);
+      }
+    }
+    __syncthreads();
+
+    T* y_band = y + b * ybs + static_cast<long long>(k0) * Wo;
+    for (int kl = 0; kl < k1 - k0; kl += 2 * kUpRowsPerSync) {
+      up_rows<T, KR, KC, G, ZW, 0>(y_band, kl, min(kUpRowsPerSync, k1 - k0 - kl), W, Wo, s_x, s_z, s_off, s_rw,
+                                   s_state, ci, cw, tid, nan);
+      const int kl2 = kl + kUpRowsPerSync;
+      if (kl2 < k1 - k0)
+        up_rows<T, KR, KC, G, ZW, 1>(y_band, kl2, min(kUpRowsPerSync, k1 - k0 - kl2), W, Wo, s_x, s_z, s_off,
+                                     s_rw, s_state, ci, cw, tid, nan);
+    }
+    __syncthreads();
+  }
+}
+
+// Eligibility + launch.  Returns RG_ERR_UNSUPPORTED when the generic kernels should be used instead.
+template <typename T>
+int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
+                        const Band<T>& rows, const Band<T>& cols, int rows_span, const DeviceInfo& dev,
+                        cudaStream_t stream) {
+  const int W = cols.n_src, Wo = cols.n_out;
+  if (rows.k_max > 4 || cols.k_max > 4) return RG_ERR_UNSUPPORTED;
+  if (rows_span <= 0 || rows_span > kUpRowCap) return RG_ERR_UNSUPPORTED;
+  if (Wo < 2 * W || Wo > kUpThreads * 4 * 4) return RG_ERR_UNSUPPORTED;  // upsampling, <= 4 groups / thread
+  if ((reinterpret_cast<uintptr_t>(y) % 16) != 0 || (ybs * sizeof(T)) % 16 != 0 || (Wo * sizeof(T)) % 16 != 0)
+    return RG_ERR_UNSUPPORTED;
+  if (W > 1024) return RG_ERR_UNSUPPORTED;
+  const int zw = W <= 512 ? 512 : 1024;
+  const size_t smem = (static_cast<size_t>(kUpRowCap) * W + 2 * kUpRowsPerSync * zw) * sizeof(T);
+  if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_UNSUPPORTED;
+  const int groups = ((Wo + 3) / 4 + kUpThreads - 1) / kUpThreads;  // 1..4
+  const int kr = rows.k_max <= 1 ? 1 : rows.k_max <= 2 ? 2 : 4;
+  const int kc = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : 4;
+  using Kernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, Band<T>, int);
+  // output rows per task: the band's source rows (span + rows advanced inside the band) must fit the
+  // staged window; bands are sorted, so the advance is about band_rows * H / Ho
+  const int H = rows.n_src, Ho = rows.n_out;
+  int band_rows = static_cast<int>((static_cast<long long>(kUpRowCap - rows_span - 1) * Ho) / (H > 0 ? H : 1));
+  if (band_rows > kUpBandRows) band_rows = kUpBandRows;
+  band_rows = band_rows / kUpRowsPerSync * kUpRowsPerSync;
+  if (band_rows < kUpRowsPerSync) return RG_ERR_UNSUPPORTED;
+  Kernel kern = nullptr;
+#define RG_UP(KR_, KC_, G_)                                                                     \
+  if (kr == KR_ && kc == KC_ && groups == G_)                                                   \
+    kern = zw == 512 ? upsample_kernel<T, KR_, KC_, G_, 512> : upsample_kernel<T, KR_, KC_, G_, 1024>;
+#define RG_UP_G(KR_, KC_) RG_UP(KR_, KC_, 1) RG_UP(KR_, KC_, 2) RG_UP(KR_, KC_, 3) RG_UP(KR_, KC_, 4)
+  RG_UP_G(1, 1) RG_UP_G(2, 2) RG_UP_G(4, 4)
+#undef RG_UP_G
+#undef RG_UP
+  if (!kern) return RG_ERR_UNSUPPORTED;  // mixed tap counts: generic kernels
+  if (smem > 48 * 1024)
+    RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kUpThreads, smem));
+  if (per_sm < 1) return RG_ERR_UNSUPPORTED;
+  const int n_bands = (rows.n_out + band_rows - 1) / band_rows;
+  const long long tasks = static_cast<long long>(batch) * n_bands;
+  long long grid = static_cast<long long>(dev.sm_count) * per_sm;
+  if (grid > tasks) grid = tasks;
+  kern<<<static_cast<unsigned>(grid), kUpThreads, smem, stream>>>(x, y, batch, xbs, xrs, ybs, rows, cols,
+                                                                 band_rows);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace rg

@@ -46,9 +46,17 @@ class DeviceBand:
         self.w = torch.from_numpy(np.ascontiguousarray(band.w.astype(np_dtype))).to(device)
         self.cnt = torch.from_numpy(np.ascontiguousarray(band.cnt, dtype=np.int32)).to(device)
         self.cover = torch.from_numpy(np.ascontiguousarray(band.cover, dtype=np.uint8)).to(device)
+        live = np.arange(band.k_max)[:, None] < band.cnt[None, :]
+        real = live & (band.idx < band.n_src)
+        if real.any():
+            hi = np.where(real, band.idx, -1).max(axis=0)
+            lo = np.where(real, band.idx, band.n_src).min(axis=0)
+            span = int(np.where(real.any(axis=0), hi - lo + 1, 0).max())
+        else:
+            span = 0
         self.c = rg_band_t(
             self.idx.data_ptr(), self.w.data_ptr(), self.cnt.data_ptr(), self.cover.data_ptr(),
-            band.n_out, band.k_max, band.n_src,
+            band.n_out, band.k_max, band.n_src, span,
         )
 
     @property
