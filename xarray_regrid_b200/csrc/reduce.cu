@@ -157,6 +157,133 @@ mode_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long batch, lo
   }
 }
 
+// ---------------------------------------------------------------- mode, one cell per lane
+// Throughput kernel for label counts: a warp owns a strip of 32 adjacent target cells of one target
+// row, ONE CELL PER LANE.  Each lane keeps its own counters in shared memory laid out [label][thread]
+// (bank = lane: conflict-free, no atomics, no voting); the warp stages kStageRows source rows of its strip at
+// a time with 16-byte coalesced loads and every lane walks its own cell.  Needs n_values <= kLaneMaxLabels.
+constexpr int kLaneThreads = 256;
+constexpr int kLaneWarps = kLaneThreads / 32;
+constexpr int kLaneMaxLabels = 64;
+constexpr int kStageRows = 5;
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kLaneThreads)
+mode_lanes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long batch, long long xbs, long long xrs,
+                  long long ybs, Bins rows, Bins cols, const Tin* __restrict__ values_sorted,
+                  const int32_t* __restrict__ value_rank, const Tin* __restrict__ values, int n_values, int dense,
+                  int anti, Tout fill, int stage_elems) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem);  // [n_values][kLaneThreads]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Tin* stage = reinterpret_cast<Tin*>(smem + static_cast<size_t>(n_values + 1) * kLaneThreads * 4) +
+               static_cast<size_t>(warp) * kStageRows * stage_elems;
+  const int Wo = cols.n_out;
+  const int strips = (Wo + 31) / 32;
+  const long long tasks = batch * rows.n_out * strips;  // one task = one 32-cell strip, handled by one warp
+  const long long warp_id = static_cast<long long>(blockIdx.x) * kLaneWarps + warp;
+  const long long n_warps = static_cast<long long>(gridDim.x) * kLaneWarps;
+
+  for (long long task = warp_id; task < tasks; task += n_warps) {
+    const int strip = static_cast<int>(task % strips);
+    const int k = static_cast<int>((task / strips) % rows.n_out);
+    const long long b = task / (static_cast<long long>(strips) * rows.n_out);
+    const int l = strip * 32 + lane;
+    const bool in = l < Wo;
+    const int l_last = min(strip * 32 + 31, Wo - 1);
+    const bool row_ok = rows.cover[k] != 0;
+    const int r0 = rows.start[k], nr = row_ok ? rows.count[k] : 0;
+    const int p0 = cols.start[strip * 32];
+    const int ncol = cols.start[l_last] + cols.count[l_last] - p0;  // host contract: <= stage_elems
+    const int c0 = in ? cols.start[l] - p0 : 0;
+    const int nc = (in && cols.cover[l]) ? cols.count[l] : 0;
+    int nc_max = nc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, o));
+
+    for (int i = 0; i <= n_values; ++i) s_cnt[i * kLaneThreads + tid] = 0;  // + 1 trash row
+    const Tin* xb = x + b * xbs;
+    // the strip's source columns are contiguous (no wrap inside the strip) in the common case
+    const int s0 = src_index(cols, p0);
+    const bool contiguous = cols.src_step == 1 && s0 + ncol <= cols.n_src;
+
+    // lanes without a live cell count everything into their trash slot (stride 0)
+    const bool live = nc > 0;
+    const int lane_stride = live ? kLaneThreads : 0;
+    uint32_t* mine = s_cnt + (live ? 0 : n_values * kLaneThreads) + tid;
+    const int nc_eff = live ? nc : nc_max;
+    int nc_min = nc_eff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nc_min = min(nc_min, __shfl_xor_sync(0xffffffffu, nc_min, o));
+    const int row_first = src_index(rows, r0);  // rows of a bin never wrap: plain +-1 steps from here
+
+    for (int rb = 0; rb < nr; rb += kStageRows) {
+      const int nrb = min(kStageRows, nr - rb);
+      __syncwarp();
+      // ---- stage nrb rows x ncol columns (coalesced; 16-byte loads when the segment is aligned)
+      for (int r = 0; r < nrb; ++r) {
+        const Tin* src = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs;
+        Tin* dst = stage + r * stage_elems;
+        if (contiguous) {
+          // keep the source's 16-byte phase in shared memory: element c lives at dst[shift + c], so every
+          // aligned 16-byte chunk of the source is copied with one LDG.128 + one STS.128
+          const Tin* seg = src + s0;
+          constexpr int V = 16 / sizeof(Tin);
+          const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(seg) & 15) / sizeof(Tin));
+          const int4* gsrc = reinterpret_cast<const int4*>(seg - shift);
+          int4* sdst = reinterpret_cast<int4*>(dst);
+          const int nvec = (shift + ncol + V - 1) / V;  // may read a few elements before / after the segment
+          for (int v = lane; v < nvec; v += 32) sdst[v] = __ldg(gsrc + v);
+        } else {
+          for (int c = lane; c < ncol; c += 32) dst[c] = __ldg(src + src_index(cols, p0 + c));
+        }
+      }
+      __syncwarp();
+      // ---- every lane walks its own cell.  Branch-free: labels that are not listed go to a trash counter
+      //      row (index n_values); each step is extract + clamp + LDS / IADD / STS on a lane-private counter
+      for (int r = 0; r < nrb; ++r) {
+        int shift = 0;
+        if (contiguous) {
+          const Tin* seg = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs + s0;
+          shift = static_cast<int>((reinterpret_cast<uintptr_t>(seg) & 15) / sizeof(Tin));
+        }
+        const int pos = shift + c0;
+        const Tin* trow = stage + r * stage_elems + pos;
+        if (dense) {
+          for (int c = 0; c < nc_min; ++c) {  // every lane's cell has this column: no per-lane predicate
+            const unsigned v = static_cast<unsigned>(static_cast<long long>(trow[c]));
+            mine[min(v, static_cast<unsigned>(n_values)) * lane_stride] += 1;
+          }
+          for (int c = nc_min; c < nc_max; ++c) {  // ragged tail
+            const unsigned v = static_cast<unsigned>(static_cast<long long>(trow[c < nc_eff ? c : 0]));
+            const unsigned d = (c < nc_eff && v < static_cast<unsigned>(n_values)) ? v : static_cast<unsigned>(n_values);
+            mine[d * lane_stride] += 1;
+          }
+        } else {
+          for (int c = 0; c < nc_max; ++c) {
+            int d = label_index(trow[c < nc_eff ? c : 0], values_sorted, n_values, 0);
+            d = (c < nc_eff && d >= 0) ? value_rank[d] : n_values;
+            mine[d * lane_stride] += 1;
+          }
+        }
+      }
+    }
+    // ---- arg-max (arg-min): empty labels count as -1 (flox fill_value=-1), ties -> first in `values`
+    Tout out = fill;
+    if (row_ok && in && cols.cover[l]) {
+      int best_i = 0;
+      int best = anti ? 0x7fffffff : -0x7fffffff;
+      for (int i = 0; i < n_values; ++i) {
+        const int cval = s_cnt[i * kLaneThreads + tid] > 0 ? static_cast<int>(s_cnt[i * kLaneThreads + tid]) : -1;
+        const bool better = anti ? (cval < best) : (cval > best);
+        if (better) { best = cval; best_i = i; }
+      }
+      out = static_cast<Tout>(values[best_i]);
+    }
+    if (in) y[b * ybs + static_cast<long long>(rows.out_index[k]) * Wo + cols.out_index[l]] = out;
+  }
+}
+
 // ------------------------------------------------------------------------------ stats
 template <typename T>
 __device__ __forceinline__ void bitonic_sort_warp(T* a, int n_pow2, int lane) {
@@ -298,8 +425,8 @@ struct ChunkPlan {
 template <typename Tin, typename Tout>
 int mode_launch(const void* x, void* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
                 const rg_bins_t* rows_c, const rg_bins_t* cols_c, int32_t cols_per_chunk, int32_t tile_elems,
-                const void* values_sorted, const int32_t* value_rank, const void* values, int32_t n_values,
-                int32_t dense, int32_t anti, double fill, cudaStream_t stream) {
+                int32_t strip_elems, const void* values_sorted, const int32_t* value_rank, const void* values,
+                int32_t n_values, int32_t dense, int32_t anti, double fill, cudaStream_t stream) {
   Bins rows, cols;
   int rc = make_bins(rows_c, &rows);
   if (rc != RG_OK) return rc;
@@ -308,6 +435,32 @@ int mode_launch(const void* x, void* y, int64_t batch, int64_t xbs, int64_t xrs,
   DeviceInfo dev;
   rc = device_info(&dev);
   if (rc != RG_OK) return rc;
+  // ---- throughput path: one cell per lane, lane-private counters (needs few labels and strips whose
+  //      source columns fit the per-warp staging buffer)
+  if (n_values <= kLaneMaxLabels && strip_elems > 0) {
+    const int stage_elems = (strip_elems + 48 + 15) / 16 * 16;  // slack: 16-byte phase + whole-word reads
+    const size_t smem_l = static_cast<size_t>(n_values + 1) * kLaneThreads * 4 +
+                          static_cast<size_t>(kLaneWarps) * kStageRows * stage_elems * sizeof(Tin);
+    if (smem_l <= 100 * 1024) {
+      auto kl = mode_lanes_kernel<Tin, Tout>;
+      if (smem_l > 48 * 1024)
+        RG_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_l)));
+      int per_sm_l = 0;
+      RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, kl, kLaneThreads, smem_l));
+      if (per_sm_l >= 1) {
+        const long long strips = (cols.n_out + 31) / 32;
+        const long long tasks_l = static_cast<long long>(batch) * rows.n_out * strips;
+        long long grid_l = static_cast<long long>(dev.sm_count) * per_sm_l * 2;
+        const long long need = (tasks_l + kLaneWarps - 1) / kLaneWarps;
+        if (grid_l > need) grid_l = need;
+        kl<<<static_cast<unsigned>(grid_l), kLaneThreads, smem_l, stream>>>(
+            static_cast<const Tin*>(x), static_cast<Tout*>(y), batch, xbs, xrs, ybs, rows, cols,
+            static_cast<const Tin*>(values_sorted), value_rank, static_cast<const Tin*>(values), n_values,
+            dense, anti, static_cast<Tout>(fill), stage_elems);
+        return static_cast<int>(cudaGetLastError());
+      }
+    }
+  }
   const size_t smem = (static_cast<size_t>(tile_elems) * sizeof(Tin) + 15) / 16 * 16 +
                       static_cast<size_t>(kRedWarps) * n_values * sizeof(int32_t);
   if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_SMEM;
@@ -368,9 +521,9 @@ extern "C" {
 
 int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t batch,
             int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride, const rg_bins_t* rows,
-            const rg_bins_t* cols, int32_t cols_per_chunk, int32_t tile_elems, const void* values_sorted,
-            const int32_t* value_rank, const void* values, int32_t n_values, int32_t dense,
-            int32_t anti_mode, double fill, void* stream) {
+            const rg_bins_t* cols, int32_t cols_per_chunk, int32_t tile_elems, int32_t strip_elems,
+            const void* values_sorted, const int32_t* value_rank, const void* values, int32_t n_values,
+            int32_t dense, int32_t anti_mode, double fill, void* stream) {
   if (!x || !y || !values || (!dense && (!values_sorted || !value_rank))) return RG_ERR_NULL;
   if (n_values <= 0 || cols_per_chunk <= 0 || tile_elems <= 0 || batch < 0) return RG_ERR_SHAPE;
   if (batch == 0) return RG_OK;
@@ -379,12 +532,12 @@ int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t b
   if (in_type == CODE) {                                                                                    \
     if (out_type == CODE)                                                                                   \
       return rg::mode_launch<TIN, TIN>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows,     \
-                                       cols, cols_per_chunk, tile_elems, values_sorted, value_rank, values, \
-                                       n_values, dense, anti_mode, fill, s);                                \
+                                       cols, cols_per_chunk, tile_elems, strip_elems, values_sorted,        \
+                                       value_rank, values, n_values, dense, anti_mode, fill, s);            \
     if (out_type == RG_F64)                                                                                 \
       return rg::mode_launch<TIN, double>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows,  \
-                                          cols, cols_per_chunk, tile_elems, values_sorted, value_rank,      \
-                                          values, n_values, dense, anti_mode, fill, s);                     \
+                                          cols, cols_per_chunk, tile_elems, strip_elems, values_sorted,     \
+                                          value_rank, values, n_values, dense, anti_mode, fill, s);         \
     return RG_ERR_UNSUPPORTED;                                                                              \
   }
   RG_MODE(RG_U8, uint8_t)

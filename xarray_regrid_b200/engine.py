@@ -518,11 +518,14 @@ class ReducePlan:
         B, Ho, Wo = x3.shape[0], rows.host.n_out, cols.host.n_out
         y = torch.empty((B, Ho, Wo), dtype=out_dtype, device=x3.device)
         cpc, tile = tables.plan_chunks(rows.host, cols.host, x3.element_size(), 8 * vals.size * 4)
+        ends = cols.host.start.astype(np.int64) + cols.host.count
+        first = np.arange(0, Wo, 32)
+        strip = int((ends[np.minimum(first + 31, Wo - 1)] - cols.host.start[first]).max())
         if B:
             check(
                 lib.rg_mode(x3.data_ptr(), y.data_ptr(), _TYPE_CODE[x3.dtype], _TYPE_CODE[out_dtype], B,
                             x3.stride(0) if B > 1 else x3.shape[1] * x3.stride(1), x3.stride(1), Ho * Wo,
-                            rows.ref, cols.ref, cpc, tile, vs_dev.data_ptr(), rank_dev.data_ptr(),
+                            rows.ref, cols.ref, cpc, tile, strip, vs_dev.data_ptr(), rank_dev.data_ptr(),
                             v_dev.data_ptr(), int(vals.size), int(dense), int(bool(anti_mode)), fill,
                             _stream_ptr(x3.device)),
                 "rg_mode",
