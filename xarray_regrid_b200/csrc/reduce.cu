@@ -157,6 +157,26 @@ mode_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long batch, lo
   }
 }
 
+// Stage one source row segment of a strip (columns p0 .. p0 + ncol of the formatted axis) into shared
+// memory.  Contiguous segments keep the source's 16-byte phase: element c lives at dst[shift + c] (shift is
+// returned), so every aligned 16-byte chunk is copied with one LDG.128 + one STS.128.
+template <typename T>
+__device__ __forceinline__ int stage_row(T* dst, const T* __restrict__ src, const Bins& cols, int p0, int s0,
+                                         int ncol, bool contiguous, int lane) {
+  if (contiguous) {
+    const T* seg = src + s0;
+    constexpr int V = 16 / sizeof(T);
+    const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(seg) & 15) / sizeof(T));
+    const int4* gsrc = reinterpret_cast<const int4*>(seg - shift);
+    int4* sdst = reinterpret_cast<int4*>(dst);
+    const int nvec = (shift + ncol + V - 1) / V;  // may read a few elements before / after the segment
+    for (int v = lane; v < nvec; v += 32) sdst[v] = __ldg(gsrc + v);
+    return shift;
+  }
+  for (int c = lane; c < ncol; c += 32) dst[c] = __ldg(src + src_index(cols, p0 + c));
+  return 0;
+}
+
 // ---------------------------------------------------------------- mode, one cell per lane
 // Throughput kernel for label counts: a warp owns a strip of 32 adjacent target cells of one target
 // row, ONE CELL PER LANE.  Each lane keeps its own counters in shared memory laid out [label][thread]
@@ -223,20 +243,7 @@ mode_lanes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long bat
       // ---- stage nrb rows x ncol columns (coalesced; 16-byte loads when the segment is aligned)
       for (int r = 0; r < nrb; ++r) {
         const Tin* src = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs;
-        Tin* dst = stage + r * stage_elems;
-        if (contiguous) {
-          // keep the source's 16-byte phase in shared memory: element c lives at dst[shift + c], so every
-          // aligned 16-byte chunk of the source is copied with one LDG.128 + one STS.128
-          const Tin* seg = src + s0;
-          constexpr int V = 16 / sizeof(Tin);
-          const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(seg) & 15) / sizeof(Tin));
-          const int4* gsrc = reinterpret_cast<const int4*>(seg - shift);
-          int4* sdst = reinterpret_cast<int4*>(dst);
-          const int nvec = (shift + ncol + V - 1) / V;  // may read a few elements before / after the segment
-          for (int v = lane; v < nvec; v += 32) sdst[v] = __ldg(gsrc + v);
-        } else {
-          for (int c = lane; c < ncol; c += 32) dst[c] = __ldg(src + src_index(cols, p0 + c));
-        }
+        stage_row<Tin>(stage + r * stage_elems, src, cols, p0, s0, ncol, contiguous, lane);
       }
       __syncwarp();
       // ---- every lane walks its own cell.  Branch-free: labels that are not listed go to a trash counter
@@ -282,6 +289,46 @@ mode_lanes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long bat
     }
     if (in) y[b * ybs + static_cast<long long>(rows.out_index[k]) * Wo + cols.out_index[l]] = out;
   }
+}
+
+// ---- warp-level selection of order statistics (median) -------------------------------------------
+// Values are mapped to order-preserving unsigned keys; every lane holds up to kSelCap keys of the cell in
+// registers and the warp determines the k-th smallest key bit by bit (MSB first) with one REDUX per bit.
+constexpr int kSelCap = 32;  // keys per lane -> cells of up to 1024 valid values
+
+__device__ __forceinline__ unsigned int to_key(float v) {
+  const unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_key(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ unsigned long long to_key(double v) {
+  const unsigned long long u = static_cast<unsigned long long>(__double_as_longlong(v));
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double from_key(unsigned long long k) {
+  return __longlong_as_double(static_cast<long long>((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
+// k-th smallest (0-based) of the valid keys spread over the warp's registers (bit i of `valid` marks slot i).
+template <typename K>
+__device__ __forceinline__ K warp_select(const K (&keys)[kSelCap], unsigned valid, int k) {
+  constexpr int BITS = sizeof(K) * 8;
+  K prefix = 0;
+  for (int b = BITS - 1; b >= 0; --b) {
+    // keys that agree with `prefix` on the bits above b and have bit b clear
+    const K want = prefix >> b;  // bit b of `want` is 0
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kSelCap; ++i) cnt += (((valid >> i) & 1u) && (keys[i] >> b) == want) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (k >= cnt) {
+      k -= cnt;
+      prefix |= static_cast<K>(1) << b;
+    }
+  }
+  return prefix;
 }
 
 // ------------------------------------------------------------------------------ stats
@@ -386,7 +433,45 @@ stat_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long lo
           }
           m2 = warp_sum(m2) / n;
           out = static_cast<T>(op == OP_STD ? sqrt(m2) : m2);
-        } else {  // OP_MEDIAN: gather the valid values, sort, average the two middle ones
+        } else if (nr <= kSelCap && nc <= 32) {
+          // OP_MEDIAN, cells of up to 32 x 32: lane c keeps column c of the cell (one key per row) in
+          // registers; bitwise radix select over the warp
+          using K = decltype(to_key(T(0)));
+          K keys[kSelCap];
+          unsigned valid = 0;
+#pragma unroll
+          for (int q = 0; q < kSelCap; ++q) {
+            T v = nan;
+            if (q < nr && lane < nc) v = tile[q * ncol + c0 + lane];
+            const bool ok = (v == v);
+            keys[q] = ok ? to_key(v) : K(0);
+            valid |= (ok ? 1u : 0u) << q;
+          }
+          const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
+          const K key_lo = warp_select<K>(keys, valid, k_lo);
+          K key_hi = key_lo;
+          if (k_hi != k_lo) {
+            // the next order statistic: the same value if it occurs often enough, else the smallest larger one
+            int le = 0;
+            K next = ~K(0);
+#pragma unroll
+            for (int i = 0; i < kSelCap; ++i) {
+              if ((valid >> i) & 1u) {
+                le += keys[i] <= key_lo ? 1 : 0;
+                if (keys[i] > key_lo && keys[i] < next) next = keys[i];
+              }
+            }
+            le = __reduce_add_sync(0xffffffffu, le);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const K other = __shfl_xor_sync(0xffffffffu, next, o);
+              next = other < next ? other : next;
+            }
+            key_hi = (le > k_hi) ? key_lo : next;
+          }
+          const double lo = static_cast<double>(from_key(key_lo)), hi = static_cast<double>(from_key(key_hi));
+          out = static_cast<T>((lo + hi) / 2);
+        } else {  // OP_MEDIAN, larger cells: gather the valid values, sort, average the two middle ones
           T* s = scratch + warp * sort_cap;
           int n_pow2 = 1;
           while (n_pow2 < n) n_pow2 <<= 1;
@@ -414,6 +499,102 @@ stat_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long lo
       if (lane == 0) yrow[cols.out_index[l]] = out;
     }
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------ stats, one cell per lane
+// sum / mean / min / max / var / std with the strip staging of the mode kernel: a warp owns 32 adjacent
+// target cells, every lane accumulates its own cell in registers (fp64 sums), no shuffles, no atomics.
+// With 25-column cells the lanes' shared-memory reads are conflict-free (stride 25 words, gcd(25, 32) = 1).
+// var / std make a second pass over the strip (re-staged, L2 hits) around the exact mean, like np.var.
+template <typename T>
+__global__ void __launch_bounds__(kLaneThreads)
+stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
+                  long long ybs, Bins rows, Bins cols, int op, int skipna, T fill, int stage_elems,
+                  int stage_rows) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  T* stage = reinterpret_cast<T*>(smem) + static_cast<size_t>(warp) * stage_rows * stage_elems;
+  const int Wo = cols.n_out;
+  const int strips = (Wo + 31) / 32;
+  const long long tasks = batch * rows.n_out * strips;
+  const long long warp_id = static_cast<long long>(blockIdx.x) * kLaneWarps + warp;
+  const long long n_warps = static_cast<long long>(gridDim.x) * kLaneWarps;
+  const T nan = quiet_nan<T>();
+
+  for (long long task = warp_id; task < tasks; task += n_warps) {
+    const int strip = static_cast<int>(task % strips);
+    const int k = static_cast<int>((task / strips) % rows.n_out);
+    const long long b = task / (static_cast<long long>(strips) * rows.n_out);
+    const int l = strip * 32 + lane;
+    const bool in = l < Wo;
+    const int l_last = min(strip * 32 + 31, Wo - 1);
+    const bool row_ok = rows.cover[k] != 0;
+    const int r0 = rows.start[k], nr = row_ok ? rows.count[k] : 0;
+    const int p0 = cols.start[strip * 32];
+    const int ncol = cols.start[l_last] + cols.count[l_last] - p0;  // host contract: <= stage_elems
+    const int c0 = in ? cols.start[l] - p0 : 0;
+    const int nc = (in && cols.cover[l]) ? cols.count[l] : 0;
+    const T* xb = x + b * xbs;
+    const int s0 = src_index(cols, p0);
+    const bool contiguous = cols.src_step == 1 && s0 + ncol <= cols.n_src;
+    const int row_first = src_index(rows, r0);
+
+    double sum = 0.0, m2 = 0.0, mean = 0.0;
+    int n = 0, n_nan = 0;
+    T vmin = CUDART_INF, vmax = -CUDART_INF;
+    const int passes = (op == OP_VAR || op == OP_STD) ? 2 : 1;
+    for (int pass = 0; pass < passes; ++pass) {
+      for (int rb = 0; rb < nr; rb += stage_rows) {
+        const int nrb = min(stage_rows, nr - rb);
+        __syncwarp();
+        for (int r = 0; r < nrb; ++r) {
+          const T* src = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs;
+          stage_row<T>(stage + r * stage_elems, src, cols, p0, s0, ncol, contiguous, lane);
+        }
+        __syncwarp();
+        for (int r = 0; r < nrb; ++r) {
+          int sh = 0;  // the row's 16-byte phase (see stage_row)
+          if (contiguous) {
+            const T* seg = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs + s0;
+            sh = static_cast<int>((reinterpret_cast<uintptr_t>(seg) & 15) / sizeof(T));
+          }
+          const T* trow = stage + r * stage_elems + sh + c0;
+          if (pass == 0) {
+            for (int c = 0; c < nc; ++c) {
+              const T v = trow[c];
+              if (v == v) {
+                sum += static_cast<double>(v);
+                ++n;
+                vmin = v < vmin ? v : vmin;
+                vmax = v > vmax ? v : vmax;
+              } else {
+                ++n_nan;
+              }
+            }
+          } else {
+            for (int c = 0; c < nc; ++c) {
+              const T v = trow[c];
+              if (v == v) { const double d = static_cast<double>(v) - mean; m2 += d * d; }
+            }
+          }
+        }
+      }
+      if (pass == 0 && n > 0) mean = sum / n;
+    }
+    T out = fill;
+    if (row_ok && in && cols.cover[l]) {
+      const bool poisoned = !skipna && n_nan > 0;
+      if (poisoned) out = nan;
+      else if (n == 0) out = (op == OP_SUM) ? T(0) : nan;
+      else if (op == OP_SUM) out = static_cast<T>(sum);
+      else if (op == OP_MEAN) out = static_cast<T>(mean);
+      else if (op == OP_MIN) out = vmin;
+      else if (op == OP_MAX) out = vmax;
+      else if (op == OP_VAR) out = static_cast<T>(m2 / n);
+      else out = static_cast<T>(sqrt(m2 / n));
+    }
+    if (in) y[b * ybs + static_cast<long long>(rows.out_index[k]) * Wo + cols.out_index[l]] = out;
   }
 }
 
@@ -484,7 +665,8 @@ int mode_launch(const void* x, void* y, int64_t batch, int64_t xbs, int64_t xrs,
 template <typename T>
 int stat_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
                 const rg_bins_t* rows_c, const rg_bins_t* cols_c, int32_t cols_per_chunk, int32_t tile_elems,
-                int32_t op, int32_t skipna, int32_t sort_cap, double fill, cudaStream_t stream) {
+                int32_t op, int32_t skipna, int32_t sort_cap, int32_t strip_elems, double fill,
+                cudaStream_t stream) {
   if (!x || !y) return RG_ERR_NULL;
   if (op < OP_SUM || op > OP_MEDIAN || cols_per_chunk <= 0 || tile_elems <= 0) return RG_ERR_SHAPE;
   Bins rows, cols;
@@ -496,6 +678,30 @@ int stat_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64
   DeviceInfo dev;
   rc = device_info(&dev);
   if (rc != RG_OK) return rc;
+  // ---- throughput path (everything but the median): one cell per lane
+  if (op != OP_MEDIAN && strip_elems > 0) {
+    const int stage_elems = (strip_elems + 48 + 15) / 16 * 16;
+    int stage_rows = static_cast<int>((56 * 1024) / (static_cast<size_t>(kLaneWarps) * stage_elems * sizeof(T)));
+    if (stage_rows > 8) stage_rows = 8;
+    if (stage_rows >= 1) {
+      const size_t smem_l = static_cast<size_t>(kLaneWarps) * stage_rows * stage_elems * sizeof(T);
+      auto kl = stat_lanes_kernel<T>;
+      if (smem_l > 48 * 1024)
+        RG_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_l)));
+      int per_sm_l = 0;
+      RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, kl, kLaneThreads, smem_l));
+      if (per_sm_l >= 1) {
+        const long long strips = (cols.n_out + 31) / 32;
+        const long long tasks_l = static_cast<long long>(batch) * rows.n_out * strips;
+        long long grid_l = static_cast<long long>(dev.sm_count) * per_sm_l * 2;
+        const long long need = (tasks_l + kLaneWarps - 1) / kLaneWarps;
+        if (grid_l > need) grid_l = need;
+        kl<<<static_cast<unsigned>(grid_l), kLaneThreads, smem_l, stream>>>(
+            x, y, batch, xbs, xrs, ybs, rows, cols, op, skipna, static_cast<T>(fill), stage_elems, stage_rows);
+        return static_cast<int>(cudaGetLastError());
+      }
+    }
+  }
   const size_t smem = (static_cast<size_t>((tile_elems + 3) / 4 * 4) +
                        (op == OP_MEDIAN ? static_cast<size_t>(kRedWarps) * sort_cap : 0)) * sizeof(T);
   if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_SMEM;
@@ -552,18 +758,18 @@ int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t b
 int rg_stat_f64(const double* x, double* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
                 int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
                 int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
-                double fill, void* stream) {
+                int32_t strip_elems, double fill, void* stream) {
   return rg::stat_launch<double>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows, cols,
-                                 cols_per_chunk, tile_elems, op, skipna, sort_cap, fill,
+                                 cols_per_chunk, tile_elems, op, skipna, sort_cap, strip_elems, fill,
                                  static_cast<cudaStream_t>(stream));
 }
 
 int rg_stat_f32(const float* x, float* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
                 int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
                 int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
-                double fill, void* stream) {
+                int32_t strip_elems, double fill, void* stream) {
   return rg::stat_launch<float>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows, cols,
-                                cols_per_chunk, tile_elems, op, skipna, sort_cap, fill,
+                                cols_per_chunk, tile_elems, op, skipna, sort_cap, strip_elems, fill,
                                 static_cast<cudaStream_t>(stream));
 }
 

@@ -431,6 +431,13 @@ class DeviceBins:
         return C.byref(self.c)
 
 
+def _strip_elems(cols: tables.Bins) -> int:
+    """Max number of source columns spanned by 32 consecutive target columns (strip kernels)."""
+    ends = cols.start.astype(np.int64) + cols.count
+    first = np.arange(0, cols.n_out, 32)
+    return int((ends[np.minimum(first + 31, cols.n_out - 1)] - cols.start[first]).max())
+
+
 _STAT_CODE = {"sum": 0, "mean": 1, "var": 2, "std": 3, "min": 4, "max": 5, "median": 6}
 VALID_STAT_METHODS = ["sum", "mean", "var", "std", "median", "max", "min"]
 
@@ -518,9 +525,7 @@ class ReducePlan:
         B, Ho, Wo = x3.shape[0], rows.host.n_out, cols.host.n_out
         y = torch.empty((B, Ho, Wo), dtype=out_dtype, device=x3.device)
         cpc, tile = tables.plan_chunks(rows.host, cols.host, x3.element_size(), 8 * vals.size * 4)
-        ends = cols.host.start.astype(np.int64) + cols.host.count
-        first = np.arange(0, Wo, 32)
-        strip = int((ends[np.minimum(first + 31, Wo - 1)] - cols.host.start[first]).max())
+        strip = _strip_elems(cols.host)
         if B:
             check(
                 lib.rg_mode(x3.data_ptr(), y.data_ptr(), _TYPE_CODE[x3.dtype], _TYPE_CODE[out_dtype], B,
@@ -555,7 +560,7 @@ class ReducePlan:
             check(
                 fn(x3.data_ptr(), y.data_ptr(), B, x3.stride(0) if B > 1 else x3.shape[1] * x3.stride(1),
                    x3.stride(1), Ho * Wo, rows.ref, cols.ref, cpc, tile, _STAT_CODE[method],
-                   int(bool(skipna)), sort_cap, fill, _stream_ptr(x3.device)),
+                   int(bool(skipna)), sort_cap, _strip_elems(cols.host), fill, _stream_ptr(x3.device)),
                 "rg_stat",
             )
         return y.view(tuple(lead) + (Ho, Wo))
