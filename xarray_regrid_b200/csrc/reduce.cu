@@ -180,7 +180,8 @@ __device__ __forceinline__ int stage_row(T* dst, const T* __restrict__ src, cons
 // ---------------------------------------------------------------- mode, one cell per lane
 // Throughput kernel for label counts: a warp owns a strip of 32 adjacent target cells of one target
 // row, ONE CELL PER LANE.  Each lane keeps its own counters in shared memory laid out [label][thread]
-// (bank = lane: conflict-free, no atomics, no voting); the warp stages kStageRows source rows of its strip at
+// (bank = lane: conflict-free; the increment is a fire-and-forget shared atomic on a word no other lane
+// touches, which is cheaper than LDS + IADD + STS; no voting); the warp stages kStageRows source rows of its strip at
 // a time with 16-byte coalesced loads and every lane walks its own cell.  Needs n_values <= kLaneMaxLabels.
 constexpr int kLaneThreads = 256;
 constexpr int kLaneWarps = kLaneThreads / 32;
@@ -259,18 +260,18 @@ mode_lanes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long bat
         if (dense) {
           for (int c = 0; c < nc_min; ++c) {  // every lane's cell has this column: no per-lane predicate
             const unsigned v = static_cast<unsigned>(static_cast<long long>(trow[c]));
-            mine[min(v, static_cast<unsigned>(n_values)) * lane_stride] += 1;
+            atomicAdd(mine + min(v, static_cast<unsigned>(n_values)) * lane_stride, 1u);
           }
           for (int c = nc_min; c < nc_max; ++c) {  // ragged tail
             const unsigned v = static_cast<unsigned>(static_cast<long long>(trow[c < nc_eff ? c : 0]));
             const unsigned d = (c < nc_eff && v < static_cast<unsigned>(n_values)) ? v : static_cast<unsigned>(n_values);
-            mine[d * lane_stride] += 1;
+            atomicAdd(mine + d * lane_stride, 1u);  // fire-and-forget ATOMS on a lane-private word
           }
         } else {
           for (int c = 0; c < nc_max; ++c) {
             int d = label_index(trow[c < nc_eff ? c : 0], values_sorted, n_values, 0);
             d = (c < nc_eff && d >= 0) ? value_rank[d] : n_values;
-            mine[d * lane_stride] += 1;
+            atomicAdd(mine + d * lane_stride, 1u);  // fire-and-forget ATOMS on a lane-private word
           }
         }
       }
