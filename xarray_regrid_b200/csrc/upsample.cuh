@@ -19,7 +19,7 @@
 
 namespace rg {
 
-constexpr int kUpThreads = 256;
+constexpr int kUpMaxThreads = 512;
 constexpr int kUpRowCap = 16;      // source rows held in shared memory
 constexpr int kUpBandRows = 32;    // output rows per task
 constexpr int kUpRowsPerSync = 4;  // output rows produced per barrier
@@ -40,7 +40,7 @@ __device__ __forceinline__ void st_stream4(double* p, const Vec4<double>& a) {
 
 // Rows [kb, kb + nk) of a band: latitude pass into the z buffers of parity BUF, one barrier, longitude
 // pass + stores.  BUF and the row slot are compile-time so that every z read is LDS [reg + immediate].
-template <typename T, int KR, int KC, int G, int ZW, int BUF>
+template <typename T, int KR, int KC, int G, int ZW, int NT, int BUF>
 __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, int nk, int W, int Wo,
                                         const T* s_x, T* s_z, const int (*s_off)[KR], const T (*s_rw)[KR],
                                         const int* s_state, const int (&ci)[G][4][KC], const T (&cw)[G][4][KC],
@@ -53,7 +53,7 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
 #pragma unroll
     for (int t = 0; t < KR; ++t) { off[t] = s_off[m][t]; w[t] = s_rw[m][t]; }
     T* z = s_z + (BUF * kUpRowsPerSync + q) * ZW;
-    for (int j = tid; j < W; j += kUpThreads) {
+    for (int j = tid; j < W; j += NT) {
       T acc = T(0);
 #pragma unroll
       for (int t = 0; t < KR; ++t) acc = fma(w[t], s_x[off[t] + j], acc);
@@ -70,7 +70,7 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
       const int state = s_state[kb_local + q];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const int l = (tid + g * kUpThreads) * 4;
+        const int l = (tid + g * NT) * 4;
         if (l < Wo) {
           Vec4<T> out;
 #pragma unroll
@@ -98,8 +98,8 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
   }
 }
 
-template <typename T, int KR, int KC, int G, int ZW>
-__global__ void __launch_bounds__(kUpThreads)
+template <typename T, int KR, int KC, int G, int ZW, int NT>
+__global__ void __launch_bounds__(NT)
 upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
                 long long ybs, Band<T> rows, Band<T> cols, int band_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -123,7 +123,7 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
   for (int g = 0; g < G; ++g) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int l = (tid + g * kUpThreads) * 4 + e;
+      const int l = (tid + g * NT) * 4 + e;
       const bool in = l < Wo;
       const int n = in ? cols.cnt[l] : 0;
 #pragma unroll
@@ -182,18 +182,18 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
       const int wn = min(kUpRowCap, H - w0);
       for (int r = 0; r < wn; ++r) {
         const T* src = xb + static_cast<long long>(w0 + r) * xrs;
-        for (int j = tid; j < W; j += kUpThreads) s_x[r * W + j] = __ldg(src + j);
+        for (int j = tid; j < W; j += NT) s_x[r * W + j] = __ldg(src + j);
       }
     }
     __syncthreads();
 
     T* y_band = y + b * ybs + static_cast<long long>(k0) * Wo;
     for (int kl = 0; kl < k1 - k0; kl += 2 * kUpRowsPerSync) {
-      up_rows<T, KR, KC, G, ZW, 0>(y_band, kl, min(kUpRowsPerSync, k1 - k0 - kl), W, Wo, s_x, s_z, s_off, s_rw,
+      up_rows<T, KR, KC, G, ZW, NT, 0>(y_band, kl, min(kUpRowsPerSync, k1 - k0 - kl), W, Wo, s_x, s_z, s_off, s_rw,
                                    s_state, ci, cw, tid, nan);
       const int kl2 = kl + kUpRowsPerSync;
       if (kl2 < k1 - k0)
-        up_rows<T, KR, KC, G, ZW, 1>(y_band, kl2, min(kUpRowsPerSync, k1 - k0 - kl2), W, Wo, s_x, s_z, s_off,
+        up_rows<T, KR, KC, G, ZW, NT, 1>(y_band, kl2, min(kUpRowsPerSync, k1 - k0 - kl2), W, Wo, s_x, s_z, s_off,
                                      s_rw, s_state, ci, cw, tid, nan);
     }
     __syncthreads();
@@ -208,14 +208,16 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   const int W = cols.n_src, Wo = cols.n_out;
   if (rows.k_max > 4 || cols.k_max > 4) return RG_ERR_UNSUPPORTED;
   if (rows_span <= 0 || rows_span > kUpRowCap) return RG_ERR_UNSUPPORTED;
-  if (Wo < 2 * W || Wo > kUpThreads * 4 * 4) return RG_ERR_UNSUPPORTED;  // upsampling, <= 4 groups / thread
+  // heavy taps (4 fp64 taps per column) use 512-thread CTAs so that the per-thread tap registers halve
+  const int nt = (cols.k_max > 2 && sizeof(T) == 8) ? 512 : 256;
+  if (Wo < 2 * W || Wo > nt * 4 * 4) return RG_ERR_UNSUPPORTED;  // upsampling, <= 4 groups / thread
   if ((reinterpret_cast<uintptr_t>(y) % 16) != 0 || (ybs * sizeof(T)) % 16 != 0 || (Wo * sizeof(T)) % 16 != 0)
     return RG_ERR_UNSUPPORTED;
   if (W > 1024) return RG_ERR_UNSUPPORTED;
   const int zw = W <= 512 ? 512 : 1024;
   const size_t smem = (static_cast<size_t>(kUpRowCap) * W + 2 * kUpRowsPerSync * zw) * sizeof(T);
   if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_UNSUPPORTED;
-  const int groups = ((Wo + 3) / 4 + kUpThreads - 1) / kUpThreads;  // 1..4
+  const int groups = ((Wo + 3) / 4 + nt - 1) / nt;  // 1..4
   const int kr = rows.k_max <= 1 ? 1 : rows.k_max <= 2 ? 2 : 4;
   const int kc = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : 4;
   using Kernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, Band<T>, int);
@@ -227,9 +229,14 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   band_rows = band_rows / kUpRowsPerSync * kUpRowsPerSync;
   if (band_rows < kUpRowsPerSync) return RG_ERR_UNSUPPORTED;
   Kernel kern = nullptr;
-#define RG_UP(KR_, KC_, G_)                                                                     \
-  if (kr == KR_ && kc == KC_ && groups == G_)                                                   \
-    kern = zw == 512 ? upsample_kernel<T, KR_, KC_, G_, 512> : upsample_kernel<T, KR_, KC_, G_, 1024>;
+#define RG_UP(KR_, KC_, G_)                                                                              \
+  if (kr == KR_ && kc == KC_ && groups == G_) {                                                          \
+    if (nt == 256)                                                                                       \
+      kern = zw == 512 ? upsample_kernel<T, KR_, KC_, G_, 512, 256> : upsample_kernel<T, KR_, KC_, G_, 1024, 256>; \
+    else if (G_ <= 2)                                                                                    \
+      kern = zw == 512 ? upsample_kernel<T, KR_, KC_, (G_ <= 2 ? G_ : 1), 512, 512>                      \
+                       : upsample_kernel<T, KR_, KC_, (G_ <= 2 ? G_ : 1), 1024, 512>;                    \
+  }
 #define RG_UP_G(KR_, KC_) RG_UP(KR_, KC_, 1) RG_UP(KR_, KC_, 2) RG_UP(KR_, KC_, 3) RG_UP(KR_, KC_, 4)
   RG_UP_G(1, 1) RG_UP_G(2, 2) RG_UP_G(4, 4)
 #undef RG_UP_G
@@ -238,13 +245,13 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   if (smem > 48 * 1024)
     RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
-  RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kUpThreads, smem));
+  RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
   if (per_sm < 1) return RG_ERR_UNSUPPORTED;
   const int n_bands = (rows.n_out + band_rows - 1) / band_rows;
   const long long tasks = static_cast<long long>(batch) * n_bands;
   long long grid = static_cast<long long>(dev.sm_count) * per_sm;
   if (grid > tasks) grid = tasks;
-  kern<<<static_cast<unsigned>(grid), kUpThreads, smem, stream>>>(x, y, batch, xbs, xrs, ybs, rows, cols,
+  kern<<<static_cast<unsigned>(grid), nt, smem, stream>>>(x, y, batch, xbs, xrs, ybs, rows, cols,
                                                                  band_rows);
   return static_cast<int>(cudaGetLastError());
 }
