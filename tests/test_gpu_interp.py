@@ -178,3 +178,21 @@ def test_single_axis_and_leading_dims(engine):
         want = oi.regrid(x, [src], [tgt], [-2], method)
         assert y.shape == (2, 3, tgt.size, 9)
         _check(y, want, 1e-11, 1e-13)
+
+
+def test_empty_batch_and_ragged_shapes(engine):
+    """Empty stacks, a 1-row / 1-column source axis for nearest, and widths that defeat 16-byte alignment."""
+    lat, lon = np.arange(0.0, 7.0, 1.0), np.arange(0.0, 9.0, 1.0)
+    tlat, tlon = np.arange(0.5, 6.0, 0.5), np.arange(0.25, 8.0, 0.75)
+    for method in ("linear", "nearest", "cubic"):
+        plan = engine.InterpPlan(engine.AxisSpec(lat, tlat), engine.AxisSpec(lon, tlon), method)
+        y = plan(torch.empty((0, 7, 9), dtype=torch.float64, device="cuda"))
+        assert y.shape == (0, tlat.size, tlon.size)
+        rng = np.random.default_rng(21)
+        x = rng.random((5, 7, 9))
+        _check(plan(torch.from_numpy(x).cuda()), oi.regrid(x, [lat, lon], [tlat, tlon], [-2, -1], method),
+               1e-11, 1e-13)
+    with pytest.raises(ValueError):
+        engine.InterpPlan(engine.AxisSpec(lat, tlat), None, "quadratic")
+    with pytest.raises(ValueError):
+        engine.InterpPlan(engine.AxisSpec(np.arange(3.0), tlat), None, "cubic")  # needs >= 4 points (scipy)

@@ -183,3 +183,22 @@ def test_errors(engine):
         plan.stat(torch.zeros((11, 11), device="cuda"), "mode")  # flox_reduce.py:70-73
     with pytest.raises(ValueError):
         plan.mode(torch.zeros((11, 11), device="cuda"), LABELS)  # flox_reduce.py:156-162
+
+
+def test_empty_batch_large_bins_and_median_paths(engine):
+    """Empty stack; bins wider than 32 columns (bitonic median path); many labels (tile + match.any path)."""
+    rng = np.random.default_rng(22)
+    lat, lon = np.arange(0.5, 40, 1.0), np.arange(0.5, 200, 1.0)
+    tlat, tlon = np.arange(5.0, 40, 10.0), np.arange(25.0, 200, 50.0)  # 10 x 50 cells per bin
+    plan = _plan(engine, lat, lon, tlat, tlon)
+    assert plan.stat(torch.empty((0, lat.size, lon.size), device="cuda"), "mean").shape == (0, 4, 4)
+    x = rng.normal(size=(2, lat.size, lon.size))
+    x[rng.random(x.shape) < 0.05] = np.nan
+    for skipna in (False, True):
+        y = plan.stat(torch.from_numpy(x).cuda(), "median", skipna=skipna).cpu().numpy()
+        want = orr.stat(x, [lat, lon], [tlat, tlon], [-2, -1], "median", skipna=skipna)
+        np.testing.assert_array_equal(y, want)
+    labels = np.arange(100)  # > 64 labels: the warp-per-cell kernel
+    xi = rng.integers(0, 100, size=(2, lat.size, lon.size)).astype(np.int16)
+    y = plan.mode(torch.from_numpy(xi).cuda(), labels).cpu().numpy()
+    np.testing.assert_array_equal(y, orr.mode(xi, [lat, lon], [tlat, tlon], [-2, -1], labels))

@@ -131,3 +131,108 @@ def test_row_ring_schedule_rejects_pole_rows():
                                     np.arange(-90.0, 91, 1), spherical=True)
     if (rows.idx >= rows.n_src).any():
         assert tables.row_ring_schedule(rows, 1) is None
+
+
+# ------------------------------------------------------------------ interpolation / bin tables (CPU)
+from oracle import interp as oi  # noqa: E402
+from oracle import reduce as orr  # noqa: E402
+
+
+def _apply_band(band, y, n_src=None):
+    """Dense application of a band along the last axis, NaN poisoning through every tap like the kernels."""
+    n_src = band.n_src if n_src is None else n_src
+    out = np.zeros(y.shape[:-1] + (band.n_out,))
+    for o in range(band.n_out):
+        acc = np.zeros(y.shape[:-1])
+        for t in range(band.cnt[o]):
+            acc = acc + band.w[t, o] * y[..., band.idx[t, o]]
+        out[..., o] = acc if band.cover[o] else np.nan
+    return out
+
+
+@pytest.mark.parametrize("method", ["linear", "nearest", "cubic"])
+@pytest.mark.parametrize(
+    "src,tgt",
+    [
+        (np.arange(0.0, 40.0, 1.0), np.linspace(-1, 41, 97)),          # upsampling, targets outside
+        (np.arange(0.0, 40.0, 0.25), np.arange(0.5, 39.0, 1.7)),        # downsampling
+        (np.sort(np.random.default_rng(3).uniform(0, 50, 31)), np.linspace(1, 49, 40)),  # irregular source
+        (np.arange(10.0, 0.0, -0.5), np.arange(9.5, 0.4, -0.75)),       # descending source and target
+    ],
+)
+def test_interp_bands_match_scipy(method, src, tgt):
+    rng = np.random.default_rng(0)
+    y = rng.random((3, src.size))
+    if method == "linear":
+        y[1, 4] = np.nan
+    ax = tables.plain_axis(src)
+    want = oi.regrid(y, [src], [tgt], [-1], method)
+    if method == "cubic":
+        pre, ev = tables.cubic_bands(ax, tgt)
+        got = _apply_band(ev, _apply_band(pre, y), n_src=ax.values.size)
+    else:
+        band = tables.linear_band(ax, tgt) if method == "linear" else tables.nearest_band(ax, tgt)
+        got = _apply_band(band, y)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+
+
+def test_nearest_ties_go_to_lower_neighbour():
+    ax = tables.plain_axis(np.arange(5.0))
+    idx, cover = tables.nearest_index(ax, np.array([0.5, 1.5, 2.5, 3.5, -0.1, 4.0, 4.1]))
+    np.testing.assert_array_equal(idx, [0, 1, 2, 3, 0, 4, 4])
+    np.testing.assert_array_equal(cover, [1, 1, 1, 1, 0, 1, 0])
+
+
+@pytest.mark.parametrize(
+    "src,tgt",
+    [
+        (np.linspace(0, 40, 11), np.arange(0.0, 41.0, 8.0)),            # reference tests/test_reduce.py grids
+        (np.linspace(0, 40, 11), np.arange(-8.0, 49.0, 8.0)),           # oversized target
+        (np.round(np.arange(-9.995, 10, 0.01), 3), np.arange(-10.0, 10.01, 0.25)),  # edges ON source centres
+        (np.arange(20.0, 0.0, -0.5), np.arange(18.0, 1.0, -2.0)),       # descending source and target
+    ],
+)
+def test_bins_match_oracle_membership(src, tgt):
+    """Bin tables against the oracle's digitize-based membership, coverage and target order."""
+    bins = tables.bins_axis(tables.plain_axis(src), tgt)
+    data = np.arange(src.size, dtype=np.float64)  # value = source index
+    want = orr.stat(data, [src], [tgt], [0], "sum")
+    want_n = orr.stat(np.ones(src.size), [src], [tgt], [0], "sum")
+    got = np.full(tgt.size, np.nan)
+    got_n = np.full(tgt.size, np.nan)
+    for o in range(bins.n_out):
+        pos = bins.start[o] + np.arange(bins.count[o])
+        idx = (bins.src_offset + bins.src_step * pos) % bins.n_src
+        if bins.cover[o]:
+            got[bins.out_index[o]] = data[idx].sum()
+            got_n[bins.out_index[o]] = idx.size
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_array_equal(np.nan_to_num(got), np.nan_to_num(want))
+    np.testing.assert_array_equal(np.nan_to_num(got_n), np.nan_to_num(want_n))
+
+
+def test_bins_with_longitude_wrap_padding():
+    """stats=True formatting keeps the wrap columns: a pole-centred 2 degree target over a cell-centred
+    1 degree source gets the wrapped column in its first bin (tests/test_format.py:182-218)."""
+    lon = np.arange(0.5, 360, 1.0)
+    tlon = np.arange(0.0, 361, 2.0)
+    ax = tables.format_lon_axis(lon, tlon)
+    assert ax.values[0] == -1.5 and ax.values[-1] == 361.5
+    bins = tables.bins_axis(ax, tlon)
+    assert bins.gather is None and bins.src_step == 1
+    first = (bins.src_offset + bins.start[0] + np.arange(bins.count[0])) % bins.n_src
+    np.testing.assert_array_equal(first, [359, 0])  # [-1, 1): the wrapped -0.5 and 0.5
+    assert bins.cover.all()
+
+
+def test_plan_chunks_respects_shared_memory_budget():
+    rows = tables.bins_axis(tables.plain_axis(np.round(np.arange(-89.995, 90, 0.01), 3)), np.arange(-89.875, 90, 0.25))
+    cols = tables.bins_axis(tables.plain_axis(np.round(np.arange(0.005, 360, 0.01), 3)), np.arange(0.125, 360, 0.25))
+    for esize in (1, 4, 8):
+        cpc, tile = tables.plan_chunks(rows, cols, esize)
+        assert tile * esize <= 72 * 1024 and tile >= 25 * 25 * min(cpc, 1)
+    with pytest.raises(NotImplementedError):
+        big = tables.Bins(np.array([0], np.int32), np.array([2000], np.int32), np.ones(1, np.uint8),
+                          np.zeros(1, np.int32), 2000, 0, 1)
+        tables.plan_chunks(big, big, 8)
