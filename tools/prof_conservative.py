@@ -18,6 +18,7 @@ ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--no-ring", action="store_true")
 ap.add_argument("--no-skipna", action="store_true")
 ap.add_argument("--dtype", default="f64")
+ap.add_argument("--nan", type=float, default=0.10)
 a = ap.parse_args()
 
 lat, lon = synthetic.grid_025()
@@ -25,7 +26,7 @@ tlat, tlon = synthetic.grid_1()
 plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"))
 plan.use_ring = not a.no_ring
 dtype = torch.float64 if a.dtype == "f64" else torch.float32
-x = synthetic.conservative_stack(a.steps, lat, lon, dtype=dtype, nan_fraction=0.10)
+x = synthetic.conservative_stack(a.steps, lat, lon, dtype=dtype, nan_fraction=a.nan)
 y = torch.empty((a.steps, 181, 360), dtype=dtype, device="cuda")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.launches + 1)]
 ev[0].record()

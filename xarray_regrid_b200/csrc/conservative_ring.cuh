@@ -105,6 +105,23 @@ __device__ __forceinline__ void st_release_smem(uint32_t addr, uint32_t v) {
   asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// so / sv for the normalisation step.  fp64: hardware reciprocal seed + two Newton steps + one residual
+// correction of the quotient (9 instructions instead of the ~35 of the IEEE division routine).  sv is a
+// valid mass in [valid_thr, 1 + eps] and so a weighted mean of the data, so the special-case handling of
+// the full routine is not needed; the result is within 1 ulp of the correctly rounded quotient (and equal
+// to it in all but rare cases), far inside the 1e-12 parity tolerance.
+__device__ __forceinline__ double normalise_div(double so, double sv) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(sv));
+  double e = fma(-sv, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-sv, r, 1.0);
+  r = fma(r, e, r);
+  const double q = so * r;
+  return fma(fma(-sv, q, so), r, q);
+}
+__device__ __forceinline__ float normalise_div(float so, float sv) { return so / sv; }
+
 // {t, v} entry of the warp-private strip buffer.
 template <typename T, bool SKIPNA> struct TV;
 template <typename T> struct alignas(2 * sizeof(T)) TV<T, true> { T t, v; };
@@ -355,7 +372,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
               so = fma(tw[i], e[i].t, so);
               if constexpr (SKIPNA) sv = fma(tw[i], e[i].v, sv);
             }
-            if constexpr (SKIPNA) out = (sv >= thr) ? so / sv : nan;
+            if constexpr (SKIPNA) out = (sv >= thr) ? normalise_div(so, sv) : nan;
             else out = so;
           }
           st_stream(yrow + l0 + lane, out);
