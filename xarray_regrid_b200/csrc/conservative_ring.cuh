@@ -272,8 +272,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
         const int run = static_cast<int>(task % ring.n_runs);
         const int n = ring.run_sched[run + 1] - ring.run_sched[run];
         for (int i = 0; i < n; ++i) {
-          while (!mbar_try_wait(full0 + 8u * slot, parity)) {
-          }
+          while (!mbar_try_wait(full0 + 8u * slot, parity)) __nanosleep(32);  // do not steal issue slots
           st_release_smem(flags0, ++g);  // rows [0, g) are in the ring and visible
           if (++slot == ring_slots) { slot = 0; parity ^= 1; }
         }
@@ -330,7 +329,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
       const int cnt = rec.z > 0 ? rec.z : 0;
 
       // ---- wait until every row this output needs has landed in the ring
-      while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(32);
+      while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(100);
       newest += static_cast<int>(need_g - newest_g);
       newest_g = need_g;
       if (newest >= ring_slots) newest -= ring_slots;
