@@ -281,13 +281,17 @@ typedef struct rg_bins {
  *   cols_per_chunk target columns staged per CTA; tile_elems >= rows-per-bin * source columns of any chunk
  *   strip_elems    max source columns spanned by 32 consecutive target columns (0 = unknown): enables the
  *                  one-cell-per-lane throughput kernel when n_values <= 64
+ *   max_bin_rows, max_bin_cols   largest number of source rows / columns in one target cell (0 = unknown):
+ *                  with dense labels, n_values <= 32, cells of <= 32 columns and <= 4095 source cells the
+ *                  counters live bit-sliced in registers (carry-save adder kernel)
  *   in_type        RG_U8 / RG_I8 / RG_I16 / RG_I32 / RG_I64; out_type = in_type or RG_F64 (NaN fill)
  */
 int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t batch,
             int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
             const rg_bins_t* rows, const rg_bins_t* cols, int32_t cols_per_chunk, int32_t tile_elems,
-            int32_t strip_elems, const void* values_sorted, const int32_t* value_rank, const void* values,
-            int32_t n_values, int32_t dense, int32_t anti_mode, double fill, void* stream);
+            int32_t strip_elems, int32_t max_bin_rows, int32_t max_bin_cols, const void* values_sorted,
+            const int32_t* value_rank, const void* values, int32_t n_values, int32_t dense, int32_t anti_mode,
+            double fill, void* stream);
 
 /* Statistic codes of rg_stat_*. */
 #define RG_STAT_SUM 0

@@ -91,8 +91,8 @@ def _load():
         "rg_nan_flag_f32": (C.c_int, [p, i64, i32, i32, i64, i64, p, p]),
         "rg_poison_if_f64": (C.c_int, [p, i64, p, p]),
         "rg_poison_if_f32": (C.c_int, [p, i64, p, p]),
-        "rg_mode": (C.c_int, [p, p, i32, i32, i64, i64, i64, i64, bins, bins, i32, i32, i32, p, p, p, i32, i32,
-                              i32, f64, p]),
+        "rg_mode": (C.c_int, [p, p, i32, i32, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, p, p, p,
+                              i32, i32, i32, f64, p]),
         "rg_stat_f64": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, i32, f64, p]),
         "rg_stat_f32": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, i32, f64, p]),
         "rg_conservative_host_workspace": (sz, [i64, i32, i32, i32, i32, i32]),

@@ -177,6 +177,34 @@ __device__ __forceinline__ int stage_row(T* dst, const T* __restrict__ src, cons
   return 0;
 }
 
+// Asynchronous variant: contiguous segments go through LDGSTS (cp.async, 16 bytes per lane and request) so a
+// warp can put several rows in flight without holding them in registers; the caller commits the group and
+// waits (cp_async_wait) before reading.  Gathered segments fall back to the synchronous copy.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_row_async(T* dst, const T* __restrict__ src, const Bins& cols, int p0, int s0,
+                                                int ncol, bool contiguous, int lane) {
+  if (contiguous) {
+    const T* seg = src + s0;
+    constexpr int V = 16 / sizeof(T);
+    const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(seg) & 15) / sizeof(T));
+    const int4* gsrc = reinterpret_cast<const int4*>(seg - shift);
+    int4* sdst = reinterpret_cast<int4*>(dst);
+    const int nvec = (shift + ncol + V - 1) / V;
+    for (int v = lane; v < nvec; v += 32) cp_async_16(sdst + v, gsrc + v);
+    return;
+  }
+  for (int c = lane; c < ncol; c += 32) dst[c] = __ldg(src + src_index(cols, p0 + c));
+}
+
 // ---------------------------------------------------------------- mode, one cell per lane
 // Throughput kernel for label counts: a warp owns a strip of 32 adjacent target cells of one target
 // row, ONE CELL PER LANE.  Each lane keeps its own counters in shared memory laid out [label][thread]
@@ -503,6 +531,164 @@ stat_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long lo
   }
 }
 
+// ------------------------------------------------- mode, bit-sliced counters in registers
+// For <= 32 dense labels the per-label counters of a lane's cell are kept BIT-SLICED in registers: plane b
+// holds bit b of all 32 counters (bit j of the word = label j).  A row of the cell is turned into one-hot
+// masks (1 << label), the masks are summed per bit position with a carry-save adder tree (LOP3 full adders:
+// 3-input XOR and majority), and the resulting 6-bit column sums are added to the planes with one ripple
+// pass.  No shared-memory read-modify-write, no atomics: ~3 ALU instructions per element.
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t onehot(uint32_t label) {
+  uint32_t r;  // PTX shl clamps the shift amount: labels >= 32 give 0
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(1u), "r"(label));
+  return r;
+}
+
+#include "csa_networks.inc"  // csa_sum<N>(m, s): generated Wallace trees (tools/gen_csa.py)
+
+constexpr int kPlanes = 12;  // counters up to 4095 per label and cell (the launcher checks the cell size)
+
+template <typename Tin, typename Tout, int NIN>
+__global__ void __launch_bounds__(kLaneThreads, 3)
+mode_planes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long batch, long long xbs, long long xrs,
+                   long long ybs, Bins rows, Bins cols, const Tin* __restrict__ values, int n_values, int anti,
+                   Tout fill, int stage_elems, int stage_rows) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Tin* stage = reinterpret_cast<Tin*>(smem) + static_cast<size_t>(warp) * 2 * stage_rows * stage_elems;
+  const int Wo = cols.n_out;
+  const int strips = (Wo + 31) / 32;
+  const long long tasks = batch * rows.n_out * strips;
+  const long long warp_id = static_cast<long long>(blockIdx.x) * kLaneWarps + warp;
+  const long long n_warps = static_cast<long long>(gridDim.x) * kLaneWarps;
+  const uint32_t label_mask = n_values >= 32 ? 0xffffffffu : ((1u << n_values) - 1u);
+
+  for (long long task = warp_id; task < tasks; task += n_warps) {
+    const int strip = static_cast<int>(task % strips);
+    const int k = static_cast<int>((task / strips) % rows.n_out);
+    const long long b = task / (static_cast<long long>(strips) * rows.n_out);
+    const int l = strip * 32 + lane;
+    const bool in = l < Wo;
+    const int l_last = min(strip * 32 + 31, Wo - 1);
+    const bool row_ok = rows.cover[k] != 0;
+    const int r0 = rows.start[k], nr = row_ok ? rows.count[k] : 0;
+    const int p0 = cols.start[strip * 32];
+    const int ncol = cols.start[l_last] + cols.count[l_last] - p0;  // host contract: <= stage_elems
+    const int c0 = in ? cols.start[l] - p0 : 0;
+    const int nc = (in && cols.cover[l]) ? cols.count[l] : 0;       // host contract: <= NIN
+    const Tin* xb = x + b * xbs;
+    const int s0 = src_index(cols, p0);
+    const bool contiguous = cols.src_step == 1 && s0 + ncol <= cols.n_src;
+    const int row_first = src_index(rows, r0);
+
+    uint32_t plane[kPlanes];
+#pragma unroll
+    for (int q = 0; q < kPlanes; ++q) plane[q] = 0;
+    // byte labels: columns past this lane's cell width are forced to 0xff (one-hot of 255 = 0), one OR per
+    // word instead of a compare + select per element
+    constexpr int kPadWords = (NIN + 3) / 4;
+    uint32_t pad[kPadWords];
+#pragma unroll
+    for (int q = 0; q < kPadWords; ++q) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w |= (4 * q + e >= nc) ? (0xffu << (8 * e)) : 0u;
+      pad[q] = w;
+    }
+
+    // double-buffered staging: chunk ch + 1 is in flight (LDGSTS) while chunk ch is counted
+    const int n_chunks = (nr + stage_rows - 1) / stage_rows;
+    auto issue = [&](int ch) {
+      Tin* buf = stage + (ch & 1) * stage_rows * stage_elems;
+      const int rb = ch * stage_rows, nrb = min(stage_rows, nr - rb);
+      for (int r = 0; r < nrb; ++r) {
+        const Tin* src = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs;
+        stage_row_async<Tin>(buf + r * stage_elems, src, cols, p0, s0, ncol, contiguous, lane);
+      }
+    };
+    if (n_chunks > 0) issue(0);
+    cp_async_commit();
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      if (ch + 1 < n_chunks) issue(ch + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      const Tin* buf = stage + (ch & 1) * stage_rows * stage_elems;
+      const int rb = ch * stage_rows, nrb = min(stage_rows, nr - rb);
+      for (int r = 0; r < nrb; ++r) {
+        int sh = 0;  // the row's 16-byte phase (see stage_row)
+        if (contiguous) {
+          const Tin* seg = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs + s0;
+          sh = static_cast<int>((reinterpret_cast<uintptr_t>(seg) & 15) / sizeof(Tin));
+        }
+        const Tin* trow = buf + r * stage_elems + sh + c0;
+        // one-hot masks of this lane's row segment (columns past the cell's width contribute nothing)
+        uint32_t m[NIN];
+        if constexpr (sizeof(Tin) == 1) {
+          // byte labels: read the segment as aligned words, realign with funnel shifts, pick bytes at
+          // compile-time positions; a byte >= 32 (or a negative int8) shifts the 1 out: no range checks
+          const int pos = static_cast<int>(trow - (buf + r * stage_elems));
+          const uint32_t* wrow = reinterpret_cast<const uint32_t*>(buf + r * stage_elems) + (pos >> 2);
+          const int shb = (pos & 3) * 8;
+          constexpr int NW = (NIN + 3) / 4;
+          uint32_t wv[NW + 1];
+#pragma unroll
+          for (int q = 0; q <= NW; ++q) wv[q] = wrow[q];
+          uint32_t al[NW];
+#pragma unroll
+          for (int q = 0; q < NW; ++q) al[q] = __funnelshift_r(wv[q], wv[q + 1], shb) | pad[q];
+#pragma unroll
+          for (int c = 0; c < NIN; ++c) m[c] = onehot(__byte_perm(al[c >> 2], 0, 0x4440 + (c & 3)));
+        } else {
+#pragma unroll
+          for (int c = 0; c < NIN; ++c) {
+            const Tin t = trow[c];
+            const uint32_t v = (t >= Tin(0) && t < Tin(32)) ? static_cast<uint32_t>(t) : 32u;
+            m[c] = (c < nc) ? onehot(v) : 0u;
+          }
+        }
+        // carry-save adder tree: 6-bit sums per label position
+        uint32_t s[6];
+        csa_sum<NIN>(m, s);
+        // ripple the 6-bit column sums into the planes
+        uint32_t carry = 0;
+#pragma unroll
+        for (int q = 0; q < kPlanes; ++q) {
+          const uint32_t add = q < 6 ? s[q] : 0u;
+          const uint32_t nc_ = maj3(plane[q], add, carry);
+          plane[q] = xor3(plane[q], add, carry);
+          carry = nc_;
+        }
+      }
+      __syncwarp();  // the buffer is refilled by the next iteration's issue
+    }
+    // ---- decode without transposing: walk the planes from the top bit down, keeping the labels that still
+    // tie for the largest (smallest) count; the lowest surviving bit is the first label (idxmax / idxmin
+    // tie rule).  A zero count is the reference's -1: still the smallest value, and "all zero" keeps every
+    // label, so label 0 wins exactly like idxmax over an all -1 column.
+    Tout out = fill;
+    if (row_ok && in && cols.cover[l]) {
+      uint32_t cand = label_mask;
+#pragma unroll
+      for (int q = kPlanes - 1; q >= 0; --q) {
+        const uint32_t t = cand & (anti ? ~plane[q] : plane[q]);
+        cand = t ? t : cand;
+      }
+      out = static_cast<Tout>(values[__ffs(cand) - 1]);
+    }
+    if (in) y[b * ybs + static_cast<long long>(rows.out_index[k]) * Wo + cols.out_index[l]] = out;
+  }
+}
+
 // ------------------------------------------------------------ stats, one cell per lane
 // sum / mean / min / max / var / std with the strip staging of the mode kernel: a warp owns 32 adjacent
 // target cells, every lane accumulates its own cell in registers (fp64 sums), no shuffles, no atomics.
@@ -607,8 +793,9 @@ struct ChunkPlan {
 template <typename Tin, typename Tout>
 int mode_launch(const void* x, void* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
                 const rg_bins_t* rows_c, const rg_bins_t* cols_c, int32_t cols_per_chunk, int32_t tile_elems,
-                int32_t strip_elems, const void* values_sorted, const int32_t* value_rank, const void* values,
-                int32_t n_values, int32_t dense, int32_t anti, double fill, cudaStream_t stream) {
+                int32_t strip_elems, int32_t max_bin_rows, int32_t max_bin_cols, const void* values_sorted,
+                const int32_t* value_rank, const void* values, int32_t n_values, int32_t dense, int32_t anti,
+                double fill, cudaStream_t stream) {
   Bins rows, cols;
   int rc = make_bins(rows_c, &rows);
   if (rc != RG_OK) return rc;
@@ -617,6 +804,39 @@ int mode_launch(const void* x, void* y, int64_t batch, int64_t xbs, int64_t xrs,
   DeviceInfo dev;
   rc = device_info(&dev);
   if (rc != RG_OK) return rc;
+  // ---- fastest path: <= 32 dense labels, cells of <= 32 columns: bit-sliced counters in registers
+  if (dense && n_values <= 32 && strip_elems > 0 && max_bin_cols > 0 && max_bin_cols <= 32 && max_bin_rows > 0 &&
+      static_cast<long long>(max_bin_rows) * max_bin_cols <= (1 << kPlanes) - 1) {
+    const int stage_elems = (strip_elems + 48 + 15) / 16 * 16;
+    // two staging buffers per warp; three CTAs per SM (80 registers) share the shared memory
+    int stage_rows = static_cast<int>((56 * 1024) / (static_cast<size_t>(kLaneWarps) * 2 * stage_elems * sizeof(Tin)));
+    if (stage_rows > 8) stage_rows = 8;
+    if (stage_rows >= 1) {
+      const size_t smem_p = static_cast<size_t>(kLaneWarps) * 2 * stage_rows * stage_elems * sizeof(Tin);
+      using PK = void (*)(const Tin*, Tout*, long long, long long, long long, long long, Bins, Bins, const Tin*,
+                          int, int, Tout, int, int);
+      PK kp = max_bin_cols <= 8    ? mode_planes_kernel<Tin, Tout, 8>
+              : max_bin_cols <= 16 ? mode_planes_kernel<Tin, Tout, 16>
+              : max_bin_cols <= 25 ? mode_planes_kernel<Tin, Tout, 25>
+              : max_bin_cols <= 26 ? mode_planes_kernel<Tin, Tout, 26>
+                                   : mode_planes_kernel<Tin, Tout, 32>;
+      if (smem_p > 48 * 1024)
+        RG_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_p)));
+      int per_sm_p = 0;
+      RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, kp, kLaneThreads, smem_p));
+      if (per_sm_p >= 1) {
+        const long long strips = (cols.n_out + 31) / 32;
+        const long long tasks_p = static_cast<long long>(batch) * rows.n_out * strips;
+        long long grid_p = static_cast<long long>(dev.sm_count) * per_sm_p * 2;
+        const long long need = (tasks_p + kLaneWarps - 1) / kLaneWarps;
+        if (grid_p > need) grid_p = need;
+        kp<<<static_cast<unsigned>(grid_p), kLaneThreads, smem_p, stream>>>(
+            static_cast<const Tin*>(x), static_cast<Tout*>(y), batch, xbs, xrs, ybs, rows, cols,
+            static_cast<const Tin*>(values), n_values, anti, static_cast<Tout>(fill), stage_elems, stage_rows);
+        return static_cast<int>(cudaGetLastError());
+      }
+    }
+  }
   // ---- throughput path: one cell per lane, lane-private counters (needs few labels and strips whose
   //      source columns fit the per-warp staging buffer)
   if (n_values <= kLaneMaxLabels && strip_elems > 0) {
@@ -729,8 +949,8 @@ extern "C" {
 int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t batch,
             int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride, const rg_bins_t* rows,
             const rg_bins_t* cols, int32_t cols_per_chunk, int32_t tile_elems, int32_t strip_elems,
-            const void* values_sorted, const int32_t* value_rank, const void* values, int32_t n_values,
-            int32_t dense, int32_t anti_mode, double fill, void* stream) {
+            int32_t max_bin_rows, int32_t max_bin_cols, const void* values_sorted, const int32_t* value_rank,
+            const void* values, int32_t n_values, int32_t dense, int32_t anti_mode, double fill, void* stream) {
   if (!x || !y || !values || (!dense && (!values_sorted || !value_rank))) return RG_ERR_NULL;
   if (n_values <= 0 || cols_per_chunk <= 0 || tile_elems <= 0 || batch < 0) return RG_ERR_SHAPE;
   if (batch == 0) return RG_OK;
@@ -739,12 +959,16 @@ int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t b
   if (in_type == CODE) {                                                                                    \
     if (out_type == CODE)                                                                                   \
       return rg::mode_launch<TIN, TIN>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows,     \
-                                       cols, cols_per_chunk, tile_elems, strip_elems, values_sorted,        \
-                                       value_rank, values, n_values, dense, anti_mode, fill, s);            \
+                                       cols, cols_per_chunk, tile_elems, strip_elems, max_bin_rows,         \
+                                       max_bin_cols,                                                        \
+                                       values_sorted, value_rank, values, n_values, dense, anti_mode, fill, \
+                                       s);                                                                  \
     if (out_type == RG_F64)                                                                                 \
       return rg::mode_launch<TIN, double>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows,  \
-                                          cols, cols_per_chunk, tile_elems, strip_elems, values_sorted,     \
-                                          value_rank, values, n_values, dense, anti_mode, fill, s);         \
+                                          cols, cols_per_chunk, tile_elems, strip_elems, max_bin_rows,      \
+                                          max_bin_cols,                                                     \
+                                          values_sorted, value_rank, values, n_values, dense, anti_mode,    \
+                                          fill, s);                                                         \
     return RG_ERR_UNSUPPORTED;                                                                              \
   }
   RG_MODE(RG_U8, uint8_t)

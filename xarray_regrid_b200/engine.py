@@ -465,6 +465,32 @@ class ReducePlan:
                          else tables.plain_axis(cols.src))
             self.cols_bins = tables.bins_axis(cols_axis, cols.tgt)
         self._dev: dict = {}
+        self._labels: dict = {}   # (dtype, values) -> device label tables
+        self._launch: dict = {}   # launch geometry per (shape, element size, scratch)
+
+    def _label_tables(self, np_dtype, values):
+        """Device copies of the label list (as given / sorted / rank), cached per plan."""
+        vals = np.asarray(values).astype(np_dtype)
+        key = (np_dtype.str, vals.tobytes())
+        if key not in self._labels:
+            order = np.argsort(vals, kind="stable")
+            self._labels[key] = (
+                vals,
+                bool(np.array_equal(vals, np.arange(vals.size))),
+                torch.from_numpy(np.ascontiguousarray(vals)).to(self.device),
+                torch.from_numpy(np.ascontiguousarray(vals[order])).to(self.device),
+                torch.from_numpy(order.astype(np.int32)).to(self.device),
+            )
+        return self._labels[key]
+
+    def _geometry(self, rows, cols, elem_size: int, scratch: int):
+        """(cols_per_chunk, tile_elems, strip_elems, max_bin_rows, max_bin_cols) of a table pair."""
+        key = (id(rows), id(cols), elem_size, scratch)
+        if key not in self._launch:
+            cpc, tile = tables.plan_chunks(rows.host, cols.host, elem_size, scratch)
+            self._launch[key] = (cpc, tile, _strip_elems(cols.host), int(rows.host.count.max()),
+                                 int(cols.host.count.max()))
+        return self._launch[key]
 
     def _bins(self, n_rows: int, n_cols: int):
         if (n_rows, n_cols) not in self._dev:
@@ -506,12 +532,7 @@ class ReducePlan:
             )
         x3, lead, rows, cols = self._prepare(x)
         np_dtype = np.dtype(str(x.dtype).replace("torch.", ""))
-        vals = np.asarray(values).astype(np_dtype)
-        dense = bool(np.array_equal(vals, np.arange(vals.size)))
-        order = np.argsort(vals, kind="stable")
-        v_dev = torch.from_numpy(np.ascontiguousarray(vals)).to(self.device)
-        vs_dev = torch.from_numpy(np.ascontiguousarray(vals[order])).to(self.device)
-        rank_dev = torch.from_numpy(order.astype(np.int32)).to(self.device)
+        vals, dense, v_dev, vs_dev, rank_dev = self._label_tables(np_dtype, values)
         if fill_value is None and not self.fully_covered:
             import warnings
 
@@ -524,13 +545,13 @@ class ReducePlan:
             out_dtype, fill = x.dtype, 0.0 if fill_value is None else float(fill_value)
         B, Ho, Wo = x3.shape[0], rows.host.n_out, cols.host.n_out
         y = torch.empty((B, Ho, Wo), dtype=out_dtype, device=x3.device)
-        cpc, tile = tables.plan_chunks(rows.host, cols.host, x3.element_size(), 8 * vals.size * 4)
-        strip = _strip_elems(cols.host)
+        cpc, tile, strip, max_rows, max_cols = self._geometry(rows, cols, x3.element_size(), 8 * vals.size * 4)
         if B:
             check(
                 lib.rg_mode(x3.data_ptr(), y.data_ptr(), _TYPE_CODE[x3.dtype], _TYPE_CODE[out_dtype], B,
                             x3.stride(0) if B > 1 else x3.shape[1] * x3.stride(1), x3.stride(1), Ho * Wo,
-                            rows.ref, cols.ref, cpc, tile, strip, vs_dev.data_ptr(), rank_dev.data_ptr(),
+                            rows.ref, cols.ref, cpc, tile, strip, max_rows, max_cols,
+                            vs_dev.data_ptr(), rank_dev.data_ptr(),
                             v_dev.data_ptr(), int(vals.size), int(dense), int(bool(anti_mode)), fill,
                             _stream_ptr(x3.device)),
                 "rg_mode",
@@ -550,17 +571,16 @@ class ReducePlan:
         y = torch.empty((B, Ho, Wo), dtype=x3.dtype, device=x3.device)
         sort_cap = 0
         if method == "median":
-            biggest = int(rows.host.count.max()) * int(cols.host.count.max())
-            sort_cap = 1 << max(biggest - 1, 0).bit_length()
-        cpc, tile = tables.plan_chunks(rows.host, cols.host, x3.element_size(),
-                                       8 * sort_cap * x3.element_size())
+            _, _, _, max_rows, max_cols = self._geometry(rows, cols, x3.element_size(), 0)
+            sort_cap = 1 << max(max_rows * max_cols - 1, 0).bit_length()
+        cpc, tile, strip, _, _ = self._geometry(rows, cols, x3.element_size(), 8 * sort_cap * x3.element_size())
         fn = lib.rg_stat_f64 if x3.dtype == torch.float64 else lib.rg_stat_f32
         fill = float("nan") if fill_value is None else float(fill_value)
         if B:
             check(
                 fn(x3.data_ptr(), y.data_ptr(), B, x3.stride(0) if B > 1 else x3.shape[1] * x3.stride(1),
                    x3.stride(1), Ho * Wo, rows.ref, cols.ref, cpc, tile, _STAT_CODE[method],
-                   int(bool(skipna)), sort_cap, _strip_elems(cols.host), fill, _stream_ptr(x3.device)),
+                   int(bool(skipna)), sort_cap, strip, fill, _stream_ptr(x3.device)),
                 "rg_stat",
             )
         return y.view(tuple(lead) + (Ho, Wo))
