@@ -162,6 +162,23 @@ def test_stats_all_methods(engine, dtype, rtol, skipna):
             np.testing.assert_allclose(y, want, rtol=rtol, atol=rtol * 10, err_msg=method)
 
 
+def test_var_fp32_large_offset(engine):
+    """fp32 var / std use one pass with fp64 moments shifted by the cell's first valid value: a field with
+    mean / spread = 1e4 (temperatures in K with 0.03 K noise) must still match np.var within fp32 tolerance."""
+    rng = np.random.default_rng(23)
+    lat, lon = np.round(np.arange(-4.995, 5, 0.01), 3), np.round(np.arange(0.005, 20, 0.01), 3)
+    tlat, tlon = np.arange(-4.875, 5, 0.25), np.arange(0.125, 20, 0.25)
+    x = (300.0 + 0.03 * rng.normal(size=(1, lat.size, lon.size))).astype(np.float32)
+    x[rng.random(x.shape) < 0.05] = np.nan
+    x[0, :, ::25] = np.nan  # the first column of every cell is missing: the shift comes from a later sample
+    plan = _plan(engine, lat, lon, tlat, tlon, ("lat", "lon"))
+    for method in ("var", "std", "mean"):
+        y = plan.stat(torch.from_numpy(x).cuda(), method, skipna=True).cpu().numpy()
+        want = orr.regrid_latlon(x, lat, lon, tlat, tlon, "stat", method=method, skipna=True)
+        np.testing.assert_array_equal(np.isnan(y), np.isnan(want), err_msg=method)
+        np.testing.assert_allclose(y, want, rtol=1e-5, err_msg=method)
+
+
 def test_stat_global_wrap_and_uncovered(engine):
     """Global 1 deg cell-centred source -> 2 deg pole-centred target: longitude wrap padding is applied
     (stats=True skips the pole rows, tests/test_format.py:182-218) and edge bins are half populated."""

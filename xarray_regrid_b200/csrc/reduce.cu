@@ -693,15 +693,19 @@ mode_planes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long ba
 // sum / mean / min / max / var / std with the strip staging of the mode kernel: a warp owns 32 adjacent
 // target cells, every lane accumulates its own cell in registers (fp64 sums), no shuffles, no atomics.
 // With 25-column cells the lanes' shared-memory reads are conflict-free (stride 25 words, gcd(25, 32) = 1).
-// var / std make a second pass over the strip (re-staged, L2 hits) around the exact mean, like np.var.
-template <typename T>
-__global__ void __launch_bounds__(kLaneThreads)
+// Rows are staged with LDGSTS into two buffers per warp (the next chunk is in flight while this one is
+// reduced); columns are walked in unrolled blocks of 8, branch-free (NaN -> predicated add, FMNMX skips NaN).
+// var / std of fp64 data make a second pass over the strip around the exact mean, like np.var; fp32 data
+// use one pass with shifted fp64 moments (see below).
+// OPC selects the accumulator set at compile time: 0 = sum / mean, 1 = min / max, 2 = var / std.
+template <typename T, int OPC>
+__global__ void __launch_bounds__(kLaneThreads, 3)
 stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
                   long long ybs, Bins rows, Bins cols, int op, int skipna, T fill, int stage_elems,
                   int stage_rows) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  T* stage = reinterpret_cast<T*>(smem) + static_cast<size_t>(warp) * stage_rows * stage_elems;
+  T* stage = reinterpret_cast<T*>(smem) + static_cast<size_t>(warp) * 2 * stage_rows * stage_elems;
   const int Wo = cols.n_out;
   const int strips = (Wo + 31) / 32;
   const long long tasks = batch * rows.n_out * strips;
@@ -726,49 +730,92 @@ stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, l
     const int s0 = src_index(cols, p0);
     const bool contiguous = cols.src_step == 1 && s0 + ncol <= cols.n_src;
     const int row_first = src_index(rows, r0);
+    const int n_chunks = (nr + stage_rows - 1) / stage_rows;
 
-    double sum = 0.0, m2 = 0.0, mean = 0.0;
-    int n = 0, n_nan = 0;
-    T vmin = CUDART_INF, vmax = -CUDART_INF;
-    const int passes = (op == OP_VAR || op == OP_STD) ? 2 : 1;
-    for (int pass = 0; pass < passes; ++pass) {
-      for (int rb = 0; rb < nr; rb += stage_rows) {
-        const int nrb = min(stage_rows, nr - rb);
+    auto issue = [&](int ch) {
+      T* buf = stage + (ch & 1) * stage_rows * stage_elems;
+      const int rb = ch * stage_rows, nrb = min(stage_rows, nr - rb);
+      for (int r = 0; r < nrb; ++r) {
+        const T* src = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs;
+        stage_row_async<T>(buf + r * stage_elems, src, cols, p0, s0, ncol, contiguous, lane);
+      }
+    };
+    // walk every staged row segment of this lane's cell: f(v) per element
+    auto sweep = [&](auto&& f) {
+      if (n_chunks > 0) issue(0);
+      cp_async_commit();
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        if (ch + 1 < n_chunks) issue(ch + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncwarp();
-        for (int r = 0; r < nrb; ++r) {
-          const T* src = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs;
-          stage_row<T>(stage + r * stage_elems, src, cols, p0, s0, ncol, contiguous, lane);
-        }
-        __syncwarp();
+        const T* buf = stage + (ch & 1) * stage_rows * stage_elems;
+        const int rb = ch * stage_rows, nrb = min(stage_rows, nr - rb);
         for (int r = 0; r < nrb; ++r) {
           int sh = 0;  // the row's 16-byte phase (see stage_row)
           if (contiguous) {
             const T* seg = xb + static_cast<long long>(row_first + rows.src_step * (rb + r)) * xrs + s0;
             sh = static_cast<int>((reinterpret_cast<uintptr_t>(seg) & 15) / sizeof(T));
           }
-          const T* trow = stage + r * stage_elems + sh + c0;
-          if (pass == 0) {
-            for (int c = 0; c < nc; ++c) {
-              const T v = trow[c];
-              if (v == v) {
-                sum += static_cast<double>(v);
-                ++n;
-                vmin = v < vmin ? v : vmin;
-                vmax = v > vmax ? v : vmax;
-              } else {
-                ++n_nan;
-              }
-            }
-          } else {
-            for (int c = 0; c < nc; ++c) {
-              const T v = trow[c];
-              if (v == v) { const double d = static_cast<double>(v) - mean; m2 += d * d; }
-            }
+          const T* trow = buf + r * stage_elems + sh + c0;
+          int c = 0;
+          for (; c + 8 <= nc; c += 8) {
+            T v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = trow[c + e];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f(v[e]);
           }
+          for (; c < nc; ++c) f(trow[c]);
         }
+        __syncwarp();  // the buffer is refilled by the next iteration's issue
       }
-      if (pass == 0 && n > 0) mean = sum / n;
+    };
+
+    double sum = 0.0, m2 = 0.0, mean = 0.0;
+    int n = 0;
+    T vmin = CUDART_INF, vmax = -CUDART_INF;
+    if constexpr (OPC == 1) {
+      sweep([&](T v) {
+        n += (v == v) ? 1 : 0;
+        vmin = v < vmin ? v : vmin;  // comparisons with NaN are false: NaN never replaces a value
+        vmax = v > vmax ? v : vmax;
+      });
+    } else if constexpr (OPC == 2 && sizeof(T) == 4) {
+      // fp32 data: ONE pass with fp64 moments around the cell's first valid value.  The shift is a sample
+      // of the cell, so (sum d)^2 / n <= 2 n var and the cancellation costs at most ~2n * 2^-53 relative:
+      // far below the fp32 rounding of the result (the strip is ~300 MB in flight across the GPU, a
+      // second pass would come from DRAM again).
+      bool have = false;
+      double shift = 0.0;
+      sweep([&](T v) {
+        const bool ok = v == v;
+        if (ok && !have) { shift = static_cast<double>(v); have = true; }
+        const double d = ok ? static_cast<double>(v) - shift : 0.0;
+        n += ok ? 1 : 0;
+        sum += d;
+        m2 += d * d;
+      });
+      if (n > 0) {
+        const double md = sum / n;
+        m2 = fmax(m2 - md * sum, 0.0);
+        mean = shift + md;
+      }
+    } else {
+      sweep([&](T v) {
+        const bool ok = v == v;
+        n += ok ? 1 : 0;
+        sum += ok ? static_cast<double>(v) : 0.0;
+      });
+      if (n > 0) mean = sum / n;
+      if constexpr (OPC == 2) {
+        sweep([&](T v) {
+          const double d = (v == v) ? static_cast<double>(v) - mean : 0.0;
+          m2 += d * d;
+        });
+      }
     }
+    const int n_nan = nr * nc - n;
     T out = fill;
     if (row_ok && in && cols.cover[l]) {
       const bool poisoned = !skipna && n_nan > 0;
@@ -902,11 +949,16 @@ int stat_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64
   // ---- throughput path (everything but the median): one cell per lane
   if (op != OP_MEDIAN && strip_elems > 0) {
     const int stage_elems = (strip_elems + 48 + 15) / 16 * 16;
-    int stage_rows = static_cast<int>((56 * 1024) / (static_cast<size_t>(kLaneWarps) * stage_elems * sizeof(T)));
+    // two staging buffers per warp; aim at three CTAs per SM, but a single row per buffer is enough
+    int stage_rows = static_cast<int>((72 * 1024) / (static_cast<size_t>(kLaneWarps) * 2 * stage_elems * sizeof(T)));
     if (stage_rows > 8) stage_rows = 8;
-    if (stage_rows >= 1) {
-      const size_t smem_l = static_cast<size_t>(kLaneWarps) * stage_rows * stage_elems * sizeof(T);
-      auto kl = stat_lanes_kernel<T>;
+    if (stage_rows < 1) stage_rows = 1;
+    if (static_cast<size_t>(kLaneWarps) * 2 * stage_rows * stage_elems * sizeof(T) <=
+        static_cast<size_t>(dev.max_smem_optin)) {
+      const size_t smem_l = static_cast<size_t>(kLaneWarps) * 2 * stage_rows * stage_elems * sizeof(T);
+      auto kl = (op == OP_MIN || op == OP_MAX)   ? stat_lanes_kernel<T, 1>
+                : (op == OP_VAR || op == OP_STD) ? stat_lanes_kernel<T, 2>
+                                                 : stat_lanes_kernel<T, 0>;
       if (smem_l > 48 * 1024)
         RG_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_l)));
       int per_sm_l = 0;
