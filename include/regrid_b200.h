@@ -126,6 +126,10 @@ typedef struct rg_row_ring {
   int32_t n_strips;
   int32_t strip_cols_max;
   int32_t n_warps;   /* consumer warps (1..24); the kernel adds one producer warp */
+  int32_t lane_cols; /* 4: every target column takes taps idx0 .. idx0 + cnt - 1 (cnt <= 5, mod n_src), idx0 is
+                        even and grows by exactly 4 from one target to the next inside a strip, every strip has
+                        <= 31 targets, all covered, and n_strips <= n_warps: the kernel then keeps both
+                        contractions in registers (one lane per target column).  0: no such structure. */
 } rg_row_ring_t;
 
 /*

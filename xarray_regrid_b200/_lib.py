@@ -49,6 +49,7 @@ class rg_row_ring_t(C.Structure):  # noqa: N801 - mirrors the C name
         ("n_strips", C.c_int32),
         ("strip_cols_max", C.c_int32),
         ("n_warps", C.c_int32),
+        ("lane_cols", C.c_int32),
     ]
 
 

@@ -222,14 +222,22 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       ring_c->sched_row && ring_c->krec && ring_c->wrec && ring_c->run_first && ring_c->run_sched &&
       ring_c->strip_l0 && ring_c->strip_c0 && ring_c->strip_nc) {
     const int kw = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : cols.k_max <= 3 ? 3 : cols.k_max <= 5 ? 5 : 8;
+    // lane-owned columns variant (4 source columns + 1 per target, see conservative_ring.cuh): no strip buffers
+    const bool lanes = ring_c->lane_cols == 4 && cols.k_max <= 5 && ring_c->n_strips <= ring_c->n_warps &&
+                       ring_c->n_warps + 2 <= 14 && W % 2 == 0;
     const RingLayout probe =
-        ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, 0);
-    const long long room = static_cast<long long>(dev.max_smem_optin) - static_cast<long long>(probe.total);
+        lanes ? ring_layout<T>(W, 31, false, 0, 0, 0)
+              : ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, 0);
+    // the lanes variant stages the per-row records and weights (16 + 8 * sizeof(T) bytes per target row)
+    const size_t row_tables = lanes ? static_cast<size_t>(rows.n_out) * (16 + kRingMaxTaps * sizeof(T)) : 0;
+    const long long room = static_cast<long long>(dev.max_smem_optin) - static_cast<long long>(probe.total) -
+                           static_cast<long long>(row_tables);
     int slots = room > 0 ? static_cast<int>(room / probe.row_stride) : 0;
     if (slots > kRingMaxSlots) slots = kRingMaxSlots;
     if (slots >= ring_c->max_live + 1 && slots >= 2) {
       const RingLayout L =
-          ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, slots);
+          lanes ? ring_layout<T>(W, 31, false, 0, 0, slots)
+                : ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, slots);
       RingDev ring{ring_c->sched_row,
                    reinterpret_cast<const int4*>(ring_c->krec),
                    ring_c->wrec,
@@ -244,7 +252,8 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
                    ring_c->pad_shift,
                    ring_c->n_strips,
                    ring_c->strip_cols_max,
-                   ring_c->n_warps};
+                   ring_c->n_warps,
+                   ring_c->lane_cols};
       using RingKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev,
                                   T, int);
       const int warps = ring.n_warps + 2;  // + producer + sync
@@ -262,11 +271,19 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
         default: break;
       }
 #undef RG_PICK
-      RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(L.total)));
       const long long tasks = static_cast<long long>(batch) * ring.n_runs;
       long long grid = dev.sm_count;
       if (grid > tasks) grid = tasks;
+      if (lanes) {
+        auto lk = skipna ? conservative_lanes_kernel<T, true, 14> : conservative_lanes_kernel<T, false, 14>;
+        const size_t smem_l = L.total + row_tables;
+        RG_CUDA(cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_l)));
+        lk<<<static_cast<unsigned>(grid), warps * 32, smem_l, stream>>>(x, y, batch, xbs, xrs, ybs, cols, ring, thr,
+                                                                       slots, rows.n_out);
+        return static_cast<int>(cudaGetLastError());
+      }
+      RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(L.total)));
       kern<<<static_cast<unsigned>(grid), warps * 32, L.total, stream>>>(x, y, batch, xbs, xrs, ybs, cols,
                                                                         ring, thr, slots);
       return static_cast<int>(cudaGetLastError());

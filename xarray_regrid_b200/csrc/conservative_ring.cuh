@@ -33,7 +33,7 @@ struct RingDev {
   const int32_t* __restrict__ strip_l0;
   const int32_t* __restrict__ strip_c0;
   const int32_t* __restrict__ strip_nc;
-  int n_runs, n_sched, max_live, pad_shift, n_strips, strip_cols_max, n_warps;
+  int n_runs, n_sched, max_live, pad_shift, n_strips, strip_cols_max, n_warps, lane_cols;
 };
 
 constexpr int kRingMaxSlots = 16;
@@ -208,6 +208,54 @@ __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row
   }
 }
 
+// ---------------------------------------------------------------- producer / sync roles
+// producer: one thread streams the scheduled source rows of every task into the ring with TMA bulk copies
+template <typename T>
+__device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long xbs, long long xrs,
+                                              const RingDev& ring, long long tasks, int ring_slots,
+                                              uint32_t row_bytes, int row_stride, uint32_t full0, uint32_t flags0,
+                                              uint32_t ring0, int n_warps) {
+  uint32_t g = 0, freed = 0;  // rows issued / rows released by every consumer warp
+  int slot = 0;
+  for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int run = static_cast<int>(task % ring.n_runs);
+    const T* xb = x + (task / ring.n_runs) * xbs;
+    const int p1 = ring.run_sched[run + 1];
+    for (int p = ring.run_sched[run]; p < p1; ++p) {
+      const long long off = static_cast<long long>(ring.sched_row[p]) * xrs;
+      while (static_cast<int>(g - freed) >= ring_slots) {  // ring full: wait for the slowest warp
+        uint32_t m = ld_acquire_smem(flags0 + 4);
+        for (int w = 1; w < n_warps; ++w) {
+          const uint32_t d = ld_acquire_smem(flags0 + 4 * (1 + w));
+          if (static_cast<int>(d - m) < 0) m = d;
+        }
+        freed = m;
+        if (static_cast<int>(g - freed) >= ring_slots) __nanosleep(64);
+      }
+      mbar_arrive_expect_tx(full0 + 8u * slot, row_bytes);
+      tma_load_row(ring0 + static_cast<uint32_t>(slot) * row_stride, xb + off, row_bytes, full0 + 8u * slot);
+      ++g;
+      if (++slot == ring_slots) slot = 0;
+    }
+  }
+}
+
+// sync: one thread waits on the "full" mbarriers in order and publishes the landed-row count
+__device__ __forceinline__ void ring_sync(const RingDev& ring, long long tasks, int ring_slots, uint32_t full0,
+                                          uint32_t flags0) {
+  uint32_t g = 0, parity = 0;
+  int slot = 0;
+  for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int run = static_cast<int>(task % ring.n_runs);
+    const int n = ring.run_sched[run + 1] - ring.run_sched[run];
+    for (int i = 0; i < n; ++i) {
+      while (!mbar_try_wait(full0 + 8u * slot, parity)) __nanosleep(32);  // do not steal issue slots
+      st_release_smem(flags0, ++g);  // rows [0, g) are in the ring and visible
+      if (++slot == ring_slots) { slot = 0; parity ^= 1; }
+    }
+  }
+}
+
 template <typename T, bool SKIPNA, int KW, int MAXWARPS>
 __global__ void __launch_bounds__(MAXWARPS * 32, 1)
 conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
@@ -233,51 +281,13 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
   const uint32_t row_bytes = static_cast<uint32_t>(W) * sizeof(T);
   const uint32_t full0 = smem_u32(s_full), flags0 = smem_u32(s_flags), ring0 = smem_u32(smem);
 
-  // ================================================================ producer: TMA row loads
+  // ================================================================ producer / sync warps
   if (warp == n_warps) {
-    if (lane == 0) {
-      uint32_t g = 0, freed = 0;  // rows issued / rows released by every consumer warp
-      int slot = 0;
-      for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
-        const int run = static_cast<int>(task % ring.n_runs);
-        const T* xb = x + (task / ring.n_runs) * xbs;
-        const int p1 = ring.run_sched[run + 1];
-        for (int p = ring.run_sched[run]; p < p1; ++p) {
-          const long long off = static_cast<long long>(ring.sched_row[p]) * xrs;
-          while (static_cast<int>(g - freed) >= ring_slots) {  // ring full: wait for the slowest warp
-            uint32_t m = ld_acquire_smem(flags0 + 4);
-            for (int w = 1; w < n_warps; ++w) {
-              const uint32_t d = ld_acquire_smem(flags0 + 4 * (1 + w));
-              if (static_cast<int>(d - m) < 0) m = d;
-            }
-            freed = m;
-            if (static_cast<int>(g - freed) >= ring_slots) __nanosleep(64);
-          }
-          mbar_arrive_expect_tx(full0 + 8u * slot, row_bytes);
-          tma_load_row(ring0 + static_cast<uint32_t>(slot) * L.row_stride, xb + off, row_bytes,
-                       full0 + 8u * slot);
-          ++g;
-          if (++slot == ring_slots) slot = 0;
-        }
-      }
-    }
+    if (lane == 0) ring_producer<T>(x, xbs, xrs, ring, tasks, ring_slots, row_bytes, L.row_stride, full0, flags0, ring0, n_warps);
     return;
   }
-  // ================================================================ sync: relay TMA completion
   if (warp > n_warps) {
-    if (warp == n_warps + 1 && lane == 0) {
-      uint32_t g = 0, parity = 0;
-      int slot = 0;
-      for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
-        const int run = static_cast<int>(task % ring.n_runs);
-        const int n = ring.run_sched[run + 1] - ring.run_sched[run];
-        for (int i = 0; i < n; ++i) {
-          while (!mbar_try_wait(full0 + 8u * slot, parity)) __nanosleep(32);  // do not steal issue slots
-          st_release_smem(flags0, ++g);  // rows [0, g) are in the ring and visible
-          if (++slot == ring_slots) { slot = 0; parity ^= 1; }
-        }
-      }
-    }
+    if (warp == n_warps + 1 && lane == 0) ring_sync(ring, tasks, ring_slots, full0, flags0);
     return;
   }
 
@@ -376,6 +386,224 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
           }
           st_stream(yrow + l0 + lane, out);
         }
+      }
+    }
+    gbase += static_cast<uint32_t>(ring.run_sched[run + 1] - ring.run_sched[run]);
+  }
+}
+
+// ====================================================================== lane-owned columns variant
+// For the common coarsening case -- every target column takes `4 source columns + 1` contiguous taps and
+// neighbouring targets are exactly 4 source columns apart (0.25 deg -> 1 deg, edge- or centre-aligned) --
+// the two contractions fuse in registers: lane m of a strip's warp contracts ITS OWN 4 source columns along
+// latitude (two 2-column vector loads per row tap straight out of the TMA ring), fetches the 5th column's
+// {t, v} from lane m + 1 with a shuffle, and finishes the longitude contraction, normalisation, mask and
+// store.  No strip buffer, no __syncwarp, one pass per target row: ~1/3 of the instructions and 2/3 of the
+// shared-memory traffic of the two-phase kernel.  Lane nl (one past the strip's last target) only produces
+// the halo column.  Lanes alternate which of their two column pairs they read first (bit SWZ of the lane id)
+// so that a 2-column load of 8 (fp64) / 16 (fp32) neighbouring lanes touches every bank exactly once.
+// Eligibility is decided on the host (rg_row_ring_t.lane_cols == 4).
+template <typename T> struct Pair2 { T a, b; };
+__device__ __forceinline__ Pair2<double> lds_pair(uint32_t addr, double) {
+  Pair2<double> r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.a), "=d"(r.b) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ Pair2<float> lds_pair(uint32_t addr, float) {
+  Pair2<float> r;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.a), "=f"(r.b) : "r"(addr));
+  return r;
+}
+
+// Latitude contraction of CNT row taps for the lane's two column pairs (A at offA, B at offB bytes into a
+// ring row).  t* = sum w x (NaN-cleaned when SKIPNA), v* = valid mass.
+template <typename T, bool SKIPNA, int CNT>
+__device__ __forceinline__ void lane_phase1(uint32_t ring0, int row_stride, int ring_slots, int newest,
+                                            uint32_t back, uint32_t wk_addr, uint32_t offA, uint32_t offB,
+                                            T (&t)[4], T (&v)[4]) {
+  constexpr int N = CNT > 0 ? CNT : 1;
+  T w[N];
+#pragma unroll
+  for (int i = 0; i < CNT; i += 2) {  // the target row's tap weights: broadcast reads of the staged table
+    const Pair2<T> p = lds_pair(wk_addr + static_cast<uint32_t>(i * sizeof(T)), T(0));
+    w[i] = p.a;
+    if (i + 1 < CNT) w[i + 1] = p.b;
+  }
+  Pair2<T> xa[N], xb[N];
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    int slot = newest - static_cast<int>((back >> (4 * i)) & 15u);  // rows back from the newest landed row
+    if (slot < 0) slot += ring_slots;
+    const uint32_t row = ring0 + static_cast<uint32_t>(slot * row_stride);
+    xa[i] = lds_pair(row + offA, T(0));
+    xb[i] = lds_pair(row + offB, T(0));
+  }
+  T wsum = T(0);
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) wsum += w[i];
+  // fast path: contract as if nothing were missing; a NaN result flags a missing tap (or inf - inf)
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { t[e] = T(0); v[e] = wsum; }
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    t[0] = fma(w[i], xa[i].a, t[0]);
+    t[1] = fma(w[i], xa[i].b, t[1]);
+    t[2] = fma(w[i], xb[i].a, t[2]);
+    t[3] = fma(w[i], xb[i].b, t[3]);
+  }
+  if constexpr (SKIPNA) {
+    const bool redo = (t[0] != t[0]) | (t[1] != t[1]) | (t[2] != t[2]) | (t[3] != t[3]);
+    if (redo) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { t[e] = T(0); v[e] = T(0); }
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) {
+        accum_valid(t[0], v[0], w[i], xa[i].a);
+        accum_valid(t[1], v[1], w[i], xa[i].b);
+        accum_valid(t[2], v[2], w[i], xb[i].a);
+        accum_valid(t[3], v[3], w[i], xb[i].b);
+      }
+    }
+  }
+}
+
+template <typename T, bool SKIPNA, int MAXWARPS>
+__global__ void __launch_bounds__(MAXWARPS * 32, 1)
+conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
+                          long long xrs, long long ybs, Band<T> cols, RingDev ring, T thr, int ring_slots,
+                          int n_rows_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int W = cols.n_src, Wo = cols.n_out;
+  const int n_warps = ring.n_warps;  // consumer warps; then one producer warp and one sync warp
+  const RingLayout L = ring_layout<T>(W, 31, false, 0, 0, ring_slots);  // no strip buffers
+  unsigned long long* s_full = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
+  uint32_t* s_flags = reinterpret_cast<uint32_t*>(smem + L.off_flags);
+  // per target row tables, staged once: 16-byte record + 8 tap weights (host contract: they fit)
+  int4* s_krec = reinterpret_cast<int4*>(smem + L.total);
+  T* s_wrec = reinterpret_cast<T*>(smem + L.total + static_cast<size_t>(n_rows_out) * 16);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < ring_slots; ++s) mbar_init(&s_full[s], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) s_flags[tid] = 0;
+  for (int i = tid; i < n_rows_out; i += blockDim.x) s_krec[i] = ring.krec[i];
+  for (int i = tid; i < n_rows_out * kRingMaxTaps; i += blockDim.x) s_wrec[i] = static_cast<const T*>(ring.wrec)[i];
+  __syncthreads();
+
+  const long long tasks = batch * ring.n_runs;
+  const uint32_t row_bytes = static_cast<uint32_t>(W) * sizeof(T);
+  const uint32_t full0 = smem_u32(s_full), flags0 = smem_u32(s_flags), ring0 = smem_u32(smem);
+
+  if (warp == n_warps) {
+    if (lane == 0) ring_producer<T>(x, xbs, xrs, ring, tasks, ring_slots, row_bytes, L.row_stride, full0, flags0, ring0, n_warps);
+    return;
+  }
+  if (warp > n_warps) {
+    if (warp == n_warps + 1 && lane == 0) ring_sync(ring, tasks, ring_slots, full0, flags0);
+    return;
+  }
+
+  // ================================================================ consumer warps (strip = warp)
+  const T nan = quiet_nan<T>();
+  const bool has_strip = warp < ring.n_strips;  // host contract: n_strips <= n_warps
+  const int l0 = has_strip ? ring.strip_l0[warp] : 0;
+  const int nl = has_strip ? ring.strip_l0[warp + 1] - l0 : 0;  // host contract: <= 31
+  const int m = lane < nl ? lane : (nl > 0 ? nl - 1 : 0);
+  const int l = l0 + m;
+  // first source column of this lane's group of 4 (the halo lane continues one group further)
+  int cfirst = (has_strip && nl > 0) ? cols.idx[l] + 4 * ((lane < nl ? lane : nl) - m) : 0;
+  constexpr int SWZ = sizeof(T) == 8 ? 2 : 3;
+  const int swz = (lane >> SWZ) & 1;
+  int jA = cfirst + 2 * swz, jB = cfirst + 2 * (1 - swz);
+  jA %= W;
+  jB %= W;
+  const uint32_t offA = static_cast<uint32_t>(jA) * sizeof(T), offB = static_cast<uint32_t>(jB) * sizeof(T);
+  // longitude taps of this lane's target: weights in register order {A.a, A.b, B.a, B.b, neighbour}
+  const int ccnt = (has_strip && lane < nl && cols.cover[l]) ? cols.cnt[l] : -1;
+  T tw[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) tw[i] = (i < ccnt && i < cols.k_max) ? cols.w[i * Wo + l] : T(0);
+  const T twA0 = swz ? tw[2] : tw[0], twA1 = swz ? tw[3] : tw[1];
+  const T twB0 = swz ? tw[0] : tw[2], twB1 = swz ? tw[1] : tw[3];
+  const T tw4 = tw[4];
+  const bool padded = ccnt >= 0 && ccnt < 5;  // zero-weight taps must not see the data (0 * NaN)
+
+  const uint32_t wrec0 = smem_u32(s_wrec);
+  uint32_t gbase = 0;    // ring position of the current run's first row
+  uint32_t newest_g = 0; // ring position + 1 of the newest row needed so far
+  int newest = ring_slots - 1;
+
+  for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int run = static_cast<int>(task % ring.n_runs);
+    const long long b = task / ring.n_runs;
+    const int k0 = ring.run_first[run], k1 = ring.run_first[run + 1];
+    for (int k = k0; k < k1; ++k) {
+      const int4 rec = s_krec[k];  // {need, release, kcnt (-1: latitude not covered), packed tap_back}
+      const uint32_t need_g = gbase + static_cast<uint32_t>(rec.x);
+      const int cnt = rec.z > 0 ? rec.z : 0;
+      while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(100);
+      newest += static_cast<int>(need_g - newest_g);
+      newest_g = need_g;
+      if (newest >= ring_slots) newest -= ring_slots;
+
+      const uint32_t wk = wrec0 + static_cast<uint32_t>(k) * (kRingMaxTaps * sizeof(T));
+      T t[4], v[4];
+#define RG_L1(C)                                                                                              \
+  case C:                                                                                                     \
+    lane_phase1<T, SKIPNA, C>(ring0, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk, offA, \
+                              offB, t, v);                                                                    \
+    break;
+      switch (cnt) {
+        RG_L1(0) RG_L1(1) RG_L1(2) RG_L1(3) RG_L1(4) RG_L1(5) RG_L1(6) RG_L1(7)
+        default:
+          lane_phase1<T, SKIPNA, 8>(ring0, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk,
+                                    offA, offB, t, v);
+          break;
+      }
+#undef RG_L1
+      // every value this warp needs from the rows that die after this output is now in registers
+      __syncwarp();
+      if (lane == 0) st_release_smem(flags0 + 4u * (1 + warp), gbase + static_cast<uint32_t>(rec.y));
+
+      // the 5th tap is the first column of the next lane's group
+      const T t_first = swz ? t[2] : t[0];
+      const T tn = __shfl_down_sync(0xffffffffu, t_first, 1);
+      T vn = T(0);
+      if constexpr (SKIPNA) {
+        const T v_first = swz ? v[2] : v[0];
+        vn = __shfl_down_sync(0xffffffffu, v_first, 1);
+      }
+      if (lane < nl) {
+        T out = nan;
+        if (rec.z >= 0 && ccnt >= 0) {
+          T e0 = t[0], e1 = t[1], e2 = t[2], e3 = t[3], e4 = tn;
+          if (padded) {
+            e0 = twA0 != T(0) ? e0 : T(0);
+            e1 = twA1 != T(0) ? e1 : T(0);
+            e2 = twB0 != T(0) ? e2 : T(0);
+            e3 = twB1 != T(0) ? e3 : T(0);
+            e4 = tw4 != T(0) ? e4 : T(0);
+          }
+          T so = twA0 * e0;
+          so = fma(twA1, e1, so);
+          so = fma(twB0, e2, so);
+          so = fma(twB1, e3, so);
+          so = fma(tw4, e4, so);
+          if constexpr (SKIPNA) {
+            T sv = twA0 * v[0];
+            sv = fma(twA1, v[1], sv);
+            sv = fma(twB0, v[2], sv);
+            sv = fma(twB1, v[3], sv);
+            sv = fma(tw4, vn, sv);
+            out = (sv >= thr) ? normalise_div(so, sv) : nan;
+          } else {
+            out = so;
+          }
+        }
+        st_stream(y + b * ybs + static_cast<long long>(k) * Wo + l0 + lane, out);
       }
     }
     gbase += static_cast<uint32_t>(ring.run_sched[run + 1] - ring.run_sched[run]);

@@ -83,7 +83,7 @@ class DeviceRing:
             self.run_first.data_ptr(), self.run_sched.data_ptr(), self.strip_l0.data_ptr(),
             self.strip_c0.data_ptr(), self.strip_nc.data_ptr(),
             ring.n_runs, int(ring.sched_row.size), ring.max_live, ring.pad_shift,
-            ring.n_strips, ring.strip_cols_max, ring.n_warps,
+            ring.n_strips, ring.strip_cols_max, ring.n_warps, ring.lane_cols,
         )
 
     @property

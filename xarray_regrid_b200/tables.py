@@ -294,6 +294,7 @@ class RowRing:
     strip_c0: np.ndarray = None  # int32 [n_strips]
     strip_nc: np.ndarray = None  # int32 [n_strips]
     n_warps: int = 0
+    lane_cols: int = 0  # 4: lane-owned columns structure (see ``lane_owned_columns``), else 0
 
     @property
     def n_strips(self) -> int:
@@ -442,7 +443,33 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
         if cols.n_src % vec != 0:
             return None
         ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = column_strips(cols, vec)
+        ring.lane_cols = lane_owned_columns(cols, ring.strip_l0, ring.n_warps)
     return ring
+
+
+def lane_owned_columns(cols: Band, strip_l0: np.ndarray, n_warps: int, step: int = 4) -> int:
+    """``step`` if the columns band has the regular coarsening structure the register-resident kernel
+    needs (``rg_row_ring_t.lane_cols``), else 0: every target covered with 1..step+1 contiguous taps
+    (modulo n_src) starting at an even source column, neighbouring targets of a strip exactly ``step``
+    source columns apart, strips of <= 31 targets, one strip per consumer warp, at most 12 consumer warps."""
+    n_src, n_out = cols.n_src, cols.n_out
+    if n_out == 0 or n_src % 2 or cols.k_max > step + 1 or n_warps > 12 or strip_l0.size - 1 > n_warps:
+        return 0
+    if not (cols.cover > 0).all() or (cols.cnt < 1).any() or (cols.cnt > step + 1).any():
+        return 0
+    first = cols.idx[0].astype(np.int64)
+    if (first % 2).any():
+        return 0
+    for i in range(1, cols.k_max):
+        live = cols.cnt > i
+        if ((cols.idx[i].astype(np.int64) - first - i) % n_src)[live].any():
+            return 0
+    for a, b in zip(strip_l0[:-1], strip_l0[1:]):
+        if b - a > 31:
+            return 0
+        if ((first[a + 1:b] - first[a:b - 1] - step) % n_src).any():
+            return 0
+    return step
 
 
 # ------------------------------------------------------------ interpolation bands (xr.interp)
