@@ -39,16 +39,25 @@ def _latlon_plan(engine, lat, lon, tlat, tlon):
     )
 
 
+def _pick(plan, kernel):
+    """kernel: "lanes" (register-resident ring variant), "ring" (two-phase ring kernel) or "generic"."""
+    plan.use_ring = kernel != "generic"
+    plan.use_lanes = kernel == "lanes"
+
+
+KERNELS = ["lanes", "ring", "generic"]
+
+
 @pytest.mark.parametrize("skipna", [False, True])
-@pytest.mark.parametrize("ring", [True, False])
+@pytest.mark.parametrize("ring", KERNELS)
 def test_c1_fp64(eng, skipna, ring):
-    """BASELINE config 1: one 721x1440 fp64 step -> 181x360, no NaNs (TMA ring and generic kernel)."""
+    """BASELINE config 1: one 721x1440 fp64 step -> 181x360, no NaNs (every kernel variant)."""
     engine, syn = eng
     lat, lon = syn.grid_025()
     tlat, tlon = syn.grid_1()
     x = syn.conservative_stack(1, lat, lon, nan_fraction=0.0)
     plan = _latlon_plan(engine, lat, lon, tlat, tlon)
-    plan.use_ring = ring
+    _pick(plan, ring)
     y = plan(x, skipna=skipna)
     want = oc.regrid_latlon(x.cpu().numpy(), lat, lon, tlat, tlon, skipna=skipna)
     assert y.shape == (1, 181, 360) and y.dtype == torch.float64
@@ -56,7 +65,7 @@ def test_c1_fp64(eng, skipna, ring):
 
 
 @pytest.mark.parametrize("nan_threshold", [0.0, 0.25, 0.5, 1.0])
-@pytest.mark.parametrize("ring", [True, False])
+@pytest.mark.parametrize("ring", KERNELS)
 def test_c2_nan_semantics_fp64(eng, nan_threshold, ring):
     """BASELINE config 2 semantics on 3 steps: 10 % NaN, skipna=True, joint 2-D valid mass."""
     engine, syn = eng
@@ -65,7 +74,7 @@ def test_c2_nan_semantics_fp64(eng, nan_threshold, ring):
     x = syn.conservative_stack(3, lat, lon, nan_fraction=0.10, chunk=2)
     x[2, 100:140, 200:300] = float("nan")  # a block that wipes out whole target cells
     plan = _latlon_plan(engine, lat, lon, tlat, tlon)
-    plan.use_ring = ring
+    _pick(plan, ring)
     y = plan(x, skipna=True, nan_threshold=nan_threshold)
     want = oc.regrid_latlon(x.cpu().numpy(), lat, lon, tlat, tlon, skipna=True,
                             nan_threshold=nan_threshold)
@@ -73,19 +82,57 @@ def test_c2_nan_semantics_fp64(eng, nan_threshold, ring):
     _check(y, want, 1e-12)
 
 
-@pytest.mark.parametrize("ring", [True, False])
+@pytest.mark.parametrize("ring", KERNELS)
 def test_fp32(eng, ring):
     engine, syn = eng
     lat, lon = syn.grid_025()
     tlat, tlon = syn.grid_1()
     x = syn.conservative_stack(2, lat, lon, dtype=torch.float32, nan_fraction=0.10)
     plan = _latlon_plan(engine, lat, lon, tlat, tlon)
-    plan.use_ring = ring
+    _pick(plan, ring)
     y = plan(x, skipna=True, nan_threshold=0.5)
     assert y.dtype == torch.float32
     want = oc.regrid_latlon(x.cpu().numpy(), lat, lon, tlat, tlon, skipna=True, nan_threshold=0.5)
     assert want.dtype == np.float32
     _check(y, want, 1e-5)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("skipna", [False, True])
+@pytest.mark.parametrize("aligned_edges", [False, True])
+def test_lane_owned_columns_variant(eng, dtype, skipna, aligned_edges):
+    """The register-resident kernel on small global 4:1 grids: target cells centred on source centres
+    (5 taps, half weights at both ends, wrap at the date line) and target edges on source edges (4 taps:
+    the 5th, zero-weight column must not leak its NaN).  Checked against the oracle AND the generic kernel."""
+    engine, _ = eng
+    from xarray_regrid_b200 import tables
+
+    if aligned_edges:
+        lat, lon = np.arange(-89.5, 90, 1.0), np.arange(0.5, 360, 1.0)
+        tlat, tlon = np.arange(-88.0, 90, 4.0), np.arange(2.0, 360, 4.0)
+    else:
+        lat, lon = np.arange(-90.0, 90.5, 1.0), np.arange(0.0, 360, 1.0)
+        tlat, tlon = np.arange(-88.0, 89, 4.0), np.arange(0.0, 360, 4.0)
+    rng = np.random.default_rng(31)
+    x = (0.5 + rng.random((5, lat.size, lon.size))).astype(dtype)
+    x[rng.random(x.shape) < 0.08] = np.nan
+    x[1, :, 40:48] = np.nan      # whole target columns missing
+    x[2, 60:70, :] = np.nan      # whole target rows missing
+    x[3] = 1.25                  # NaN-free slab: the fast path only
+    plan = _latlon_plan(engine, lat, lon, tlat, tlon)
+    assert not plan.pole_rows
+    xt = torch.from_numpy(x).cuda()
+    ring = plan._ring(5, lat.size, lon.size, xt.dtype)
+    assert ring is not None and ring.host.lane_cols == 4, "grid should qualify for the lanes variant"
+    assert int(ring.host.n_strips) <= int(ring.host.n_warps) <= 12
+    y = plan(xt, skipna=skipna, nan_threshold=0.5)
+    # skipna=False: NaN reaches a target only through non-zero taps (the reference's sparse weights)
+    want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=0.5,
+                            nan_through_zero_weights=False)
+    _check(y, want, RTOL[dtype])
+    plan.use_ring = False
+    _check(plan(xt, skipna=skipna, nan_threshold=0.5), want, RTOL[dtype])
+    assert tables.lane_owned_columns(plan.cols_band, ring.host.strip_l0, ring.host.n_warps) == 4
 
 
 def test_skipna_false_with_nans_uses_sparse_semantics(eng):

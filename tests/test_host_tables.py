@@ -236,3 +236,30 @@ def test_plan_chunks_respects_shared_memory_budget():
         big = tables.Bins(np.array([0], np.int32), np.array([2000], np.int32), np.ones(1, np.uint8),
                           np.zeros(1, np.int32), 2000, 0, 1)
         tables.plan_chunks(big, big, 8)
+
+
+def test_lane_owned_columns_eligibility():
+    """rg_row_ring_t.lane_cols: only regular 4:1 coarsening with full coverage qualifies."""
+    from xarray_regrid_b200 import engine
+
+    def ring_for(lat, lon, tlat, tlon, vec=2):
+        cols = tables.conservative_band(engine._axis(engine.AxisSpec(lon, tlon, "lon"), False), tlon)
+        rows = tables.conservative_band(engine._axis(engine.AxisSpec(lat, tlat, "lat"), True), tlat,
+                                        spherical=True)
+        return tables.row_ring_schedule(rows, 4, cols, vec), cols
+
+    lat025, lon025 = np.arange(-90, 90.25, 0.25), np.arange(0, 360, 0.25)
+    lat1, lon1 = np.arange(-90, 91, 1.0), np.arange(0, 360, 1.0)
+    for vec in (2, 4):  # fp64 / fp32 strip alignment
+        ring, cols = ring_for(lat025, lon025, lat1, lon1, vec)
+        assert ring.lane_cols == 4 and ring.n_strips <= ring.n_warps <= 12
+        assert all(b - a <= 31 for a, b in zip(ring.strip_l0[:-1], ring.strip_l0[1:]))
+        first = cols.idx[0].astype(np.int64)
+        assert (first % 2 == 0).all() and ((np.diff(first) - 4) % cols.n_src == 0).all()
+    # 2:1 coarsening, a regional target (uncovered edge cells) and a non-integer ratio do not qualify
+    ring, _ = ring_for(lat1, lon1, np.arange(-90, 91, 2.0), np.arange(0, 360, 2.0))
+    assert ring is None or ring.lane_cols == 0
+    ring, _ = ring_for(lat025[200:400], lon025[100:700], lat1[40:110], lon1[20:180])
+    assert ring is None or ring.lane_cols == 0
+    ring, _ = ring_for(lat025, lon025, np.arange(-90, 90.1, 0.7), np.arange(0, 360, 0.7))
+    assert ring is None or ring.lane_cols == 0

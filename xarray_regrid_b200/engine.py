@@ -140,6 +140,7 @@ class BandOp:
         self._dev: dict = {}
         self._rings: dict = {}
         self.use_ring = True  # tests flip this to exercise the generic kernel
+        self.use_lanes = True  # ... and this to exercise the two-phase ring kernel where the lanes variant applies
 
     def _host_bands(self, n_rows: int, n_cols: int):
         rows = self.rows_band if self.rows_band is not None else tables.identity_band(n_rows)
@@ -154,9 +155,11 @@ class BandOp:
         sms = max(sm_count(), 1)
         n_runs = int(min(rows.n_out, max(1, -(-2 * sms // max(batch, 1)))))
         vec = 2 if dtype == torch.float64 else 4
-        key = (n_runs, n_rows, n_cols, vec)
+        key = (n_runs, n_rows, n_cols, vec, self.use_lanes)
         if key not in self._rings:
             host = tables.row_ring_schedule(rows, n_runs, cols, vec)
+            if host is not None and not self.use_lanes:
+                host.lane_cols = 0
             self._rings[key] = None if host is None else DeviceRing(host, rows, dtype, self.device)
         return self._rings[key]
 
