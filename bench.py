@@ -288,14 +288,15 @@ def run_engine_arm(args) -> None:
     achieved = bytes_per_step / (avg_launch_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "kernel": "rg::conservative_ring_kernel<double, skipna=true, KW=5, 14 warps>",
+        "traffic": None, "kernel": "rg::conservative_lanes_kernel<double, skipna=true, 14 warps>",
         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_step,
         "launch_ms_avg": avg_launch_ms, "launch_ms_min": min(launch_ms),
     }
     traffic_file = ROOT / "profiles" / "traffic_conservative.json"
     if traffic_file.exists():
         try:
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch_8760")
+            per_step = json.loads(traffic_file.read_text()).get("dram_bytes_per_timestep")
+            roofline["traffic"] = None if per_step is None else round(per_step * args.timesteps)
         except Exception:  # noqa: BLE001
             pass
 
