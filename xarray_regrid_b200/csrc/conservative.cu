@@ -218,7 +218,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   //      axis, a ring that fits shared memory)
   if (ring_c && !pole && aligned && (static_cast<size_t>(W) * sizeof(T)) % 16 == 0 &&
       rows.k_max <= kRingMaxTaps && cols.k_max <= 8 && ring_c->n_runs > 0 && ring_c->n_strips > 0 &&
-      ring_c->n_warps >= 1 && ring_c->n_warps <= kRingMaxWarps && ring_c->max_live < kRingMaxSlots &&
+      ring_c->n_warps >= 1 && ring_c->n_warps <= kRingMaxWarps && ring_c->max_live <= kRingMaxLive &&
       ring_c->sched_row && ring_c->krec && ring_c->wrec && ring_c->run_first && ring_c->run_sched &&
       ring_c->strip_l0 && ring_c->strip_c0 && ring_c->strip_nc) {
     const int kw = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : cols.k_max <= 3 ? 3 : cols.k_max <= 5 ? 5 : 8;

@@ -36,7 +36,8 @@ struct RingDev {
   int n_runs, n_sched, max_live, pad_shift, n_strips, strip_cols_max, n_warps, lane_cols;
 };
 
-constexpr int kRingMaxSlots = 16;
+constexpr int kRingMaxSlots = 32;  // ring depth cap (a tap reaches at most 15 rows back: 4-bit tap_back)
+constexpr int kRingMaxLive = 15;
 constexpr int kRingMaxTaps = 8;   // row taps per output handled by the ring kernel
 constexpr int kRingMaxWarps = 24; // consumer warps
 
@@ -101,6 +102,12 @@ __device__ __forceinline__ uint32_t ld_acquire_smem(uint32_t addr) {
   asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed_smem(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.relaxed.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ void st_release_smem(uint32_t addr, uint32_t v) {
   asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -224,13 +231,16 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
     for (int p = ring.run_sched[run]; p < p1; ++p) {
       const long long off = static_cast<long long>(ring.sched_row[p]) * xrs;
       while (static_cast<int>(g - freed) >= ring_slots) {  // ring full: wait for the slowest warp
-        uint32_t m = ld_acquire_smem(flags0 + 4);
+        // relaxed loads pipeline (acquire loads would serialise: 12-24 round trips per poll); one fence
+        // below turns the poll into an acquire before the slot is overwritten
+        uint32_t m = ld_relaxed_smem(flags0 + 4);
         for (int w = 1; w < n_warps; ++w) {
-          const uint32_t d = ld_acquire_smem(flags0 + 4 * (1 + w));
+          const uint32_t d = ld_relaxed_smem(flags0 + 4 * (1 + w));
           if (static_cast<int>(d - m) < 0) m = d;
         }
         freed = m;
-        if (static_cast<int>(g - freed) >= ring_slots) __nanosleep(64);
+        if (static_cast<int>(g - freed) >= ring_slots) __nanosleep(32);
+        else fence_acq_rel_cta();
       }
       mbar_arrive_expect_tx(full0 + 8u * slot, row_bytes);
       tma_load_row(ring0 + static_cast<uint32_t>(slot) * row_stride, xb + off, row_bytes, full0 + 8u * slot);
