@@ -127,7 +127,13 @@ __device__ __forceinline__ double normalise_div(double so, double sv) {
   const double q = so * r;
   return fma(fma(-sv, q, so), r, q);
 }
-__device__ __forceinline__ float normalise_div(float so, float sv) { return so / sv; }
+__device__ __forceinline__ float normalise_div(float so, float sv) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(sv));  // 1 ulp seed
+  r = fmaf(r, fmaf(-sv, r, 1.0f), r);
+  const float q = so * r;
+  return fmaf(fmaf(-sv, q, so), r, q);  // residual correction: within 1 ulp of so / sv, no subroutine call
+}
 
 // {t, v} entry of the warp-private strip buffer.
 template <typename T, bool SKIPNA> struct TV;
@@ -219,7 +225,8 @@ __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row
 // producer: one thread streams the scheduled source rows of every task into the ring with TMA bulk copies
 template <typename T>
 __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long xbs, long long xrs,
-                                              const RingDev& ring, long long tasks, int ring_slots,
+                                              const RingDev& ring, const int32_t* sched_row, long long tasks,
+                                              int ring_slots,
                                               uint32_t row_bytes, int row_stride, uint32_t full0, uint32_t flags0,
                                               uint32_t ring0, int n_warps) {
   uint32_t g = 0, freed = 0;  // rows issued / rows released by every consumer warp
@@ -229,7 +236,7 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
     const T* xb = x + (task / ring.n_runs) * xbs;
     const int p1 = ring.run_sched[run + 1];
     for (int p = ring.run_sched[run]; p < p1; ++p) {
-      const long long off = static_cast<long long>(ring.sched_row[p]) * xrs;
+      const long long off = static_cast<long long>(sched_row[p]) * xrs;  // shared memory: no global load per row
       while (static_cast<int>(g - freed) >= ring_slots) {  // ring full: wait for the slowest warp
         // relaxed loads pipeline (acquire loads would serialise: 12-24 round trips per poll); one fence
         // below turns the poll into an acquire before the slot is overwritten
@@ -285,6 +292,8 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
     fence_mbar_init();
   }
   if (tid < 32) s_flags[tid] = 0;
+  int32_t* s_sched = reinterpret_cast<int32_t*>(smem + L.total);  // the row load order, staged once
+  for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
   __syncthreads();
 
   const long long tasks = batch * ring.n_runs;
@@ -293,7 +302,9 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
 
   // ================================================================ producer / sync warps
   if (warp == n_warps) {
-    if (lane == 0) ring_producer<T>(x, xbs, xrs, ring, tasks, ring_slots, row_bytes, L.row_stride, full0, flags0, ring0, n_warps);
+    if (lane == 0)
+      ring_producer<T>(x, xbs, xrs, ring, s_sched, tasks, ring_slots, row_bytes, L.row_stride, full0, flags0, ring0,
+                       n_warps);
     return;
   }
   if (warp > n_warps) {
@@ -501,6 +512,8 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   if (tid < 32) s_flags[tid] = 0;
   for (int i = tid; i < n_rows_out; i += blockDim.x) s_krec[i] = ring.krec[i];
   for (int i = tid; i < n_rows_out * kRingMaxTaps; i += blockDim.x) s_wrec[i] = static_cast<const T*>(ring.wrec)[i];
+  int32_t* s_sched = reinterpret_cast<int32_t*>(s_wrec + static_cast<size_t>(n_rows_out) * kRingMaxTaps);
+  for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
   __syncthreads();
 
   const long long tasks = batch * ring.n_runs;
@@ -508,7 +521,9 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   const uint32_t full0 = smem_u32(s_full), flags0 = smem_u32(s_flags), ring0 = smem_u32(smem);
 
   if (warp == n_warps) {
-    if (lane == 0) ring_producer<T>(x, xbs, xrs, ring, tasks, ring_slots, row_bytes, L.row_stride, full0, flags0, ring0, n_warps);
+    if (lane == 0)
+      ring_producer<T>(x, xbs, xrs, ring, s_sched, tasks, ring_slots, row_bytes, L.row_stride, full0, flags0, ring0,
+                       n_warps);
     return;
   }
   if (warp > n_warps) {
