@@ -1,6 +1,6 @@
 """Small driver for ncu: a few launches of the conservative kernel on a C2-shaped stack.
 
-    python tools/prof_conservative.py [--steps 256] [--no-ring] [--launches 3] [--dtype f64]
+    python tools/prof_conservative.py [--steps 256] [--no-ring] [--no-lanes] [--launches 3] [--dtype f64]
 """
 import argparse
 import sys
@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=256)
 ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--no-ring", action="store_true")
+ap.add_argument("--no-lanes", action="store_true")
 ap.add_argument("--no-skipna", action="store_true")
 ap.add_argument("--dtype", default="f64")
 ap.add_argument("--nan", type=float, default=0.10)
@@ -25,6 +26,7 @@ lat, lon = synthetic.grid_025()
 tlat, tlon = synthetic.grid_1()
 plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"))
 plan.use_ring = not a.no_ring
+plan.use_lanes = not a.no_lanes
 dtype = torch.float64 if a.dtype == "f64" else torch.float32
 x = synthetic.conservative_stack(a.steps, lat, lon, dtype=dtype, nan_fraction=a.nan)
 y = torch.empty((a.steps, 181, 360), dtype=dtype, device="cuda")
