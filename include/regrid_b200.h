@@ -71,8 +71,11 @@ typedef struct rg_band {
   int32_t n_out;
   int32_t k_max;
   int32_t n_src;
-  int32_t span; /* max over outputs of (largest - smallest tap index + 1); 0 = unknown.  Lets the
-                   library pick the shared-memory upsampling kernel for interpolation bands. */
+  int32_t span; /* max over outputs of (largest - smallest tap index + 1); 0 = unknown */
+  int32_t window_rows; /* rows axis of an interpolation band: the largest multiple of 4 (<= 32) such that
+                          every aligned group of that many consecutive outputs takes its taps from at most
+                          16 consecutive source indices; 0 = no such grouping / unknown.  Lets the library
+                          pick the shared-memory upsampling kernel (it stages 16 source rows per group). */
 } rg_band_t;
 
 /*
@@ -236,6 +239,19 @@ int rg_nearest(const void* x, void* y, int32_t in_type, int32_t out_type, int64_
                int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
                int32_t Ho, int32_t Wo, const int32_t* row_idx, const uint8_t* row_ok,
                const int32_t* col_idx, const uint8_t* col_ok, double fill, void* stream);
+
+/*
+ * Spline coefficients of the cubic method, in place: solves A c = y along `axis` (0: rows, 1: columns) of
+ * every slab of the dense-column [batch, H, W] fp64 stack, where A = L U is the banded (two sub-, two
+ * super-diagonals) not-a-knot collocation matrix of scipy's make_interp_spline(x, y, k=3)
+ * (scipy/interpolate/_bsplines.py; the reference reaches it through xarray's interp ->
+ * scipy.interpolate.interp1d(kind="cubic"), methods/interp.py:43-46).  The caller factors A without
+ * pivoting and passes lower = [l1 | l2] ([2, n]: L[i, i-1], L[i, i-2]) and upper = [1/d | u1 | u2]
+ * ([3, n]: 1/U[i, i], U[i, i+1], U[i, i+2]), n = H or W, device arrays.  RG_ERR_UNSUPPORTED when the
+ * factors do not fit shared memory (n > ~5800): use the truncated-inverse band pass then.
+ */
+int rg_spline_solve_f64(double* y, int64_t batch, int64_t y_batch_stride, int64_t y_row_stride, int32_t H,
+                        int32_t W, int32_t axis, const double* lower, const double* upper, void* stream);
 
 /*
  * The cubic spline's NaN rule (scipy interp1d: one NaN anywhere in the array makes the WHOLE result

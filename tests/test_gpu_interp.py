@@ -69,6 +69,39 @@ def test_c3_cubic_upsampling(engine):
     _check(y, want, 1e-11)  # spec: 1e-5 for fp32 input; the fp64 pipeline is ~1e-13
 
 
+@pytest.mark.parametrize("case", ["global", "irregular", "rows_only", "descending"])
+def test_cubic_lu_prefilter_matches_band_prefilter_and_oracle(engine, case):
+    """The O(n) banded LU substitution (rg_spline_solve_f64) and the truncated-inverse band pass are two
+    routes to scipy's spline coefficients: both must match the oracle (scipy itself) to 1e-11."""
+    rng = np.random.default_rng(21)
+    if case == "global":
+        (lat, lon), (tlat, tlon) = GRID_1, (np.arange(-89.9, 90, 0.7), np.arange(0.05, 359.9, 0.9))
+    elif case == "irregular":
+        lat, lon = np.sort(rng.uniform(-60, 60, 75)), np.sort(rng.uniform(10, 200, 130))
+        tlat, tlon = np.linspace(lat[0], lat[-1], 140), np.linspace(lon[0], lon[-1], 260)
+    elif case == "rows_only":
+        lat, lon = np.arange(0.0, 40.0, 1.0), np.arange(100.0, 133.0, 1.0)
+        tlat, tlon = np.arange(0.5, 38.0, 0.25), None
+    else:
+        lat, lon = np.arange(50.0, 10.0, -1.0), np.arange(100.0, 133.0, 1.0)
+        tlat, tlon = np.arange(11.0, 49.0, 0.5), np.arange(132.0, 100.0, -0.3)
+    x = rng.standard_normal((3, lat.size, lon.size))
+    if tlon is None:
+        plan = engine.InterpPlan(engine.AxisSpec(lat, tlat, "lat"), None, "cubic")
+        want = oi.regrid(x, [lat], [tlat], [-2], "cubic")
+    else:
+        plan = _plan(engine, lat, lon, tlat, tlon, "cubic")
+        want = oi.regrid_latlon(x, lat, lon, tlat, tlon, "cubic")
+    assert plan._lu is not None, "grid should qualify for the LU prefilter"
+    xt = torch.from_numpy(x).cuda()
+    y_lu = plan(xt)
+    plan.use_lu = False
+    y_band = plan(xt)
+    _check(y_lu, want, 1e-11, 1e-13)
+    _check(y_band, want, 1e-11, 1e-13)
+    assert torch.equal(xt.cpu(), torch.from_numpy(x)), "the in-place solve must not touch the input"
+
+
 def test_cubic_any_nan_makes_everything_nan(engine):
     """scipy interp1d(kind='cubic'): one NaN anywhere -> the whole result is NaN."""
     rng = np.random.default_rng(9)

@@ -263,3 +263,29 @@ def test_lane_owned_columns_eligibility():
     assert ring is None or ring.lane_cols == 0
     ring, _ = ring_for(lat025, lon025, np.arange(-90, 90.1, 0.7), np.arange(0, 360, 0.7))
     assert ring is None or ring.lane_cols == 0
+
+
+def test_band_window_rows_is_exact():
+    """rg_band_t.window_rows: regular upsampling gives 32, ratio ~2 a smaller multiple of 4, clustered
+    source points or shuffled targets 0 (the upsampling kernel then stays out of the way)."""
+    ax = tables.plain_axis(np.arange(-90.0, 91.0, 1.0))
+    assert tables.band_window_rows(tables.linear_band(ax, np.round(np.arange(-90, 90.05, 0.1), 10))) == 32
+    _, ev = tables.cubic_bands(ax, np.round(np.arange(-90, 90.05, 0.1), 10))
+    assert tables.band_window_rows(ev) == 32
+    half = tables.band_window_rows(tables.linear_band(ax, np.arange(-90, 90.01, 0.5)))
+    assert 0 < half < 32 and half % 4 == 0
+    rng = np.random.default_rng(3)
+    tgt = np.round(np.arange(-90, 90.05, 0.1), 10)
+    assert tables.band_window_rows(tables.linear_band(ax, rng.permutation(tgt))) == 0
+    clustered = tables.plain_axis(np.sort(np.r_[np.linspace(0, 1, 60), np.linspace(1.001, 100, 40)]))
+    band = tables.linear_band(clustered, np.linspace(0, 100, 400))
+    rows = tables.band_window_rows(band)
+    # the definition, checked by brute force
+    for cand in range(32, 0, -4):
+        fits = all(band.idx[:, k0:k0 + cand].max() - band.idx[:, k0:k0 + cand].min() + 1 <= 16
+                   for k0 in range(0, band.n_out, cand))
+        if fits:
+            break
+    else:
+        cand = 0
+    assert rows == cand

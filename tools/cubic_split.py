@@ -25,6 +25,17 @@ def t(fn, reps=5):
 c = plan.pre.run(x64, False, 0.0)
 y = torch.empty((64, 1801, 3600), dtype=torch.float64, device="cuda")
 print("cast fp32->fp64   %.3f ms" % t(lambda: x.double()))
-print("prefilter         %.3f ms" % t(lambda: plan.pre.run(x64, False, 0.0)))
+print("prefilter (band)  %.3f ms" % t(lambda: plan.pre.run(x64, False, 0.0)))
+Hf, Wf = plan.pre._out_hw(360, 181)
+print("prefilter (LU)    %.3f ms" % t(lambda: plan._coefficients_lu(x64, Hf, Wf)))
+from xarray_regrid_b200._lib import lib
+cc = plan._coefficients_lu(x64, Hf, Wf)
+st = torch.cuda.current_stream().cuda_stream
+for axis, name in ((0, "rows"), (1, "cols")):
+    e = plan._lu[name]
+    print("  solve axis %d      %.3f ms" % (axis, t(lambda: lib.rg_spline_solve_f64(cc.data_ptr(), 64, Hf * Wf, Wf, Hf, Wf, axis, e[1].data_ptr(), e[2].data_ptr(), st))))
+flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+print("nan flag          %.3f ms" % t(lambda: lib.rg_nan_flag_f64(x64.data_ptr(), 64, 181, 360, 181 * 360, 360, flag.data_ptr(), st)))
+print("poison            %.3f ms" % t(lambda: lib.rg_poison_if_f64(y.data_ptr(), y.numel(), flag.data_ptr(), st)))
 print("evaluate          %.3f ms" % t(lambda: plan.op.run(c, False, 0.0, out=y)))
 print("whole plan        %.3f ms" % t(lambda: plan(x)))

@@ -29,6 +29,7 @@ class rg_band_t(C.Structure):  # noqa: N801 - mirrors the C name
         ("k_max", C.c_int32),
         ("n_src", C.c_int32),
         ("span", C.c_int32),
+        ("window_rows", C.c_int32),
     ]
 
 
@@ -66,6 +67,10 @@ class rg_bins_t(C.Structure):  # noqa: N801 - mirrors the C name
     ]
 
 
+RG_OK = 0
+RG_ERR_UNSUPPORTED = -4  # include/regrid_b200.h
+
+
 def _load():
     if not LIB_PATH.exists():
         raise ImportError(
@@ -88,6 +93,7 @@ def _load():
         "rg_separable_f64": (C.c_int, [p, p, i64, i64, i64, i64, band, band, p, ring, p]),
         "rg_separable_f32": (C.c_int, [p, p, i64, i64, i64, i64, band, band, p, ring, p]),
         "rg_nearest": (C.c_int, [p, p, i32, i32, i64, i64, i64, i64, i32, i32, p, p, p, p, f64, p]),
+        "rg_spline_solve_f64": (C.c_int, [p, i64, i64, i64, i32, i32, i32, p, p, p]),
         "rg_nan_flag_f64": (C.c_int, [p, i64, i32, i32, i64, i64, p, p]),
         "rg_nan_flag_f32": (C.c_int, [p, i64, i32, i32, i64, i64, p, p]),
         "rg_poison_if_f64": (C.c_int, [p, i64, p, p]),

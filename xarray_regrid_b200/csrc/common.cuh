@@ -29,7 +29,7 @@ struct Band {
   const T* __restrict__ w;
   const int32_t* __restrict__ cnt;
   const uint8_t* __restrict__ cover;
-  int n_out, k_max, n_src, span;
+  int n_out, k_max, n_src, span, window_rows;
 };
 
 template <typename T>
@@ -44,6 +44,7 @@ inline int make_band(const rg_band_t* b, Band<T>* out) {
   out->k_max = b->k_max;
   out->n_src = b->n_src;
   out->span = b->span;
+  out->window_rows = b->window_rows;
   return RG_OK;
 }
 

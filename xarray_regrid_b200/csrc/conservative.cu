@@ -210,7 +210,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
 
   // ---- interpolation onto a much finer grid (write-bound): shared-memory upsampling kernel
   if (!skipna && !pole) {
-    rc = upsample_try_launch<T>(x, y, batch, xbs, xrs, ybs, rows, cols, rows.span, dev, stream);
+    rc = upsample_try_launch<T>(x, y, batch, xbs, xrs, ybs, rows, cols, dev, stream);
     if (rc != RG_ERR_UNSUPPORTED) return rc;
   }
 

@@ -80,6 +80,141 @@ poison_kernel(T* __restrict__ y, long long n, const int32_t* __restrict__ flag) 
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) y[i] = nan;
 }
 
+// ------------------------------------------------------------------ spline coefficient solve
+// The prefilter of the cubic method: scipy's make_interp_spline solves the banded not-a-knot collocation
+// system A c = y (two sub- and two super-diagonals) for every line along the interpolated axis.  The host
+// factors A = L U once per axis (no pivoting: the system is diagonally dominant; the host checks the
+// factorisation against scipy), the device runs the forward / backward substitution: one thread per line,
+// the five factor diagonals in shared memory (broadcast reads), values prefetched 8 at a time so the
+// recurrence is the only serial dependency.  O(n) per line instead of the O(n * 63) of the truncated inverse.
+//   forward   z_i = y_i - l1_i z_{i-1} - l2_i z_{i-2}
+//   backward  c_i = (z_i - u1_i c_{i+1} - u2_i c_{i+2}) * dinv_i
+template <int AXIS>
+__global__ void __launch_bounds__(128)
+spline_solve_kernel(double* __restrict__ y, long long batch, long long ybs, long long yrs, int H, int W,
+                    const double* __restrict__ lower, const double* __restrict__ upper) {
+  extern __shared__ double s_fac[];  // [5][n]: l1, l2, dinv, u1, u2
+  const int n = AXIS == 0 ? H : W;
+  const int per_slab = AXIS == 0 ? W : H;
+  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s_fac[i] = lower[i];
+  for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_fac[2 * n + i] = upper[i];
+  __syncthreads();
+  const double *l1 = s_fac, *l2 = s_fac + n, *dinv = s_fac + 2 * n, *u1 = s_fac + 3 * n, *u2 = s_fac + 4 * n;
+  const long long line = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (line >= batch * per_slab) return;
+  const long long b = line / per_slab;
+  const int j = static_cast<int>(line % per_slab);
+  double* p = y + b * ybs + (AXIS == 0 ? static_cast<long long>(j) : static_cast<long long>(j) * yrs);
+  const long long step = AXIS == 0 ? yrs : 1;
+
+  double z1 = 0.0, z2 = 0.0;
+  for (int i0 = 0; i0 < n; i0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (i0 + e < n) ? p[(i0 + e) * step] : 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = i0 + e;
+      if (i < n) {
+        const double zi = fma(-l2[i], z2, fma(-l1[i], z1, v[e]));
+        z2 = z1;
+        z1 = zi;
+        p[i * step] = zi;
+      }
+    }
+  }
+  double c1 = 0.0, c2 = 0.0;
+  for (int i0 = n - 1; i0 >= 0; i0 -= 8) {
+    double v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (i0 - e >= 0) ? p[(i0 - e) * step] : 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = i0 - e;
+      if (i >= 0) {
+        const double ci = fma(-u2[i], c2, fma(-u1[i], c1, v[e])) * dinv[i];
+        c2 = c1;
+        c1 = ci;
+        p[i * step] = ci;
+      }
+    }
+  }
+}
+
+// Lines along the contiguous axis: a CTA stages kTileLines whole lines in shared memory with coalesced
+// loads (odd row pitch: the per-line walkers hit distinct banks), one thread per line runs both
+// substitutions out of shared memory, the CTA writes the tile back.  One read and one write of the data.
+constexpr int kTileLines = 32;
+__global__ void __launch_bounds__(128)
+spline_solve_tile_kernel(double* __restrict__ y, long long n_lines, int H, long long ybs, long long yrs, int W,
+                         const double* __restrict__ lower, const double* __restrict__ upper) {
+  extern __shared__ double s_fac[];  // [5][W] factors, then [kTileLines][W | 1] data
+  const int n = W, pitch = W | 1;
+  double* tile = s_fac + 5 * n;
+  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s_fac[i] = lower[i];
+  for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_fac[2 * n + i] = upper[i];
+  const long long line0 = static_cast<long long>(blockIdx.x) * kTileLines;
+  const int lines = static_cast<int>(min(static_cast<long long>(kTileLines), n_lines - line0));
+  for (int l = 0; l < lines; ++l) {
+    const long long line = line0 + l;
+    const double* src = y + (line / H) * ybs + (line % H) * yrs;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) tile[l * pitch + j] = src[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < lines) {
+    const double *l1 = s_fac, *l2 = s_fac + n, *dinv = s_fac + 2 * n, *u1 = s_fac + 3 * n, *u2 = s_fac + 4 * n;
+    double* p = tile + threadIdx.x * pitch;
+    // values and factors are fetched 8 at a time so that only the recurrence itself is serial
+    double z1 = 0.0, z2 = 0.0;
+    for (int i0 = 0; i0 < n; i0 += 8) {
+      double v[8], a1[8], a2[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = min(i0 + e, n - 1);
+        v[e] = p[i];
+        a1[e] = l1[i];
+        a2[e] = l2[i];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const double zi = fma(-a2[e], z2, fma(-a1[e], z1, v[e]));
+        if (i0 + e < n) {
+          z2 = z1;
+          z1 = zi;
+          p[i0 + e] = zi;
+        }
+      }
+    }
+    double c1 = 0.0, c2 = 0.0;
+    for (int i0 = n - 1; i0 >= 0; i0 -= 8) {
+      double v[8], a1[8], a2[8], d[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = max(i0 - e, 0);
+        v[e] = p[i];
+        a1[e] = u1[i];
+        a2[e] = u2[i];
+        d[e] = dinv[i];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const double ci = fma(-a2[e], c2, fma(-a1[e], c1, v[e])) * d[e];
+        if (i0 - e >= 0) {
+          c2 = c1;
+          c1 = ci;
+          p[i0 - e] = ci;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int l = 0; l < lines; ++l) {
+    const long long line = line0 + l;
+    double* dst = y + (line / H) * ybs + (line % H) * yrs;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) dst[j] = tile[l * pitch + j];
+  }
+}
+
 }  // namespace rg
 
 extern "C" {
@@ -118,6 +253,42 @@ int rg_nearest(const void* x, void* y, int32_t in_type, int32_t out_type, int64_
     }
   }
   return RG_ERR_UNSUPPORTED;
+}
+
+int rg_spline_solve_f64(double* y, int64_t batch, int64_t ybs, int64_t yrs, int32_t H, int32_t W, int32_t axis,
+                        const double* lower, const double* upper, void* stream) {
+  if (!y || !lower || !upper) return RG_ERR_NULL;
+  if (batch < 0 || H <= 0 || W <= 0 || (axis != 0 && axis != 1) || yrs < W) return RG_ERR_SHAPE;
+  if (batch == 0) return RG_OK;
+  const int n = axis == 0 ? H : W;
+  const size_t smem = static_cast<size_t>(5) * n * sizeof(double);
+  rg::DeviceInfo dev;
+  const int rc = rg::device_info(&dev);
+  if (rc != RG_OK) return rc;
+  if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_UNSUPPORTED;  // caller uses the band pass
+  if (axis == 1) {  // contiguous lines: the staged-tile kernel when a tile fits shared memory
+    const size_t smem_t = smem + static_cast<size_t>(rg::kTileLines) * (W | 1) * sizeof(double);
+    if (smem_t <= static_cast<size_t>(dev.max_smem_optin)) {
+      if (smem_t > 48 * 1024)
+        RG_CUDA(cudaFuncSetAttribute(rg::spline_solve_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem_t)));
+      const long long n_lines = static_cast<long long>(batch) * H;
+      const long long tiles = (n_lines + rg::kTileLines - 1) / rg::kTileLines;
+      if (tiles > 0x7fffffffLL) return RG_ERR_SHAPE;
+      rg::spline_solve_tile_kernel<<<static_cast<unsigned>(tiles), 128, smem_t, static_cast<cudaStream_t>(stream)>>>(
+          y, n_lines, H, ybs, yrs, W, lower, upper);
+      return static_cast<int>(cudaGetLastError());
+    }
+  }
+  auto kern = axis == 0 ? rg::spline_solve_kernel<0> : rg::spline_solve_kernel<1>;
+  if (smem > 48 * 1024)
+    RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const long long lines = static_cast<long long>(batch) * (axis == 0 ? W : H);
+  const long long blocks = (lines + 127) / 128;
+  if (blocks > 0x7fffffffLL) return RG_ERR_SHAPE;
+  kern<<<static_cast<unsigned>(blocks), 128, smem, static_cast<cudaStream_t>(stream)>>>(y, batch, ybs, yrs, H, W,
+                                                                                     lower, upper);
+  return static_cast<int>(cudaGetLastError());
 }
 
 int rg_nan_flag_f64(const double* x, int64_t batch, int32_t H, int32_t W, int64_t xbs, int64_t xrs,

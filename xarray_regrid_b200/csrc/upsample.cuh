@@ -168,7 +168,8 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
       if (k < k1) {
 #pragma unroll
         for (int t = 0; t < KR; ++t) {
-          s_off[tid][t] = (n > 0 ? ri[t] - rmin : 0) * W;  // host contract (band span): < kUpRowCap rows
+          // host contract (window_rows): < kUpRowCap rows; clamped so a broken table cannot leave the window
+          s_off[tid][t] = (n > 0 ? min(ri[t] - rmin, kUpRowCap - 1) : 0) * W;
           s_rw[tid][t] = rw[t];
         }
         s_state[tid] = !cov ? 0 : (n == 0 ? 1 : 2);
@@ -203,11 +204,15 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
 // Eligibility + launch.  Returns RG_ERR_UNSUPPORTED when the generic kernels should be used instead.
 template <typename T>
 int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
-                        const Band<T>& rows, const Band<T>& cols, int rows_span, const DeviceInfo& dev,
+                        const Band<T>& rows, const Band<T>& cols, const DeviceInfo& dev,
                         cudaStream_t stream) {
   const int W = cols.n_src, Wo = cols.n_out;
   if (rows.k_max > 4 || cols.k_max > 4) return RG_ERR_UNSUPPORTED;
-  if (rows_span <= 0 || rows_span > kUpRowCap) return RG_ERR_UNSUPPORTED;
+  // the host guarantees (rg_band_t.window_rows) that every aligned group of `band_rows` output rows takes its
+  // taps from at most kUpRowCap consecutive source rows: the staged window
+  int band_rows = rows.window_rows;
+  if (band_rows < kUpRowsPerSync || band_rows % kUpRowsPerSync != 0) return RG_ERR_UNSUPPORTED;
+  if (band_rows > kUpBandRows) band_rows = kUpBandRows;
   // heavy taps (4 fp64 taps per column) use 512-thread CTAs so that the per-thread tap registers halve
   const int nt = (cols.k_max > 2 && sizeof(T) == 8) ? 512 : 256;
   if (Wo < 2 * W || Wo > nt * 4 * 4) return RG_ERR_UNSUPPORTED;  // upsampling, <= 4 groups / thread
@@ -221,13 +226,6 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   const int kr = rows.k_max <= 1 ? 1 : rows.k_max <= 2 ? 2 : 4;
   const int kc = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : 4;
   using Kernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, Band<T>, int);
-  // output rows per task: the band's source rows (span + rows advanced inside the band) must fit the
-  // staged window; bands are sorted, so the advance is about band_rows * H / Ho
-  const int H = rows.n_src, Ho = rows.n_out;
-  int band_rows = static_cast<int>((static_cast<long long>(kUpRowCap - rows_span - 1) * Ho) / (H > 0 ? H : 1));
-  if (band_rows > kUpBandRows) band_rows = kUpBandRows;
-  band_rows = band_rows / kUpRowsPerSync * kUpRowsPerSync;
-  if (band_rows < kUpRowsPerSync) return RG_ERR_UNSUPPORTED;
   Kernel kern = nullptr;
 #define RG_UP(KR_, KC_, G_)                                                                              \
   if (kr == KR_ && kc == KC_ && groups == G_) {                                                          \

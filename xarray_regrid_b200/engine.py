@@ -56,7 +56,7 @@ class DeviceBand:
             span = 0
         self.c = rg_band_t(
             self.idx.data_ptr(), self.w.data_ptr(), self.cnt.data_ptr(), self.cover.data_ptr(),
-            band.n_out, band.k_max, band.n_src, span,
+            band.n_out, band.k_max, band.n_src, span, tables.band_window_rows(band),
         )
 
     @property
@@ -335,6 +335,58 @@ class InterpPlan:
             # the second (column) pass blanks everything.  (The reference's axis order is the iteration
             # order of a Python set, interp.py:39; the engine and the oracle fix it to rows, then cols.)
             self.all_nan = rows is not None and cols is not None and not bool(r_ev.cover.all())
+            # O(n) prefilter: banded LU substitution per line (rg_spline_solve_f64) instead of the +-31-tap
+            # truncated inverse, when both formatted axes are plain index maps of the source (no pole rows)
+            self.use_lu = True  # tests flip this to exercise the band prefilter
+            self._lu = {}
+            for name, spec, axis in (("rows", rows, rows_axis), ("cols", cols, cols_axis)):
+                if spec is None:
+                    self._lu[name] = None
+                    continue
+                fac = None if axis.has_pole_rows else tables.cubic_lu(axis)
+                if fac is None:
+                    self._lu = None
+                    break
+                self._lu[name] = (
+                    torch.from_numpy(np.ascontiguousarray(axis.source, dtype=np.int32)).to(self.device),
+                    torch.from_numpy(np.ascontiguousarray(fac[0])).to(self.device),
+                    torch.from_numpy(np.ascontiguousarray(fac[1])).to(self.device),
+                )
+            self._lu_maps: dict = {}
+
+    def _coefficients_lu(self, xs: torch.Tensor, Hf: int, Wf: int):
+        """Spline coefficients on the formatted grid: gather (sort / wrap padding) + in-place banded solves.
+        Returns None when the library declines (factors larger than shared memory)."""
+        B, H, W = xs.shape
+        if (H, W) not in self._lu_maps:
+            def index_map(entry, n):
+                if entry is not None:
+                    return entry[0]
+                return torch.arange(n, dtype=torch.int32, device=self.device)
+            ri, ci = index_map(self._lu["rows"], H), index_map(self._lu["cols"], W)
+            self._lu_maps[(H, W)] = (ri, ci, torch.ones(ri.numel(), dtype=torch.uint8, device=self.device),
+                                     torch.ones(ci.numel(), dtype=torch.uint8, device=self.device))
+        ri, ci, rok, cok = self._lu_maps[(H, W)]
+        if ri.numel() != Hf or ci.numel() != Wf:
+            raise ValueError(f"data is [{H}, {W}] but the plan's formatted grid is [{Hf}, {Wf}]")
+        if xs.stride(2) != 1:
+            xs = xs.contiguous()
+        stream = _stream_ptr(xs.device)
+        coeff = torch.empty((B, Hf, Wf), dtype=torch.float64, device=xs.device)
+        check(lib.rg_nearest(xs.data_ptr(), coeff.data_ptr(), _TYPE_CODE[xs.dtype], _TYPE_CODE[torch.float64], B,
+                             xs.stride(0) if B > 1 else H * xs.stride(1), xs.stride(1), Hf * Wf, Hf, Wf,
+                             ri.data_ptr(), rok.data_ptr(), ci.data_ptr(), cok.data_ptr(), float("nan"), stream),
+              "rg_nearest")
+        for axis, name in ((0, "rows"), (1, "cols")):
+            entry = self._lu[name]
+            if entry is None:
+                continue
+            rc = lib.rg_spline_solve_f64(coeff.data_ptr(), B, Hf * Wf, Wf, Hf, Wf, axis, entry[1].data_ptr(),
+                                         entry[2].data_ptr(), stream)
+            if rc == _lib.RG_ERR_UNSUPPORTED:
+                return None
+            check(rc, "rg_spline_solve")
+        return coeff
 
     # nearest on integers (or out_dtype="same"): pure gather kernel
     def _gather_tables(self, n_rows: int, n_cols: int):
@@ -407,7 +459,9 @@ class InterpPlan:
                                       x3.stride(1), flag.data_ptr(), stream), "rg_nan_flag")
         for s0 in range(0, B, self.chunk):
             xs = x3[s0:s0 + self.chunk]
-            coeff = self.pre.run(xs, False, 0.0)
+            coeff = self._coefficients_lu(xs, Hf, Wf) if (self._lu is not None and self.use_lu) else None
+            if coeff is None:
+                coeff = self.pre.run(xs, False, 0.0)
             self.op.run(coeff, False, 0.0, out=y[s0:s0 + self.chunk])
         if B:
             check(lib.rg_poison_if_f64(y.data_ptr(), y.numel(), flag.data_ptr(), stream), "rg_poison_if")

@@ -472,6 +472,26 @@ def lane_owned_columns(cols: Band, strip_l0: np.ndarray, n_warps: int, step: int
     return step
 
 
+def band_window_rows(band: "Band", cap: int = 16, max_rows: int = 32, step: int = 4) -> int:
+    """``rg_band_t.window_rows``: the largest multiple of ``step`` (<= ``max_rows``) such that every aligned
+    group of that many consecutive outputs takes its taps from at most ``cap`` consecutive source indices
+    (0 if even groups of ``step`` do not).  Exact, from the band's own indices: irregular source spacing or
+    unsorted targets simply yield a small value (or 0) instead of breaking the upsampling kernel's window."""
+    live = (np.arange(band.k_max)[:, None] < band.cnt[None, :]) & (band.cover[None, :] > 0)
+    real = live & (band.idx < band.n_src)
+    if band.n_out == 0 or not real.any():
+        return 0
+    hi = np.where(real, band.idx, -1).max(axis=0).astype(np.int64)
+    lo = np.where(real, band.idx, np.iinfo(np.int32).max).min(axis=0).astype(np.int64)
+    for rows in range(max_rows, 0, -step):
+        starts = np.arange(0, band.n_out, rows)
+        g_hi = np.maximum.reduceat(hi, starts)
+        g_lo = np.minimum.reduceat(lo, starts)
+        if np.all((g_hi < 0) | (g_hi - g_lo + 1 <= cap)):
+            return rows
+    return 0
+
+
 # ------------------------------------------------------------ interpolation bands (xr.interp)
 def _restore_not_needed(n_out):
     return None
@@ -572,6 +592,67 @@ def cubic_bands(axis: FormattedAxis, tgt, rel_cut: float = 1e-18):
     ev = Band(e_idx, e_w, np.full(t.size, 4, np.int32), cover.astype(np.uint8), n, None,
               {"pole_rows": False, "method": "cubic-evaluate"})
     return pre, ev
+
+
+def cubic_lu(axis: FormattedAxis):
+    """LU factors (no pivoting) of the not-a-knot collocation matrix of ``make_interp_spline(x, y, k=3)`` on
+    the formatted axis, for ``rg_spline_solve_f64``: ``(lower [2, n], upper [3, n])`` with
+    ``lower = [L[i,i-1], L[i,i-2]]`` and ``upper = [1/U[i,i], U[i,i+1], U[i,i+2]]``, or ``None`` when the
+    matrix is not penta-diagonal, a pivot is tiny, or the substitution does not reproduce scipy's own
+    coefficients to 1e-13 (then the truncated-inverse band of ``cubic_bands`` is used).
+    """
+    from scipy.interpolate import BSpline, make_interp_spline
+
+    x = np.asarray(axis.values, dtype=np.float64)
+    n = x.size
+    if n < 6:
+        return None
+    probe = np.random.default_rng(12345).standard_normal((n, 3))
+    spl = make_interp_spline(x, probe, k=3, check_finite=False)
+    a = BSpline.design_matrix(x, spl.t, 3).todia()
+    diag = {d: np.zeros(n) for d in range(-2, 3)}  # diag[d][i] = A[i, i + d]
+    for off, data in zip(a.offsets, a.data):
+        cols = np.arange(max(off, 0), min(n, n + off))
+        if abs(int(off)) > 2:
+            if np.any(data[cols] != 0.0):
+                return None  # not penta-diagonal
+            continue
+        diag[int(off)][cols - off] = data[cols]
+    d0, u1, u2 = diag[0].copy(), diag[1].copy(), diag[2].copy()
+    s1, s2 = diag[-1].copy(), diag[-2].copy()  # A[i, i-1], A[i, i-2]
+    l1, l2 = np.zeros(n), np.zeros(n)
+    for i in range(n):
+        # eliminate A[i, i-2] with row i-2, then A[i, i-1] with row i-1 (rows above are already U rows)
+        if i >= 2:
+            l2[i] = s2[i] / d0[i - 2]
+            s1[i] -= l2[i] * u1[i - 2]
+            d0[i] -= l2[i] * u2[i - 2]
+        if i >= 1:
+            l1[i] = s1[i] / d0[i - 1]
+            d0[i] -= l1[i] * u1[i - 1]
+            u1[i] -= l1[i] * u2[i - 1]
+        if not np.isfinite(d0[i]) or abs(d0[i]) < 1e-10 * max(1.0, abs(diag[0]).max()):
+            return None
+    dinv = 1.0 / d0
+    # the device's recurrences, checked against scipy's banded LAPACK solve
+    z = probe.copy()
+    for i in range(n):
+        if i >= 1:
+            z[i] -= l1[i] * z[i - 1]
+        if i >= 2:
+            z[i] -= l2[i] * z[i - 2]
+    c = z
+    for i in range(n - 1, -1, -1):
+        acc = c[i].copy()
+        if i + 1 < n:
+            acc -= u1[i] * c[i + 1]
+        if i + 2 < n:
+            acc -= u2[i] * c[i + 2]
+        c[i] = acc * dinv[i]
+    ref = np.asarray(spl.c)
+    if not np.all(np.abs(c - ref) <= 1e-13 * np.abs(ref).max()):
+        return None
+    return np.stack([l1, l2]), np.stack([dinv, u1, u2])
 
 
 # ------------------------------------------------------------- group-by bins (most_common / stat)
