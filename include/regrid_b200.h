@@ -38,7 +38,7 @@ extern "C" {
 #define RG_ERR_UNSUPPORTED (-4)
 #define RG_ERR_ALIGN (-5)
 
-#define RG_ABI_VERSION 1
+#define RG_ABI_VERSION 2 /* 2: rg_band_t.window_rows, rg_row_ring_t.lane_cols, rg_mode max_bin_rows/cols, rg_spline_solve_f64 */
 
 /* ABI version of the loaded library (== RG_ABI_VERSION of the header it was built from). */
 int rg_abi_version(void);

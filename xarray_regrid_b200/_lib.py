@@ -12,7 +12,7 @@ from pathlib import Path
 _CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = _CSRC / "libregrid_b200.so"
 
-RG_ABI_VERSION = 1
+RG_ABI_VERSION = 2
 
 
 class RegridB200Error(RuntimeError):
