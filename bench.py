@@ -235,7 +235,10 @@ def run_engine_arm(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    from xarray_regrid_b200 import engine, synthetic
+    from xarray_regrid_b200 import engine, sharding, synthetic
+
+    # one process per GPU: keep the rank (and the pinned buffers it allocates) on the GPU's NUMA node
+    numa_cores = sharding.bind_to_gpu_numa_node(local_rank) if world > 1 else None
 
     lat, lon = synthetic.grid_025()
     tlat, tlon = synthetic.grid_1()
@@ -366,6 +369,7 @@ def run_engine_arm(args) -> None:
                 "timesteps_per_gpu": steps_per_stack,
                 "bytes_per_step_per_gpu": bytes_per_step,
                 "parallelism": f"time-sharded x{world}, no collective",
+                "rank0_cpu_affinity": (f"{len(numa_cores)} cores local to the GPU (NVML)" if numa_cores else "unchanged"),
                 "l2": f"inputs larger than L2 ({steps_per_stack * H * W * 8 / 1e9:.1f} GB read per step, 126 MB L2)",
             },
             "roofline": roofline,

@@ -30,3 +30,31 @@ def regrid_sharded(plan, x_full, rank: int, world_size: int, **kw):
     array, a host tensor, ...); only the rank's block is touched."""
     start, stop = shard_bounds(x_full.shape[0], world_size, rank)
     return start, stop, plan(x_full[start:stop], **kw)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> list[int] | None:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (same NUMA node
+    / PCIe root).  Pinned host buffers allocated afterwards land in that node's memory, so the H2D / D2H
+    streams of the ranks do not cross the inter-socket link.  Returns the cores, or None when NVML or the
+    affinity call is unavailable (the process is then left alone)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            n_cpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = [c for c in cores if c in allowed]
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:  # noqa: BLE001 - best effort: no NVML, no permission, non-Linux
+        return None
