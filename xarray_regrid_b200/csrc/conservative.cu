@@ -228,9 +228,9 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     const RingLayout probe =
         lanes ? ring_layout<T>(W, 31, false, 0, 0, 0)
               : ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, 0);
-    // the lanes variant stages the per-row records and weights (16 + 8 * sizeof(T) bytes per target row)
-    // ... and both variants stage the row load order (4 bytes per scheduled row)
-    const size_t row_tables = (lanes ? static_cast<size_t>(rows.n_out) * (16 + kRingMaxTaps * sizeof(T)) : 0) +
+    // both variants stage the per-row records and weights (16 + 8 * sizeof(T) bytes per target row) and the row
+    // load order (4 bytes per scheduled row) in shared memory
+    const size_t row_tables = static_cast<size_t>(rows.n_out) * (16 + kRingMaxTaps * sizeof(T)) +
                               static_cast<size_t>(ring_c->n_sched) * sizeof(int32_t);
     const long long room = static_cast<long long>(dev.max_smem_optin) - static_cast<long long>(probe.total) -
                            static_cast<long long>(row_tables);
@@ -257,7 +257,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
                    ring_c->n_warps,
                    ring_c->lane_cols};
       using RingKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev,
-                                  T, int);
+                                  T, int, int);
       const int warps = ring.n_warps + 2;  // + producer + sync
       const bool small = warps <= 14;
       RingKernel kern = nullptr;
@@ -287,7 +287,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       const size_t smem_r = L.total + row_tables;
       RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_r)));
       kern<<<static_cast<unsigned>(grid), warps * 32, smem_r, stream>>>(x, y, batch, xbs, xrs, ybs, cols, ring, thr,
-                                                                       slots);
+                                                                       slots, rows.n_out);
       return static_cast<int>(cudaGetLastError());
     }
   }

@@ -276,7 +276,8 @@ __device__ __forceinline__ void ring_sync(const RingDev& ring, long long tasks, 
 template <typename T, bool SKIPNA, int KW, int MAXWARPS>
 __global__ void __launch_bounds__(MAXWARPS * 32, 1)
 conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
-                         long long xrs, long long ybs, Band<T> cols, RingDev ring, T thr, int ring_slots) {
+                         long long xrs, long long ybs, Band<T> cols, RingDev ring, T thr, int ring_slots,
+                         int n_rows_out) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int W = cols.n_src, Wo = cols.n_out;
   const int pad_shift = ring.pad_shift;
@@ -292,7 +293,12 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
     fence_mbar_init();
   }
   if (tid < 32) s_flags[tid] = 0;
-  int32_t* s_sched = reinterpret_cast<int32_t*>(smem + L.total);  // the row load order, staged once
+  // per target row tables and the row load order, staged once: no global load on the per-row paths
+  int4* s_krec = reinterpret_cast<int4*>(smem + L.total);
+  T* s_wrec = reinterpret_cast<T*>(smem + L.total + static_cast<size_t>(n_rows_out) * 16);
+  int32_t* s_sched = reinterpret_cast<int32_t*>(s_wrec + static_cast<size_t>(n_rows_out) * kRingMaxTaps);
+  for (int i = tid; i < n_rows_out; i += blockDim.x) s_krec[i] = ring.krec[i];
+  for (int i = tid; i < n_rows_out * kRingMaxTaps; i += blockDim.x) s_wrec[i] = static_cast<const T*>(ring.wrec)[i];
   for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
   __syncthreads();
 
@@ -316,7 +322,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
   const T nan = quiet_nan<T>();
   using Entry = TV<T, SKIPNA>;
   Entry* s_tv = reinterpret_cast<Entry*>(smem + L.off_strip + static_cast<size_t>(warp) * L.strip_bytes);
-  const T* wrec = static_cast<const T*>(ring.wrec);
+  const T* wrec = s_wrec;
   uint32_t gbase = 0;    // ring position of the current run's first row
   uint32_t newest_g = 0; // ring position + 1 of the newest row needed so far
   int newest = ring_slots - 1;
@@ -352,10 +358,8 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
     const int run = static_cast<int>(task % ring.n_runs);
     const long long b = task / ring.n_runs;
     const int k0 = ring.run_first[run], k1 = ring.run_first[run + 1];
-    int4 rec_n = ring.krec[k0];
     for (int k = k0; k < k1; ++k) {
-      const int4 rec = rec_n;  // {need, release, kcnt (-1: latitude not covered), packed tap_back}
-      if (k + 1 < k1) rec_n = ring.krec[k + 1];  // prefetch: hides the global-load latency
+      const int4 rec = s_krec[k];  // {need, release, kcnt (-1: latitude not covered), packed tap_back}
       const uint32_t need_g = gbase + static_cast<uint32_t>(rec.x);
       const int cnt = rec.z > 0 ? rec.z : 0;
 
