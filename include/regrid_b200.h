@@ -147,13 +147,13 @@ typedef struct rg_row_ring {
  * Replaces apply_weights (methods/conservative.py:181-208) plus the coverage mask of
  * conservative.py:161-164 in ONE pass over x (no fillna/notnull/divide/where passes).
  * `valid_thr` is get_valid_threshold(nan_threshold) (conservative.py:211-216), computed
- * by the caller.  `pole` is NULL or a device [batch, 2] array holding the longitude-mean
- * of the first / last source row (rg_row_nanmean_*), referenced by idx == H / H+1.
+ * by the caller.  `pole` is NULL or a device [batch, 2, W] array whose rows hold the
+ * longitude-mean of the first / last source row repeated W times (rg_row_nanmean_*),
+ * referenced by idx == H / H+1: the synthetic pole rows are ordinary, 16-byte aligned rows.
  * H = rows.n_src, W = cols.n_src, Ho = rows.n_out, Wo = cols.n_out.  y is dense
  * [batch, Ho, Wo] with batch stride y_batch_stride.  `ring` is NULL or the row-ring
  * schedule above; the library silently uses the generic kernel when the ring kernel's
- * preconditions (16-byte aligned rows, no pole rows, <= 8 taps per axis, ring fits shared
- * memory) do not hold.
+ * preconditions (16-byte aligned rows, <= 8 taps per axis, ring fits shared memory) do not hold.
  */
 int rg_conservative_f64(const double* x, double* y, int64_t batch,
                         int64_t x_batch_stride, int64_t x_row_stride, int64_t y_batch_stride,
@@ -167,8 +167,8 @@ int rg_conservative_f32(const float* x, float* y, int64_t batch,
                         const rg_row_ring_t* ring, void* stream);
 
 /*
- * Longitude-mean (NaN-skipping) of the first and last row of every slab:
- * pole[b,0] = nanmean(x[b,0,:]), pole[b,1] = nanmean(x[b,H-1,:]); all-NaN -> NaN.
+ * Longitude-mean (NaN-skipping) of the first and last row of every slab, written as full rows:
+ * pole[b,0,:] = nanmean(x[b,0,:]), pole[b,1,:] = nanmean(x[b,H-1,:]); all-NaN -> NaN.  pole is [batch, 2, W].
  * Replaces the `.mean(lon_coord)` of format_lat (utils.py:320-333).
  */
 int rg_row_nanmean_f64(const double* x, double* pole, int64_t batch, int32_t H, int32_t W,

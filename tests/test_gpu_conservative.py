@@ -194,11 +194,42 @@ def test_cell_centred_grid_with_pole_rows_and_wrap(eng, dtype):
     x[3, 40:44, 100:104] = np.nan
     plan = _latlon_plan(engine, lat, lon, tlat, tlon)
     assert plan.rows_band.meta["pole_rows"]
-    for skipna, thr in [(True, 1.0), (True, 0.3), (False, 1.0)]:
-        y = plan(torch.from_numpy(x).cuda(), skipna=skipna, nan_threshold=thr)
-        want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr,
-                                nan_through_zero_weights=False)
-        _check(y, want, RTOL[dtype])
+    for kernel in ("ring", "generic"):  # the pole rows are ordinary rows of the TMA ring
+        _pick(plan, kernel)
+        if kernel == "ring":
+            assert plan._ring(4, lat.size, lon.size, torch.from_numpy(x).dtype) is not None
+        for skipna, thr in [(True, 1.0), (True, 0.3), (False, 1.0)]:
+            y = plan(torch.from_numpy(x).cuda(), skipna=skipna, nan_threshold=thr)
+            want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr,
+                                    nan_through_zero_weights=False)
+            _check(y, want, RTOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cell_centred_quarter_degree_grid_all_kernels(eng, dtype):
+    """Cell-centred 0.25 deg global grid (-89.875 .. 89.875, 0.125 .. 359.875) -> 1 deg: format_lat adds pole
+    rows (zero area under the spherical correction), target edges fall on source edges (4 taps), the columns
+    qualify for the register-resident kernel after re-stripping; checked against the oracle for every kernel
+    and through the host-buffer pipeline."""
+    engine, _ = eng
+    rng = np.random.default_rng(6)
+    lat, lon = np.arange(-89.875, 90, 0.25), np.arange(0.125, 360, 0.25)
+    tlat, tlon = np.arange(-90.0, 91, 1.0), np.arange(0.0, 360, 1.0)
+    x = (0.5 + rng.random((3, lat.size, lon.size))).astype(dtype)
+    x[rng.random(x.shape) < 0.05] = np.nan
+    x[1, 0, :] = np.nan  # all-NaN edge row -> NaN pole row
+    plan = _latlon_plan(engine, lat, lon, tlat, tlon)
+    assert plan.rows_band.meta["pole_rows"]
+    xt = torch.from_numpy(x).cuda()
+    ring = plan._ring(3, lat.size, lon.size, xt.dtype)
+    assert ring is not None and ring.host.lane_cols == 4
+    want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=True, nan_threshold=0.5)
+    for kernel in KERNELS:
+        _pick(plan, kernel)
+        _check(plan(xt, skipna=True, nan_threshold=0.5), want, RTOL[dtype])
+    _pick(plan, "lanes")
+    y_host = plan.apply_host(torch.from_numpy(x).pin_memory(), skipna=True, nan_threshold=0.5, chunk_batch=2)
+    _check(y_host, want, RTOL[dtype])
 
 
 def test_descending_source_and_reversed_target(eng):

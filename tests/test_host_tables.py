@@ -126,11 +126,17 @@ def test_row_ring_schedule_invariants(n_runs, descending):
         assert ring.sched_row.size == 719  # every source row with non-zero weight, exactly once
 
 
-def test_row_ring_schedule_rejects_pole_rows():
-    rows = tables.conservative_band(tables.format_lat_axis(np.arange(-89.0, 90, 2)),
-                                    np.arange(-90.0, 91, 1), spherical=True)
-    if (rows.idx >= rows.n_src).any():
-        assert tables.row_ring_schedule(rows, 1) is None
+def test_row_ring_schedule_schedules_pole_rows_like_any_row():
+    """The synthetic pole rows (indices n_src, n_src + 1) are loaded from the [batch, 2, W] pole buffer."""
+    # (with the spherical correction the pole rows have zero area and are dropped from conservative bands;
+    # they carry weight for the interpolation methods and for conservative regridding of a plain axis)
+    rows = tables.linear_band(tables.format_lat_axis(np.arange(-89.0, 90, 2)), np.arange(-90.0, 91, 1))
+    assert (rows.idx >= rows.n_src).any()
+    ring = tables.row_ring_schedule(rows, 3)
+    assert ring is not None
+    virtual = ring.sched_row[ring.sched_row >= rows.n_src]
+    assert set(virtual.tolist()) <= {rows.n_src, rows.n_src + 1} and virtual.size >= 1
+    assert ring.sched_row.max() <= rows.n_src + 1
 
 
 # ------------------------------------------------------------------ interpolation / bin tables (CPU)

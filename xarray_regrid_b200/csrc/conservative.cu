@@ -79,7 +79,7 @@ conservative_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch,
                   val[i].v[e] = (j + e < W) ? ld_stream<T, 1>(xb + off + j + e).v[0] : T(0);
               }
             } else {
-              const T pv = pole[b * 2 + (-off - 1)];
+              const T pv = pole[(b * 2 + (-off - 1)) * static_cast<long long>(W)];
 #pragma unroll
               for (int e = 0; e < VEC; ++e) val[i].v[e] = pv;
             }
@@ -160,12 +160,14 @@ row_nanmean_kernel(const T* __restrict__ x, T* __restrict__ pole, long long batc
   }
   if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = n; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double ts = 0.0;
-    long long tn = 0;
-    for (int i = 0; i < 8; ++i) { ts += s_sum[i]; tn += s_cnt[i]; }
-    pole[b * 2 + which] = tn > 0 ? static_cast<T>(ts / static_cast<double>(tn)) : quiet_nan<T>();
-  }
+  // every thread folds the 8 partials in the same order, then the mean is written as a FULL row of W
+  // copies: the pole rows are ordinary rows for the TMA row-ring kernels (and element 0 for the generic one)
+  double ts = 0.0;
+  long long tn = 0;
+  for (int i = 0; i < 8; ++i) { ts += s_sum[i]; tn += s_cnt[i]; }
+  const T mean = tn > 0 ? static_cast<T>(ts / static_cast<double>(tn)) : quiet_nan<T>();
+  T* out = pole + (b * 2 + which) * static_cast<long long>(W);
+  for (int j = threadIdx.x; j < W; j += 256) out[j] = mean;
 }
 
 template <typename T>
@@ -214,9 +216,10 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     if (rc != RG_ERR_UNSUPPORTED) return rc;
   }
 
-  // ---- fast path: TMA row-ring kernel (needs 16-byte aligned rows, no pole rows, <= 8 taps per
+  // ---- fast path: TMA row-ring kernels (need 16-byte aligned rows, <= 8 taps per
   //      axis, a ring that fits shared memory)
-  if (ring_c && !pole && aligned && (static_cast<size_t>(W) * sizeof(T)) % 16 == 0 &&
+  if (ring_c && aligned && (static_cast<size_t>(W) * sizeof(T)) % 16 == 0 &&
+      (!pole || reinterpret_cast<uintptr_t>(pole) % 16 == 0) &&
       rows.k_max <= kRingMaxTaps && cols.k_max <= 8 && ring_c->n_runs > 0 && ring_c->n_strips > 0 &&
       ring_c->n_warps >= 1 && ring_c->n_warps <= kRingMaxWarps && ring_c->max_live <= kRingMaxLive &&
       ring_c->sched_row && ring_c->krec && ring_c->wrec && ring_c->run_first && ring_c->run_sched &&
@@ -255,7 +258,9 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
                    ring_c->n_strips,
                    ring_c->strip_cols_max,
                    ring_c->n_warps,
-                   ring_c->lane_cols};
+                   ring_c->lane_cols,
+                   pole,
+                   rows.n_src};
       using RingKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev,
                                   T, int, int);
       const int warps = ring.n_warps + 2;  // + producer + sync
@@ -357,7 +362,7 @@ int conservative_host(const T* xh, T* yh, int64_t batch, int64_t chunk, const rg
   const int64_t H = rows->n_src, W = cols->n_src, Ho = rows->n_out, Wo = cols->n_out;
   const size_t in_b = round256(static_cast<size_t>(chunk) * H * W * sizeof(T));
   const size_t out_b = round256(static_cast<size_t>(chunk) * Ho * Wo * sizeof(T));
-  const size_t pole_b = round256(static_cast<size_t>(chunk) * 2 * sizeof(T));
+  const size_t pole_b = round256(static_cast<size_t>(chunk) * 2 * W * sizeof(T));
   if (ws_bytes < kSlots * (in_b + out_b + pole_b)) return RG_ERR_SHAPE;
   if (reinterpret_cast<uintptr_t>(ws) % 256 != 0) return RG_ERR_ALIGN;
 
@@ -461,7 +466,7 @@ size_t rg_conservative_host_workspace(int64_t chunk_batch, int32_t H, int32_t W,
   if (chunk_batch <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || elem_size <= 0) return 0;
   const size_t in_b = rg::round256(static_cast<size_t>(chunk_batch) * H * W * elem_size);
   const size_t out_b = rg::round256(static_cast<size_t>(chunk_batch) * Ho * Wo * elem_size);
-  const size_t pole_b = rg::round256(static_cast<size_t>(chunk_batch) * 2 * elem_size);
+  const size_t pole_b = rg::round256(static_cast<size_t>(chunk_batch) * 2 * W * elem_size);
   return rg::kSlots * (in_b + out_b + pole_b);
 }
 

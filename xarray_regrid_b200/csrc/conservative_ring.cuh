@@ -34,6 +34,8 @@ struct RingDev {
   const int32_t* __restrict__ strip_c0;
   const int32_t* __restrict__ strip_nc;
   int n_runs, n_sched, max_live, pad_shift, n_strips, strip_cols_max, n_warps, lane_cols;
+  const void* __restrict__ pole;  // [batch, 2, W] synthetic pole rows (scheduled as rows n_src_rows, + 1) or NULL
+  int n_src_rows;
 };
 
 constexpr int kRingMaxSlots = 32;  // ring depth cap (a tap reaches at most 15 rows back: 4-bit tap_back)
@@ -233,10 +235,16 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
   int slot = 0;
   for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
     const int run = static_cast<int>(task % ring.n_runs);
-    const T* xb = x + (task / ring.n_runs) * xbs;
+    const long long b = task / ring.n_runs;
+    const T* xb = x + b * xbs;
+    const T* pb = static_cast<const T*>(ring.pole) + b * 2 * static_cast<long long>(row_bytes / sizeof(T));
     const int p1 = ring.run_sched[run + 1];
     for (int p = ring.run_sched[run]; p < p1; ++p) {
-      const long long off = static_cast<long long>(sched_row[p]) * xrs;  // shared memory: no global load per row
+      const int row = sched_row[p];  // shared memory: no global load per row
+      // rows >= n_src_rows are the synthetic pole rows of format_lat: full rows in the pole buffer
+      const T* src = row < ring.n_src_rows
+                         ? xb + static_cast<long long>(row) * xrs
+                         : pb + static_cast<long long>(row - ring.n_src_rows) * (row_bytes / sizeof(T));
       while (static_cast<int>(g - freed) >= ring_slots) {  // ring full: wait for the slowest warp
         // relaxed loads pipeline (acquire loads would serialise: 12-24 round trips per poll); one fence
         // below turns the poll into an acquire before the slot is overwritten
@@ -250,7 +258,7 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
         else fence_acq_rel_cta();
       }
       mbar_arrive_expect_tx(full0 + 8u * slot, row_bytes);
-      tma_load_row(ring0 + static_cast<uint32_t>(slot) * row_stride, xb + off, row_bytes, full0 + 8u * slot);
+      tma_load_row(ring0 + static_cast<uint32_t>(slot) * row_stride, src, row_bytes, full0 + 8u * slot);
       ++g;
       if (++slot == ring_slots) slot = 0;
     }

@@ -149,7 +149,7 @@ class BandOp:
 
     def _ring(self, batch: int, n_rows: int, n_cols: int, dtype: torch.dtype):
         """Row-ring schedule sized so that (slabs x runs) fills the SMs about twice over."""
-        if not self.use_ring or self.pole_rows:
+        if not self.use_ring:
             return None
         rows, cols = self._host_bands(n_rows, n_cols)
         sms = max(sm_count(), 1)
@@ -195,7 +195,7 @@ class BandOp:
         stream = _stream_ptr(x3.device)
         pole = None
         if self.pole_rows:
-            pole = torch.empty((B, 2), dtype=dtype, device=x3.device)
+            pole = torch.empty((B, 2, W), dtype=dtype, device=x3.device)  # full rows: rg_row_nanmean_*
             fn = lib.rg_row_nanmean_f64 if dtype == torch.float64 else lib.rg_row_nanmean_f32
             check(fn(x3.data_ptr(), pole.data_ptr(), B, H, W, x3.stride(0), x3.stride(1), stream),
                   "rg_row_nanmean")

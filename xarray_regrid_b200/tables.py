@@ -324,7 +324,7 @@ class RowRing:
         return int(self.run_first.size - 1)
 
 
-def column_strips(cols: Band, vec: int, max_warps: int = 24):
+def column_strips(cols: Band, vec: int, max_warps: int = 24, n_warps: int | None = None):
     """Cut the target columns into strips of <= 32 outputs for the consumer warps of the ring
     kernel and find, per strip, the (circular) range of source columns that covers all its taps.
 
@@ -358,6 +358,9 @@ def column_strips(cols: Band, vec: int, max_warps: int = 24):
             ncs.append(length)
         return l0.astype(np.int32), np.asarray(c0s, np.int32), np.asarray(ncs, np.int32)
 
+    if n_warps is not None:  # fixed decomposition: ceil(n_out / n_warps) targets per strip
+        l0, c0, nc = build(-(-n_out // n_warps))
+        return l0, c0, nc, min(n_warps, c0.size)
     best = None
     for n_warps in range(1, max_warps + 1):
         tps = min(32, -(-n_out // n_warps))
@@ -379,12 +382,13 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
 
     Outputs are visited in order and split into ``n_runs`` contiguous runs.  Inside a run a
     source row is loaded when first needed and stays in the ring until its last use, so rows
-    shared by neighbouring outputs are read once.  Returns None when the band references the
-    synthetic pole rows (the generic kernel handles those).
+    shared by neighbouring outputs are read once.  The synthetic pole rows of ``format_lat`` (indices
+    ``n_src`` and ``n_src + 1``) are scheduled like any other row: the kernels fetch them from the
+    ``[batch, 2, W]`` pole buffer.
     """
     n_out, k_max = rows.n_out, rows.k_max
     cnt = np.where(rows.cover > 0, rows.cnt, 0)
-    if n_out == 0 or (rows.idx >= rows.n_src).any():
+    if n_out == 0 or (rows.idx > rows.n_src + 1).any():
         return None
     if k_max > 8:
         return None
@@ -444,6 +448,15 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
             return None
         ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = column_strips(cols, vec)
         ring.lane_cols = lane_owned_columns(cols, ring.strip_l0, ring.n_warps)
+        if not ring.lane_cols and cols.n_out <= 31 * 12:
+            # the register-resident kernel wants one strip of <= 31 targets per warp: try that decomposition
+            n_warps = int(min(12, max(1, -(-cols.n_out // 8))))
+            while -(-cols.n_out // n_warps) > 31:
+                n_warps += 1
+            l0, c0, nc, _ = column_strips(cols, vec, n_warps=n_warps)
+            if l0.size - 1 <= n_warps and lane_owned_columns(cols, l0, n_warps):
+                ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = l0, c0, nc, n_warps
+                ring.lane_cols = lane_owned_columns(cols, l0, n_warps)
     return ring
 
 
