@@ -45,19 +45,44 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
                                         const T* s_x, T* s_z, const int (*s_off)[KR], const T (*s_rw)[KR],
                                         const int* s_state, const int (&ci)[G][4][KC], const T (&cw)[G][4][KC],
                                         int tid, T nan) {
-  // ---- (A) latitude pass
-  for (int q = 0; q < nk; ++q) {
-    const int m = kb_local + q;
-    int off[KR];
-    T w[KR];
+  // ---- (A) latitude pass.  Only W values per row: 16-byte vectors, all rows of the step in flight at once
+  // (the pass is latency bound, not throughput bound: few warps take part, the others go to the barrier)
+  constexpr int V = 16 / sizeof(T);
+  if (W % V == 0) {
+    const int nvec = W / V;
+    for (int j = tid; j < nvec; j += NT) {
 #pragma unroll
-    for (int t = 0; t < KR; ++t) { off[t] = s_off[m][t]; w[t] = s_rw[m][t]; }
-    T* z = s_z + (BUF * kUpRowsPerSync + q) * ZW;
-    for (int j = tid; j < W; j += NT) {
-      T acc = T(0);
+      for (int q = 0; q < kUpRowsPerSync; ++q) {
+        if (q < nk) {
+          const int m = kb_local + q;
+          Pack<T, V> acc;
 #pragma unroll
-      for (int t = 0; t < KR; ++t) acc = fma(w[t], s_x[off[t] + j], acc);
-      z[j] = acc;
+          for (int e = 0; e < V; ++e) acc.v[e] = T(0);
+#pragma unroll
+          for (int t = 0; t < KR; ++t) {
+            const T w = s_rw[m][t];
+            const Pack<T, V> xv = *reinterpret_cast<const Pack<T, V>*>(s_x + s_off[m][t] + j * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc.v[e] = fma(w, xv.v[e], acc.v[e]);
+          }
+          *reinterpret_cast<Pack<T, V>*>(s_z + (BUF * kUpRowsPerSync + q) * ZW + j * V) = acc;
+        }
+      }
+    }
+  } else {
+    for (int q = 0; q < nk; ++q) {
+      const int m = kb_local + q;
+      int off[KR];
+      T w[KR];
+#pragma unroll
+      for (int t = 0; t < KR; ++t) { off[t] = s_off[m][t]; w[t] = s_rw[m][t]; }
+      T* z = s_z + (BUF * kUpRowsPerSync + q) * ZW;
+      for (int j = tid; j < W; j += NT) {
+        T acc = T(0);
+#pragma unroll
+        for (int t = 0; t < KR; ++t) acc = fma(w[t], s_x[off[t] + j], acc);
+        z[j] = acc;
+      }
     }
   }
   __syncthreads();
