@@ -232,6 +232,36 @@ def test_cell_centred_quarter_degree_grid_all_kernels(eng, dtype):
     _check(y_host, want, RTOL[dtype])
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_pole_rows_with_weight_through_ring_and_host_pipeline(eng, dtype):
+    """Without the spherical correction the synthetic pole rows keep a non-zero weight: they are fetched by
+    the TMA producer from the [batch, 2, W] pole buffer (ring kernels), read as scalars by the generic kernel,
+    and produced per chunk inside the host-buffer pipeline."""
+    engine, _ = eng
+    rng = np.random.default_rng(8)
+    lat, lon = np.arange(-89.0, 90, 2), np.arange(1.0, 360, 2)
+    tlat, tlon = np.arange(-90.0, 91, 1), np.arange(0.0, 361, 1)
+    x = (0.5 + rng.random((5, lat.size, lon.size))).astype(dtype)
+    x[1, 0, :7] = np.nan
+    x[2, -1, :] = np.nan  # all-NaN edge row -> NaN pole row
+    plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"),
+                                   spherical_rows=False)
+    assert plan.pole_rows, "the pole rows must be referenced by the rows band"
+    xt = torch.from_numpy(x).cuda()
+    for skipna, thr in [(True, 0.5), (False, 1.0)]:
+        want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr,
+                                latitude_weighting=False, nan_through_zero_weights=False)
+        for kernel in ("ring", "generic"):
+            _pick(plan, kernel)
+            if kernel == "ring":
+                ring = plan._ring(5, lat.size, lon.size, xt.dtype)
+                assert ring is not None and (ring.host.sched_row >= lat.size).any()
+            _check(plan(xt, skipna=skipna, nan_threshold=thr), want, RTOL[dtype])
+        _pick(plan, "ring")
+        y_host = plan.apply_host(torch.from_numpy(x).pin_memory(), skipna=skipna, nan_threshold=thr, chunk_batch=2)
+        _check(y_host, want, RTOL[dtype])
+
+
 def test_descending_source_and_reversed_target(eng):
     """ERA5 stores latitude 90 -> -90; targets may be reversed (tests/test_regrid.py:289-300)."""
     engine, syn = eng
