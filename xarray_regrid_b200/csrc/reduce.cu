@@ -740,8 +740,8 @@ stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, l
         stage_row_async<T>(buf + r * stage_elems, src, cols, p0, s0, ncol, contiguous, lane);
       }
     };
-    // walk every staged row segment of this lane's cell: f(v) per element
-    auto sweep = [&](auto&& f) {
+    // walk every staged row segment of this lane's cell: row(trow, nc) once per segment, f(v) per element
+    auto sweep = [&](auto&& row, auto&& f) {
       if (n_chunks > 0) issue(0);
       cp_async_commit();
       for (int ch = 0; ch < n_chunks; ++ch) {
@@ -758,6 +758,7 @@ stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, l
             sh = static_cast<int>((reinterpret_cast<uintptr_t>(seg) & 15) / sizeof(T));
           }
           const T* trow = buf + r * stage_elems + sh + c0;
+          row(trow, nc);
           int c = 0;
           for (; c + 8 <= nc; c += 8) {
             T v[8];
@@ -775,8 +776,9 @@ stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, l
     double sum = 0.0, m2 = 0.0, mean = 0.0;
     int n = 0;
     T vmin = CUDART_INF, vmax = -CUDART_INF;
+    auto no_row = [](const T*, int) {};
     if constexpr (OPC == 1) {
-      sweep([&](T v) {
+      sweep(no_row, [&](T v) {
         n += (v == v) ? 1 : 0;
         vmin = v < vmin ? v : vmin;  // comparisons with NaN are false: NaN never replaces a value
         vmax = v > vmax ? v : vmax;
@@ -788,9 +790,15 @@ stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, l
       // second pass would come from DRAM again).
       bool have = false;
       double shift = 0.0;
-      sweep([&](T v) {
+      auto find_shift = [&](const T* trow, int ncols) {  // once per row segment until a sample is found
+        if (have) return;
+        for (int c = 0; c < ncols; ++c) {
+          const T v = trow[c];
+          if (v == v) { shift = static_cast<double>(v); have = true; break; }
+        }
+      };
+      sweep(find_shift, [&](T v) {
         const bool ok = v == v;
-        if (ok && !have) { shift = static_cast<double>(v); have = true; }
         const double d = ok ? static_cast<double>(v) - shift : 0.0;
         n += ok ? 1 : 0;
         sum += d;
@@ -802,14 +810,14 @@ stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, l
         mean = shift + md;
       }
     } else {
-      sweep([&](T v) {
+      sweep(no_row, [&](T v) {
         const bool ok = v == v;
         n += ok ? 1 : 0;
         sum += ok ? static_cast<double>(v) : 0.0;
       });
       if (n > 0) mean = sum / n;
       if constexpr (OPC == 2) {
-        sweep([&](T v) {
+        sweep(no_row, [&](T v) {
           const double d = (v == v) ? static_cast<double>(v) - mean : 0.0;
           m2 += d * d;
         });
