@@ -345,6 +345,7 @@ template <typename K>
 __device__ __forceinline__ K warp_select(const K (&keys)[kSelCap], unsigned valid, int k) {
   constexpr int BITS = sizeof(K) * 8;
   K prefix = 0;
+  int cand = __reduce_add_sync(0xffffffffu, __popc(valid));  // keys still matching the prefix
   for (int b = BITS - 1; b >= 0; --b) {
     // keys that agree with `prefix` on the bits above b and have bit b clear
     const K want = prefix >> b;  // bit b of `want` is 0
@@ -354,7 +355,25 @@ __device__ __forceinline__ K warp_select(const K (&keys)[kSelCap], unsigned vali
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (k >= cnt) {
       k -= cnt;
+      cand -= cnt;
       prefix |= static_cast<K>(1) << b;
+    } else {
+      cand = cnt;
+    }
+    if (cand == 1 && b > 0) {
+      // one key left (distinct values: after ~log2(n) bits): it is the answer, fetch it instead of
+      // resolving the remaining bits one by one
+      K found = 0;
+#pragma unroll
+      for (int i = 0; i < kSelCap; ++i)
+        if (((valid >> i) & 1u) && (keys[i] >> b) == (prefix >> b)) found = keys[i];
+      if constexpr (sizeof(K) == 8) {
+        const unsigned lo = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(found));
+        const unsigned hi = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(found >> 32));
+        return (static_cast<K>(hi) << 32) | lo;
+      } else {
+        return static_cast<K>(__reduce_or_sync(0xffffffffu, static_cast<unsigned>(found)));
+      }
     }
   }
   return prefix;
