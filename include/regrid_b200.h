@@ -328,16 +328,18 @@ int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t b
  * skipna != 0: NaNs are ignored (an all-NaN bin gives NaN, 0 for sum).  Cells that are not covered get
  * `fill`.  Replaces flox.xarray.xarray_reduce(data, *coords, func=method, expected_groups=bounds,
  * skipna=..., fill_value=...) of methods/flox_reduce.py:89-96.  sort_cap (median only) >= next power
- * of two of the largest bin population; strip_elems as in rg_mode (0 = unknown: tile kernel only).
+ * of two of the largest bin population; strip_elems as in rg_mode (0 = unknown: tile kernel only);
+ * max_bin_rows / max_bin_cols as in rg_mode (0 = unknown): cells of <= 32 x 32 take the one-warp-per-cell
+ * register median kernel.
  */
 int rg_stat_f64(const double* x, double* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
                 int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
                 int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
-                int32_t strip_elems, double fill, void* stream);
+                int32_t strip_elems, int32_t max_bin_rows, int32_t max_bin_cols, double fill, void* stream);
 int rg_stat_f32(const float* x, float* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
                 int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
                 int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
-                int32_t strip_elems, double fill, void* stream);
+                int32_t strip_elems, int32_t max_bin_rows, int32_t max_bin_cols, double fill, void* stream);
 
 #ifdef __cplusplus
 }

@@ -100,8 +100,8 @@ def _load():
         "rg_poison_if_f32": (C.c_int, [p, i64, p, p]),
         "rg_mode": (C.c_int, [p, p, i32, i32, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, p, p, p,
                               i32, i32, i32, f64, p]),
-        "rg_stat_f64": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, i32, f64, p]),
-        "rg_stat_f32": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, i32, f64, p]),
+        "rg_stat_f64": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, i32, i32, i32, f64, p]),
+        "rg_stat_f32": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, i32, i32, i32, f64, p]),
         "rg_conservative_host_workspace": (sz, [i64, i32, i32, i32, i32, i32]),
         "rg_conservative_host_f64": (C.c_int, [p, p, i64, i64, band, band, i32, f64, i32, ring, p, sz]),
         "rg_conservative_host_f32": (C.c_int, [p, p, i64, i64, band, band, i32, f32, i32, ring, p, sz]),

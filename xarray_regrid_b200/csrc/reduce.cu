@@ -341,8 +341,8 @@ __device__ __forceinline__ double from_key(unsigned long long k) {
 }
 
 // k-th smallest (0-based) of the valid keys spread over the warp's registers (bit i of `valid` marks slot i).
-template <typename K>
-__device__ __forceinline__ K warp_select(const K (&keys)[kSelCap], unsigned valid, int k) {
+template <typename K, int CAP = kSelCap>
+__device__ __forceinline__ K warp_select(const K (&keys)[CAP], unsigned valid, int k) {
   constexpr int BITS = sizeof(K) * 8;
   K prefix = 0;
   int cand = __reduce_add_sync(0xffffffffu, __popc(valid));  // keys still matching the prefix
@@ -351,7 +351,7 @@ __device__ __forceinline__ K warp_select(const K (&keys)[kSelCap], unsigned vali
     const K want = prefix >> b;  // bit b of `want` is 0
     int cnt = 0;
 #pragma unroll
-    for (int i = 0; i < kSelCap; ++i) cnt += (((valid >> i) & 1u) && (keys[i] >> b) == want) ? 1 : 0;
+    for (int i = 0; i < CAP; ++i) cnt += (((valid >> i) & 1u) && (keys[i] >> b) == want) ? 1 : 0;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (k >= cnt) {
       k -= cnt;
@@ -365,7 +365,7 @@ __device__ __forceinline__ K warp_select(const K (&keys)[kSelCap], unsigned vali
       // resolving the remaining bits one by one
       K found = 0;
 #pragma unroll
-      for (int i = 0; i < kSelCap; ++i)
+      for (int i = 0; i < CAP; ++i)
         if (((valid >> i) & 1u) && (keys[i] >> b) == (prefix >> b)) found = keys[i];
       if constexpr (sizeof(K) == 8) {
         const unsigned lo = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(found));
@@ -496,7 +496,7 @@ stat_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long lo
             valid |= (ok ? 1u : 0u) << q;
           }
           const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
-          const K key_lo = warp_select<K>(keys, valid, k_lo);
+          const K key_lo = warp_select<K, kSelCap>(keys, valid, k_lo);
           K key_hi = key_lo;
           if (k_hi != k_lo) {
             // the next order statistic: the same value if it occurs often enough, else the smallest larger one
@@ -859,6 +859,77 @@ stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, l
   }
 }
 
+// ------------------------------------------------------------ median, one warp per cell, no staging
+// Cells of up to CAP rows x 32 columns: lane c loads column c of the cell straight from global memory (one key
+// per row, all rows in flight, 4 or 8 bytes per lane: a row segment is one coalesced request and neighbouring
+// cells share cache lines through L1 / L2), converts to order-preserving keys and runs the bitwise select
+// in registers.  No shared memory, no CTA barrier: warps are independent and many are resident.
+template <typename T, int CAP>
+__global__ void __launch_bounds__(256, 3)
+median_direct_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
+                     long long ybs, Bins rows, Bins cols, int skipna, T fill) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int Ho = rows.n_out, Wo = cols.n_out;
+  const long long cells = batch * Ho * Wo;
+  const T nan = quiet_nan<T>();
+  using K = decltype(to_key(T(0)));
+  for (long long cell = warp_id; cell < cells; cell += n_warps) {
+    const int l = static_cast<int>(cell % Wo);
+    const int k = static_cast<int>((cell / Wo) % Ho);
+    const long long b = cell / (static_cast<long long>(Wo) * Ho);
+    T out = fill;
+    if (rows.cover[k] != 0 && cols.cover[l] != 0) {
+      const int nr = rows.count[k], nc = cols.count[l];  // host contract: nr <= CAP, nc <= 32
+      const T* col = x + b * xbs + src_index(cols, cols.start[l] + (lane < nc ? lane : 0));
+      int ri = src_index(rows, rows.start[k]);
+      K keys[CAP];
+      unsigned valid = 0;
+#pragma unroll
+      for (int q = 0; q < CAP; ++q) {
+        T v = nan;
+        if (q < nr && lane < nc) v = __ldg(col + static_cast<long long>(ri) * xrs);
+        ri += rows.src_step;  // next source row, modulo n_src
+        ri = ri >= rows.n_src ? ri - rows.n_src : (ri < 0 ? ri + rows.n_src : ri);
+        const bool ok = (v == v);
+        keys[q] = ok ? to_key(v) : K(0);
+        valid |= (ok ? 1u : 0u) << q;
+      }
+      const int n = __reduce_add_sync(0xffffffffu, __popc(valid));
+      if ((!skipna && n < nr * nc) || n == 0) {
+        out = nan;
+      } else {
+        const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
+        const K key_lo = warp_select<K, CAP>(keys, valid, k_lo);
+        K key_hi = key_lo;
+        if (k_hi != k_lo) {
+          // the next order statistic: the same value if it occurs often enough, else the smallest larger one
+          int le = 0;
+          K next = ~K(0);
+#pragma unroll
+          for (int i = 0; i < CAP; ++i) {
+            if ((valid >> i) & 1u) {
+              le += keys[i] <= key_lo ? 1 : 0;
+              if (keys[i] > key_lo && keys[i] < next) next = keys[i];
+            }
+          }
+          le = __reduce_add_sync(0xffffffffu, le);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const K other = __shfl_xor_sync(0xffffffffu, next, o);
+            next = other < next ? other : next;
+          }
+          key_hi = (le > k_hi) ? key_lo : next;
+        }
+        const double lo = static_cast<double>(from_key(key_lo)), hi = static_cast<double>(from_key(key_hi));
+        out = static_cast<T>((lo + hi) / 2);
+      }
+    }
+    if (lane == 0) y[b * ybs + static_cast<long long>(rows.out_index[k]) * Wo + cols.out_index[l]] = out;
+  }
+}
+
 // --------------------------------------------------------------------------- launchers
 struct ChunkPlan {
   int cols_per_chunk, n_chunks, tile_elems;
@@ -960,8 +1031,8 @@ int mode_launch(const void* x, void* y, int64_t batch, int64_t xbs, int64_t xrs,
 template <typename T>
 int stat_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
                 const rg_bins_t* rows_c, const rg_bins_t* cols_c, int32_t cols_per_chunk, int32_t tile_elems,
-                int32_t op, int32_t skipna, int32_t sort_cap, int32_t strip_elems, double fill,
-                cudaStream_t stream) {
+                int32_t op, int32_t skipna, int32_t sort_cap, int32_t strip_elems, int32_t max_bin_rows,
+                int32_t max_bin_cols, double fill, cudaStream_t stream) {
   if (!x || !y) return RG_ERR_NULL;
   if (op < OP_SUM || op > OP_MEDIAN || cols_per_chunk <= 0 || tile_elems <= 0) return RG_ERR_SHAPE;
   Bins rows, cols;
@@ -973,6 +1044,25 @@ int stat_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64
   DeviceInfo dev;
   rc = device_info(&dev);
   if (rc != RG_OK) return rc;
+  // ---- median of cells up to 32 x 32: one warp per cell, keys in registers, no staging
+  if (op == OP_MEDIAN && max_bin_rows > 0 && max_bin_rows <= 32 && max_bin_cols > 0 && max_bin_cols <= 32) {
+    using MK = void (*)(const T*, T*, long long, long long, long long, long long, Bins, Bins, int, T);
+    MK mk = max_bin_rows <= 8    ? median_direct_kernel<T, 8>
+            : max_bin_rows <= 16 ? median_direct_kernel<T, 16>
+            : max_bin_rows <= 25 ? median_direct_kernel<T, 25>
+                                 : median_direct_kernel<T, 32>;
+    int per_sm_m = 0;
+    RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_m, mk, 256, 0));
+    if (per_sm_m >= 1) {
+      const long long cells = static_cast<long long>(batch) * rows.n_out * cols.n_out;
+      long long grid_m = static_cast<long long>(dev.sm_count) * per_sm_m * 4;
+      const long long need = (cells + 7) / 8;
+      if (grid_m > need) grid_m = need;
+      mk<<<static_cast<unsigned>(grid_m), 256, 0, stream>>>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna,
+                                                            static_cast<T>(fill));
+      return static_cast<int>(cudaGetLastError());
+    }
+  }
   // ---- throughput path (everything but the median): one cell per lane
   if (op != OP_MEDIAN && strip_elems > 0) {
     const int stage_elems = (strip_elems + 48 + 15) / 16 * 16;
@@ -1062,19 +1152,19 @@ int rg_mode(const void* x, void* y, int32_t in_type, int32_t out_type, int64_t b
 int rg_stat_f64(const double* x, double* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
                 int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
                 int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
-                int32_t strip_elems, double fill, void* stream) {
+                int32_t strip_elems, int32_t max_bin_rows, int32_t max_bin_cols, double fill, void* stream) {
   return rg::stat_launch<double>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows, cols,
-                                 cols_per_chunk, tile_elems, op, skipna, sort_cap, strip_elems, fill,
-                                 static_cast<cudaStream_t>(stream));
+                                 cols_per_chunk, tile_elems, op, skipna, sort_cap, strip_elems, max_bin_rows,
+                                 max_bin_cols, fill, static_cast<cudaStream_t>(stream));
 }
 
 int rg_stat_f32(const float* x, float* y, int64_t batch, int64_t x_batch_stride, int64_t x_row_stride,
                 int64_t y_batch_stride, const rg_bins_t* rows, const rg_bins_t* cols,
                 int32_t cols_per_chunk, int32_t tile_elems, int32_t op, int32_t skipna, int32_t sort_cap,
-                int32_t strip_elems, double fill, void* stream) {
+                int32_t strip_elems, int32_t max_bin_rows, int32_t max_bin_cols, double fill, void* stream) {
   return rg::stat_launch<float>(x, y, batch, x_batch_stride, x_row_stride, y_batch_stride, rows, cols,
-                                cols_per_chunk, tile_elems, op, skipna, sort_cap, strip_elems, fill,
-                                static_cast<cudaStream_t>(stream));
+                                cols_per_chunk, tile_elems, op, skipna, sort_cap, strip_elems, max_bin_rows,
+                                max_bin_cols, fill, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

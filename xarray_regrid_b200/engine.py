@@ -630,14 +630,15 @@ class ReducePlan:
         if method == "median":
             _, _, _, max_rows, max_cols = self._geometry(rows, cols, x3.element_size(), 0)
             sort_cap = 1 << max(max_rows * max_cols - 1, 0).bit_length()
-        cpc, tile, strip, _, _ = self._geometry(rows, cols, x3.element_size(), 8 * sort_cap * x3.element_size())
+        cpc, tile, strip, max_rows, max_cols = self._geometry(rows, cols, x3.element_size(),
+                                                             8 * sort_cap * x3.element_size())
         fn = lib.rg_stat_f64 if x3.dtype == torch.float64 else lib.rg_stat_f32
         fill = float("nan") if fill_value is None else float(fill_value)
         if B:
             check(
                 fn(x3.data_ptr(), y.data_ptr(), B, x3.stride(0) if B > 1 else x3.shape[1] * x3.stride(1),
                    x3.stride(1), Ho * Wo, rows.ref, cols.ref, cpc, tile, _STAT_CODE[method],
-                   int(bool(skipna)), sort_cap, strip, fill, _stream_ptr(x3.device)),
+                   int(bool(skipna)), sort_cap, strip, max_rows, max_cols, fill, _stream_ptr(x3.device)),
                 "rg_stat",
             )
         return y.view(tuple(lead) + (Ho, Wo))
