@@ -324,7 +324,7 @@ class RowRing:
         return int(self.run_first.size - 1)
 
 
-def column_strips(cols: Band, vec: int, max_warps: int = 24, n_warps: int | None = None):
+def column_strips(cols: Band, vec: int, max_warps: int = 12, n_warps: int | None = None):
     """Cut the target columns into strips of <= 32 outputs for the consumer warps of the ring
     kernel and find, per strip, the (circular) range of source columns that covers all its taps.
 
@@ -370,8 +370,9 @@ def column_strips(cols: Band, vec: int, max_warps: int = 24, n_warps: int | None
         per_warp = np.zeros(n_warps)
         for i, c in enumerate(per_strip):
             per_warp[i % n_warps] += c
-        # total issue work (with a fixed per-warp cost) and the critical path of the busiest warp
-        cost = per_strip.sum() + 75 * min(n_warps, c0.size) + 2.0 * per_warp.max()
+        # the kernel is bound by the serial per-target-row path of its busiest warp (every warp visits every
+        # target row), so the critical path dominates; total issue work only breaks ties
+        cost = 8.0 * per_warp.max() + 0.25 * (per_strip.sum() + 75 * min(n_warps, c0.size))
         if best is None or cost < best[0] - 1e-9:
             best = (cost, l0, c0, nc, min(n_warps, c0.size))
     return best[1:]
@@ -447,6 +448,10 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
         if cols.n_src % vec != 0:
             return None
         ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = column_strips(cols, vec)
+        if ring.strip_c0.size > ring.n_warps:
+            # more than 12 x 32 target columns: a warp would own several strips and reload its column taps for
+            # every (target row, strip); the generic kernel is faster there (measured: 0.25 -> 0.5 deg 3x)
+            return None
         ring.lane_cols = lane_owned_columns(cols, ring.strip_l0, ring.n_warps)
         if not ring.lane_cols and cols.n_out <= 31 * 12:
             # the register-resident kernel wants one strip of <= 31 targets per warp: try that decomposition
