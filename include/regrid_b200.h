@@ -76,6 +76,10 @@ typedef struct rg_band {
                           every aligned group of that many consecutive outputs takes its taps from at most
                           16 consecutive source indices; 0 = no such grouping / unknown.  Lets the library
                           pick the shared-memory upsampling kernel (it stages 16 source rows per group). */
+  int32_t group_span;  /* columns axis of an interpolation band whose taps are contiguous (idx[t] = idx[0] + t):
+                          max over aligned groups of 4 consecutive covered outputs of (largest - smallest tap
+                          index + 1); 0 = unknown / taps not contiguous.  <= 6 lets the 4-tap upsampling kernel
+                          load one window per group instead of 4 taps per output. */
 } rg_band_t;
 
 /*

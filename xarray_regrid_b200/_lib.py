@@ -30,6 +30,7 @@ class rg_band_t(C.Structure):  # noqa: N801 - mirrors the C name
         ("n_src", C.c_int32),
         ("span", C.c_int32),
         ("window_rows", C.c_int32),
+        ("group_span", C.c_int32),
     ]
 
 

@@ -29,7 +29,7 @@ struct Band {
   const T* __restrict__ w;
   const int32_t* __restrict__ cnt;
   const uint8_t* __restrict__ cover;
-  int n_out, k_max, n_src, span, window_rows;
+  int n_out, k_max, n_src, span, window_rows, group_span;
 };
 
 template <typename T>
@@ -45,6 +45,7 @@ inline int make_band(const rg_band_t* b, Band<T>* out) {
   out->n_src = b->n_src;
   out->span = b->span;
   out->window_rows = b->window_rows;
+  out->group_span = b->group_span;
   return RG_OK;
 }
 

@@ -40,34 +40,39 @@ __device__ __forceinline__ void st_stream4(double* p, const Vec4<double>& a) {
 
 // Rows [kb, kb + nk) of a band: latitude pass into the z buffers of parity BUF, one barrier, longitude
 // pass + stores.  BUF and the row slot are compile-time so that every z read is LDS [reg + immediate].
-template <typename T, int KR, int KC, int G, int ZW, int NT, int BUF>
+// WIN: the four outputs of a group take their taps from one window of KC + 2 consecutive z columns (host contract,
+// rg_band_t.group_span): the window is loaded once per group (KC + 2 loads instead of 4 * KC) and every output is a
+// (KC + 2)-term dot product with its taps shifted into place (zeros elsewhere).  Used for the 4-tap cubic evaluation,
+// where a NaN anywhere blanks the whole result anyway, so a zero weight times a NaN neighbour cannot matter.
+template <typename T, int KR, int KC, int G, int ZW, int NT, int BUF, int WIN>
 __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, int nk, int W, int Wo,
                                         const T* s_x, T* s_z, const int (*s_off)[KR], const T (*s_rw)[KR],
-                                        const int* s_state, const int (&ci)[G][4][KC], const T (&cw)[G][4][KC],
-                                        int tid, T nan) {
+                                        const int* s_state, const int (&ci)[G][4][KC],
+                                        const T (&cw)[G][4][KC + 2 * WIN], int tid, T nan) {
   // ---- (A) latitude pass.  Only W values per row: 16-byte vectors, all rows of the step in flight at once
   // (the pass is latency bound, not throughput bound: few warps take part, the others go to the barrier)
   constexpr int V = 16 / sizeof(T);
   if (W % V == 0) {
     const int nvec = W / V;
-    for (int j = tid; j < nvec; j += NT) {
+    // (row, vector) pairs are dealt round-robin over ALL threads: the pass is short and sits in front of a
+    // barrier, so its critical path (not its instruction count) is what the other warps wait for
+    for (int p = tid; p < nvec * nk; p += NT) {
+      int q = 0;
 #pragma unroll
-      for (int q = 0; q < kUpRowsPerSync; ++q) {
-        if (q < nk) {
-          const int m = kb_local + q;
-          Pack<T, V> acc;
+      for (int i = 1; i < kUpRowsPerSync; ++i) q += (p >= i * nvec) ? 1 : 0;
+      const int j = p - q * nvec;
+      const int m = kb_local + q;
+      Pack<T, V> acc;
 #pragma unroll
-          for (int e = 0; e < V; ++e) acc.v[e] = T(0);
+      for (int e = 0; e < V; ++e) acc.v[e] = T(0);
 #pragma unroll
-          for (int t = 0; t < KR; ++t) {
-            const T w = s_rw[m][t];
-            const Pack<T, V> xv = *reinterpret_cast<const Pack<T, V>*>(s_x + s_off[m][t] + j * V);
+      for (int t = 0; t < KR; ++t) {
+        const T w = s_rw[m][t];
+        const Pack<T, V> xv = *reinterpret_cast<const Pack<T, V>*>(s_x + s_off[m][t] + j * V);
 #pragma unroll
-            for (int e = 0; e < V; ++e) acc.v[e] = fma(w, xv.v[e], acc.v[e]);
-          }
-          *reinterpret_cast<Pack<T, V>*>(s_z + (BUF * kUpRowsPerSync + q) * ZW + j * V) = acc;
-        }
+        for (int e = 0; e < V; ++e) acc.v[e] = fma(w, xv.v[e], acc.v[e]);
       }
+      *reinterpret_cast<Pack<T, V>*>(s_z + (BUF * kUpRowsPerSync + q) * ZW + j * V) = acc;
     }
   } else {
     for (int q = 0; q < nk; ++q) {
@@ -98,13 +103,27 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
         const int l = (tid + g * NT) * 4;
         if (l < Wo) {
           Vec4<T> out;
+          if constexpr (WIN) {
+            T zw[KC + 2];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            T acc = T(0);
+            for (int c = 0; c < KC + 2; ++c)
+              zw[c] = *reinterpret_cast<const T*>(z + ci[g][0][0] + c * static_cast<int>(sizeof(T)));
 #pragma unroll
-            for (int c = 0; c < KC; ++c)
-              acc = fma(cw[g][e][c], *reinterpret_cast<const T*>(z + ci[g][e][c]), acc);
-            out.v[e] = acc;
+            for (int e = 0; e < 4; ++e) {
+              T acc = T(0);
+#pragma unroll
+              for (int c = 0; c < KC + 2; ++c) acc = fma(cw[g][e][c], zw[c], acc);
+              out.v[e] = acc;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              T acc = T(0);
+#pragma unroll
+              for (int c = 0; c < KC; ++c)
+                acc = fma(cw[g][e][c], *reinterpret_cast<const T*>(z + ci[g][e][c]), acc);
+              out.v[e] = acc;
+            }
           }
           if (state != 2) {  // uniform: uncovered latitude -> NaN row; covered without taps -> 0 (or NaN column)
 #pragma unroll
@@ -123,7 +142,7 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
   }
 }
 
-template <typename T, int KR, int KC, int G, int ZW, int NT>
+template <typename T, int KR, int KC, int G, int ZW, int NT, int WIN = 0>
 __global__ void __launch_bounds__(NT)
 upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
                 long long ybs, Band<T> rows, Band<T> cols, int band_rows) {
@@ -139,25 +158,62 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
 
   const int tid = threadIdx.x;
   const T nan = quiet_nan<T>();
+  if constexpr (WIN) {  // z columns W, W + 1 of every z row: read by windows at the right edge, weight 0
+    for (int i = tid; i < 2 * kUpRowsPerSync * 2; i += NT) s_z[(i >> 1) * ZW + W + (i & 1)] = T(0);
+  }
 
   // ---- longitude taps of the columns this thread owns (registers, loaded once): byte offsets into a
   //      z row and weights; a column outside the source range gets a NaN weight (NaN * z = NaN)
   int ci[G][4][KC];
-  T cw[G][4][KC];
+  T cw[G][4][KC + 2 * WIN];
+  if constexpr (WIN) {
+    // window form: ci[g][0][0] = byte offset of the group's window, cw[g][e][c] = weight of window column c
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
+    for (int g = 0; g < G; ++g) {
+      int first[4], n[4];
+      bool covered[4];
+      int base = W;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int l = (tid + g * NT) * 4 + e;
-      const bool in = l < Wo;
-      const int n = in ? cols.cnt[l] : 0;
-#pragma unroll
-      for (int c = 0; c < KC; ++c) {
-        const bool live = c < n && c < cols.k_max;
-        ci[g][e][c] = (live ? cols.idx[c * Wo + l] : (n > 0 ? cols.idx[l] : 0)) * static_cast<int>(sizeof(T));
-        cw[g][e][c] = live ? cols.w[c * Wo + l] : T(0);
+      for (int e = 0; e < 4; ++e) {
+        const int l = (tid + g * NT) * 4 + e;
+        const bool in = l < Wo;
+        n[e] = in ? min(cols.cnt[l], KC) : 0;
+        covered[e] = in && cols.cover[l] != 0;
+        first[e] = n[e] > 0 ? cols.idx[l] : W;
+        if (covered[e]) base = min(base, first[e]);
       }
-      if (in && !cols.cover[l]) cw[g][e][0] = nan;
+      if (base >= W) base = 0;  // (the window may reach 2 columns past W: those z columns are kept at zero)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int l = (tid + g * NT) * 4 + e;
+        const int d = first[e] - base;  // host contract: 0 <= d, d + taps <= KC + 2 for covered outputs
+#pragma unroll
+        for (int c = 0; c < KC + 2; ++c) {
+          const int t = c - d;
+          cw[g][e][c] = (covered[e] && t >= 0 && t < n[e]) ? cols.w[t * Wo + l] : T(0);
+        }
+        if (l < Wo && !covered[e]) cw[g][e][0] = nan;
+#pragma unroll
+        for (int c = 0; c < KC; ++c) ci[g][e][c] = 0;
+      }
+      ci[g][0][0] = base * static_cast<int>(sizeof(T));
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int l = (tid + g * NT) * 4 + e;
+        const bool in = l < Wo;
+        const int n = in ? cols.cnt[l] : 0;
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+          const bool live = c < n && c < cols.k_max;
+          ci[g][e][c] = (live ? cols.idx[c * Wo + l] : (n > 0 ? cols.idx[l] : 0)) * static_cast<int>(sizeof(T));
+          cw[g][e][c] = live ? cols.w[c * Wo + l] : T(0);
+        }
+        if (in && !cols.cover[l]) cw[g][e][0] = nan;
+      }
     }
   }
 
@@ -215,11 +271,11 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
 
     T* y_band = y + b * ybs + static_cast<long long>(k0) * Wo;
     for (int kl = 0; kl < k1 - k0; kl += 2 * kUpRowsPerSync) {
-      up_rows<T, KR, KC, G, ZW, NT, 0>(y_band, kl, min(kUpRowsPerSync, k1 - k0 - kl), W, Wo, s_x, s_z, s_off, s_rw,
+      up_rows<T, KR, KC, G, ZW, NT, 0, WIN>(y_band, kl, min(kUpRowsPerSync, k1 - k0 - kl), W, Wo, s_x, s_z, s_off, s_rw,
                                    s_state, ci, cw, tid, nan);
       const int kl2 = kl + kUpRowsPerSync;
       if (kl2 < k1 - k0)
-        up_rows<T, KR, KC, G, ZW, NT, 1>(y_band, kl2, min(kUpRowsPerSync, k1 - k0 - kl2), W, Wo, s_x, s_z, s_off,
+        up_rows<T, KR, KC, G, ZW, NT, 1, WIN>(y_band, kl2, min(kUpRowsPerSync, k1 - k0 - kl2), W, Wo, s_x, s_z, s_off,
                                      s_rw, s_state, ci, cw, tid, nan);
     }
     __syncthreads();
@@ -252,8 +308,16 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   const int kc = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : 4;
   using Kernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, Band<T>, int);
   Kernel kern = nullptr;
+  // 4 taps: window form of the longitude pass when every group of 4 outputs fits a 6-column window
+  const bool win = kc == 4 && kr == 4 && cols.group_span > 0 && cols.group_span <= 6 && W + 2 <= zw;
+  if (win) {
+    if (nt == 512 && groups <= 2) {
+      if (groups == 1) kern = zw == 512 ? upsample_kernel<T, 4, 4, 1, 512, 512, 1> : upsample_kernel<T, 4, 4, 1, 1024, 512, 1>;
+      else kern = zw == 512 ? upsample_kernel<T, 4, 4, 2, 512, 512, 1> : upsample_kernel<T, 4, 4, 2, 1024, 512, 1>;
+    }
+  }
 #define RG_UP(KR_, KC_, G_)                                                                              \
-  if (kr == KR_ && kc == KC_ && groups == G_) {                                                          \
+  if (!kern && kr == KR_ && kc == KC_ && groups == G_) {                                                          \
     if (nt == 256)                                                                                       \
       kern = zw == 512 ? upsample_kernel<T, KR_, KC_, G_, 512, 256> : upsample_kernel<T, KR_, KC_, G_, 1024, 256>; \
     else if (G_ <= 2)                                                                                    \

@@ -57,6 +57,7 @@ class DeviceBand:
         self.c = rg_band_t(
             self.idx.data_ptr(), self.w.data_ptr(), self.cnt.data_ptr(), self.cover.data_ptr(),
             band.n_out, band.k_max, band.n_src, span, tables.band_window_rows(band),
+            tables.band_group_span(band),
         )
 
     @property

@@ -514,6 +514,26 @@ def band_window_rows(band: "Band", cap: int = 16, max_rows: int = 32, step: int 
     return 0
 
 
+def band_group_span(band: "Band", group: int = 4) -> int:
+    """``rg_band_t.group_span``: for a band whose taps are contiguous (``idx[t] == idx[0] + t``), the largest
+    number of source indices spanned by the taps of an aligned group of ``group`` consecutive covered outputs;
+    0 when the taps are not contiguous (or nothing is covered)."""
+    live = (np.arange(band.k_max)[:, None] < band.cnt[None, :]) & (band.cover[None, :] > 0)
+    if band.n_out == 0 or not live.any() or (band.idx[live] >= band.n_src).any():
+        return 0
+    idx = band.idx.astype(np.int64)
+    if ((idx - idx[:1] - np.arange(band.k_max)[:, None]) != 0)[live].any():
+        return 0
+    has = live.any(axis=0)
+    hi = np.where(live, idx, -1).max(axis=0)
+    lo = np.where(live, idx, np.iinfo(np.int32).max).min(axis=0)
+    starts = np.arange(0, band.n_out, group)
+    g_hi = np.maximum.reduceat(np.where(has, hi, -1), starts)
+    g_lo = np.minimum.reduceat(np.where(has, lo, np.iinfo(np.int32).max), starts)
+    spans = np.where(g_hi >= 0, g_hi - g_lo + 1, 0)
+    return int(spans.max())
+
+
 # ------------------------------------------------------------ interpolation bands (xr.interp)
 def _restore_not_needed(n_out):
     return None
