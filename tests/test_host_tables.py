@@ -295,3 +295,23 @@ def test_band_window_rows_is_exact():
     else:
         cand = 0
     assert rows == cand
+
+
+def test_band_group_span():
+    """rg_band_t.group_span: contiguous-tap bands report the widest 4-output window, others 0."""
+    ax = tables.plain_axis(np.arange(0.0, 360.0, 1.0))
+    fine = np.round(np.arange(0, 358.95, 0.1), 10)
+    _, ev = tables.cubic_bands(ax, fine)
+    assert tables.band_group_span(ev) == 5          # 4 taps, 4 outputs 0.1 apart cross at most one node
+    assert tables.band_group_span(tables.linear_band(ax, fine)) == 3
+    _, ev2 = tables.cubic_bands(ax, np.arange(1.0, 350.0, 0.5))
+    assert tables.band_group_span(ev2) == 5         # ratio 2: 4 outputs 0.5 apart still cross one node only
+    cons = tables.conservative_band(tables.format_lon_axis(np.arange(0, 360, 0.25), np.arange(0, 360, 1.0)),
+                                    np.arange(0, 360, 1.0))
+    assert tables.band_group_span(cons) == 0        # wrap-around taps are not index-contiguous
+    # brute force on an irregular axis
+    rng = np.random.default_rng(4)
+    irr = tables.plain_axis(np.sort(rng.uniform(0, 100, 80)))
+    _, ev3 = tables.cubic_bands(irr, np.linspace(irr.values[0], irr.values[-1], 333))
+    want = max(ev3.idx[:, a:a + 4].max() - ev3.idx[:, a:a + 4].min() + 1 for a in range(0, ev3.n_out, 4))
+    assert tables.band_group_span(ev3) == want
