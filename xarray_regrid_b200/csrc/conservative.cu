@@ -21,9 +21,10 @@
 namespace rg {
 
 constexpr int kConsThreads = 256;
-constexpr int kRowChunk = 8;  // independent row loads in flight per thread
 
-template <typename T, bool SKIPNA, int VEC>
+// RC = independent row loads in flight per thread (the row taps are walked in chunks of RC; bands with <= 4 row
+// taps use RC = 4: the unrolled, predicated chunk body is half as long).
+template <typename T, bool SKIPNA, int VEC, int RC>
 __global__ void __launch_bounds__(kConsThreads)
 conservative_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch,
                     long long xbs, long long xrs, long long ybs, Band<T> rows, Band<T> cols,
@@ -64,10 +65,10 @@ conservative_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch,
 #pragma unroll
       for (int e = 0; e < VEC; ++e) { acc[e] = T(0); vac[e] = T(0); }
       const bool full = (j + VEC <= W);
-      for (int r0 = 0; r0 < cnt; r0 += kRowChunk) {
-        Pack<T, VEC> val[kRowChunk];
+      for (int r0 = 0; r0 < cnt; r0 += RC) {
+        Pack<T, VEC> val[RC];
 #pragma unroll
-        for (int i = 0; i < kRowChunk; ++i) {
+        for (int i = 0; i < RC; ++i) {
           if (r0 + i < cnt) {
             const long long off = s_off[r0 + i];
             if (off >= 0) {
@@ -86,7 +87,7 @@ conservative_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch,
           }
         }
 #pragma unroll
-        for (int i = 0; i < kRowChunk; ++i) {
+        for (int i = 0; i < RC; ++i) {
           if (r0 + i < cnt) {
             const T w = s_w[r0 + i];
 #pragma unroll
@@ -301,10 +302,13 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   using Kernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>,
                           Band<T>, T, const T*, int);
   Kernel kern;
+  const bool few = rows.k_max <= 4;
   if (aligned) {
-    kern = skipna ? conservative_kernel<T, true, kMaxVec> : conservative_kernel<T, false, kMaxVec>;
+    kern = skipna ? (few ? conservative_kernel<T, true, kMaxVec, 4> : conservative_kernel<T, true, kMaxVec, 8>)
+                  : (few ? conservative_kernel<T, false, kMaxVec, 4> : conservative_kernel<T, false, kMaxVec, 8>);
   } else {
-    kern = skipna ? conservative_kernel<T, true, 1> : conservative_kernel<T, false, 1>;
+    kern = skipna ? (few ? conservative_kernel<T, true, 1, 4> : conservative_kernel<T, true, 1, 8>)
+                  : (few ? conservative_kernel<T, false, 1, 4> : conservative_kernel<T, false, 1, 8>);
   }
   if (smem > 48 * 1024) {
     RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
