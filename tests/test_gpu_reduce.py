@@ -219,3 +219,26 @@ def test_empty_batch_large_bins_and_median_paths(engine):
     xi = rng.integers(0, 100, size=(2, lat.size, lon.size)).astype(np.int16)
     y = plan.mode(torch.from_numpy(xi).cuda(), labels).cpu().numpy()
     np.testing.assert_array_equal(y, orr.mode(xi, [lat, lon], [tlat, tlon], [-2, -1], labels))
+
+
+def test_latitude_band_sharding_matches_full_slab(engine):
+    """sharding.latitude_band: a single slab split by target rows over 3 'ranks' (run one after the other on this
+    GPU) reproduces the full most_common / mean result exactly, with no exchange between the bands."""
+    from xarray_regrid_b200 import sharding
+
+    rng = np.random.default_rng(29)
+    lat, lon = np.round(np.arange(-19.95, 20, 0.1), 6), np.round(np.arange(0.05, 30, 0.1), 6)
+    tlat, tlon = np.arange(-18.0, 19.0, 1.0), np.arange(1.0, 29.0, 1.0)
+    labels = torch.from_numpy(rng.integers(0, 12, (lat.size, lon.size)).astype(np.uint8)).cuda()
+    field = torch.from_numpy(rng.standard_normal((lat.size, lon.size)).astype(np.float32)).cuda()
+    full = _plan(engine, lat, lon, tlat, tlon, ("lat", "lon"))
+    want_mode = full.mode(labels, np.arange(12), fill_value=255).cpu().numpy()
+    want_mean = full.stat(field, "mean", skipna=True).cpu().numpy()
+    got_mode, got_mean = np.full_like(want_mode, 254), np.full_like(want_mean, np.nan)
+    for rank in range(3):
+        t_idx, s_rows = sharding.latitude_band(lat, tlat, 3, rank)
+        band = _plan(engine, lat[s_rows], lon, tlat[t_idx], tlon, ("lat", "lon"))
+        got_mode[t_idx] = band.mode(labels[s_rows], np.arange(12), fill_value=255).cpu().numpy()
+        got_mean[t_idx] = band.stat(field[s_rows], "mean", skipna=True).cpu().numpy()
+    np.testing.assert_array_equal(got_mode, want_mode)
+    np.testing.assert_array_equal(got_mean, want_mean)

@@ -68,3 +68,41 @@ def test_two_rank_gloo_sharding():
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         np.testing.assert_array_equal(out["y"], out["want"])
         assert out["tmax"] == float(world)
+
+
+def test_latitude_band_split_of_a_single_slab_is_exact():
+    """Single-slab configs (C5) shard over ranks by target-row bands with no exchange: the per-band results of the
+    oracle, put back in place, equal the full result bit for bit (most_common) / exactly (mean, max)."""
+    import numpy as np
+
+    from oracle import reduce as orr
+    from xarray_regrid_b200 import sharding
+
+    rng = np.random.default_rng(5)
+    lat = np.round(np.arange(-29.95, 30, 0.1), 6)[::-1].copy()  # descending source, like ERA5
+    lon = np.round(np.arange(0.05, 40, 0.1), 6)
+    tlat, tlon = np.arange(-28.0, 29.0, 1.0), np.arange(1.0, 39.0, 1.0)
+    labels = rng.integers(0, 9, (lat.size, lon.size)).astype(np.uint8)
+    field = rng.standard_normal((lat.size, lon.size))
+    full_mode = orr.mode(labels, [lat, lon], [tlat, tlon], [-2, -1], np.arange(9), fill_value=255)
+    full_mean = orr.stat(field, [lat, lon], [tlat, tlon], [-2, -1], "mean", skipna=True)
+    full_max = orr.stat(field, [lat, lon], [tlat, tlon], [-2, -1], "max")
+    for world in (1, 2, 3, 8):
+        got_mode = np.full_like(full_mode, 254)
+        got_mean = np.full_like(full_mean, np.nan)
+        got_max = np.full_like(full_max, np.nan)
+        seen = np.zeros(tlat.size, int)
+        for rank in range(world):
+            t_idx, s_rows = sharding.latitude_band(lat, tlat, world, rank)
+            if t_idx.size == 0:
+                continue
+            seen[t_idx] += 1
+            sub_t = tlat[t_idx]
+            got_mode[t_idx] = orr.mode(labels[s_rows], [lat[s_rows], lon], [sub_t, tlon], [-2, -1], np.arange(9),
+                                       fill_value=255)
+            got_mean[t_idx] = orr.stat(field[s_rows], [lat[s_rows], lon], [sub_t, tlon], [-2, -1], "mean", skipna=True)
+            got_max[t_idx] = orr.stat(field[s_rows], [lat[s_rows], lon], [sub_t, tlon], [-2, -1], "max")
+        assert (seen == 1).all(), "every target row is owned by exactly one rank"
+        np.testing.assert_array_equal(got_mode, full_mode)
+        np.testing.assert_array_equal(got_mean, full_mean)
+        np.testing.assert_array_equal(got_max, full_max)

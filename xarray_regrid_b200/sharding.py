@@ -58,3 +58,37 @@ def bind_to_gpu_numa_node(device_index: int) -> list[int] | None:
         return cores
     except Exception:  # noqa: BLE001 - best effort: no NVML, no permission, non-Linux
         return None
+
+
+def latitude_band(src, tgt, world_size: int, rank: int):
+    """Split a SINGLE-slab group-by regrid (most_common / least_common / stat) over ranks by target rows.
+
+    Returns ``(tgt_index, src_slice)``: the positions (in ``tgt``'s own order) of the target rows owned by
+    ``rank`` and the slice of source rows that rank needs.  Bins are closed-left intervals of width ``res``
+    around the targets (``_shared.py:12-18``), so a band of targets needs exactly the source rows inside
+    ``[first target - res, last target + res]`` -- the trimming rule of ``reduce_data_to_new_domain``
+    (``_shared.py:92-108``) applied to the band: no halo exchange, no collective, and the per-band result equals
+    the corresponding rows of the full result as long as the source is at least as fine as the target (the
+    coarsening case these methods exist for), which is checked.  Every rank gets at least two targets (the bin
+    width is inferred from the target spacing); surplus ranks get an empty band.
+    """
+    import numpy as np
+
+    src, tgt = np.asarray(src, dtype=np.float64), np.asarray(tgt, dtype=np.float64)
+    if tgt.size < 2:
+        raise ValueError("need at least two target points")
+    order = np.argsort(tgt, kind="stable")
+    tgt_sorted = tgt[order]
+    res = float(np.median(np.diff(tgt_sorted)))
+    if src.size > 1 and float(np.max(np.abs(np.diff(src)))) > res * (1 + 1e-9):
+        raise ValueError("latitude_band needs a source at least as fine as the target")
+    usable = max(1, min(world_size, tgt.size // 2))  # ranks that get >= 2 targets
+    if not 0 <= rank < world_size:
+        raise ValueError(f"bad rank {rank} / world size {world_size}")
+    if rank >= usable:
+        return np.empty(0, np.int64), slice(0, 0)
+    a, b = shard_bounds(tgt.size, usable, rank)
+    lo, hi = tgt_sorted[a] - res, tgt_sorted[b - 1] + res
+    inside = np.nonzero((src >= lo) & (src <= hi))[0]
+    src_slice = slice(int(inside[0]), int(inside[-1]) + 1) if inside.size else slice(0, 0)
+    return order[a:b], src_slice
