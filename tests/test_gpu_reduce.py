@@ -242,3 +242,29 @@ def test_latitude_band_sharding_matches_full_slab(engine):
         got_mean[t_idx] = band.stat(field[s_rows], "mean", skipna=True).cpu().numpy()
     np.testing.assert_array_equal(got_mode, want_mode)
     np.testing.assert_array_equal(got_mean, want_mean)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int8, np.int16, np.int32, np.int64])
+@pytest.mark.parametrize("labels", ["dense12", "dense32", "dense40", "dense100", "sparse"])
+def test_mode_every_kernel_and_label_dtype(engine, dtype, labels):
+    """All three mode kernels (bit-sliced registers <= 32 dense labels, lane counters <= 64, tile + match.any
+    otherwise / sparse label sets) for every integer dtype, with values that are NOT in the label list mixed in
+    (the reference ignores them) and both most_common and least_common."""
+    rng = np.random.default_rng(41)
+    lat, lon = np.round(np.arange(-9.95, 10, 0.1), 6), np.round(np.arange(0.05, 16, 0.1), 6)
+    tlat, tlon = np.arange(-9.0, 10.0, 1.0), np.arange(1.0, 15.0, 1.0)
+    if labels == "sparse":
+        values = np.array([3, 7, 19, 40, 77, 100, 120], dtype=dtype)
+    else:
+        values = np.arange(int(labels[5:]), dtype=dtype)
+    pool = np.concatenate([values, np.array([values.max() + 1, 126], dtype=dtype)])  # two foreign values
+    if np.issubdtype(dtype, np.signedinteger):
+        pool = np.concatenate([pool, np.array([-1], dtype=dtype)])
+    x = pool[rng.integers(0, pool.size, (2, lat.size, lon.size))]
+    plan = _plan(engine, lat, lon, tlat, tlon, ("lat", "lon"))
+    for anti in (False, True):
+        y = plan.mode(torch.from_numpy(x).cuda(), values, fill_value=int(values.max()), anti_mode=anti)
+        want = orr.regrid_latlon(x, lat, lon, tlat, tlon, "least_common" if anti else "most_common", values=values,
+                                 fill_value=int(values.max()))
+        assert y.cpu().numpy().dtype == want.dtype == dtype
+        np.testing.assert_array_equal(y.cpu().numpy(), want)
