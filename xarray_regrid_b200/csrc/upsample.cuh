@@ -149,12 +149,12 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int H = rows.n_src, W = cols.n_src, Ho = rows.n_out, Wo = cols.n_out;
   T* s_z = reinterpret_cast<T*>(smem_raw);             // [2][kUpRowsPerSync][ZW] latitude-interpolated rows
-  T* s_x = s_z + 2 * kUpRowsPerSync * ZW;              // [kUpRowCap][W] staged source rows
-  // per-band row metadata, filled by warp 0 once per task
-  __shared__ int s_off[kUpBandRows][KR];  // element offset of tap t's row inside s_x
-  __shared__ T s_rw[kUpBandRows][KR];
-  __shared__ int s_state[kUpBandRows];    // 0: row not covered (NaN), 1: covered without taps (0), 2: normal
-  __shared__ int s_win0;
+  T* s_x = s_z + 2 * kUpRowsPerSync * ZW;              // [2][kUpRowCap][W] staged source rows (this / next band)
+  // per-band row metadata, filled by warp 0 (double-buffered like the rows)
+  __shared__ int s_off[2][kUpBandRows][KR];  // element offset of tap t's row inside the window
+  __shared__ T s_rw[2][kUpBandRows][KR];
+  __shared__ int s_state[2][kUpBandRows];    // 0: row not covered (NaN), 1: covered without taps (0), 2: normal
+  __shared__ int s_win0[2];
 
   const int tid = threadIdx.x;
   const T nan = quiet_nan<T>();
@@ -217,68 +217,127 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
     }
   }
 
+  // ---- band loop.  The row taps and the staged source rows of the NEXT band are prefetched while the current
+  // band is produced (tables: warp 0 issues the loads at the band start and parks them in registers until its
+  // first step is done; rows: LDGSTS into the other window buffer), so that no global-load latency sits between
+  // two bands.  Bands with fewer than two steps fall back to the synchronous prologue.
   const int n_bands = (Ho + band_rows - 1) / band_rows;
   const long long tasks = batch * n_bands;
+  const int x_elems = kUpRowCap * W;  // one window buffer
+
+  // row taps of lane `tid`'s row of a band -> registers (warp 0 only); rmin reduced over the warp
+  auto meta_load = [&](long long task, int (&ri)[KR], T (&rw)[KR], int& n, bool& cov) {
+    const int band = static_cast<int>(task % n_bands);
+    const int k0 = band * band_rows, k1 = min(k0 + band_rows, Ho);
+    const int k = k0 + tid;
+    n = 0;
+    cov = false;
+#pragma unroll
+    for (int t = 0; t < KR; ++t) { ri[t] = 0; rw[t] = T(0); }
+    if (k < k1) {
+      cov = rows.cover[k] != 0;
+      n = rows.cnt[k];
+#pragma unroll
+      for (int t = 0; t < KR; ++t) {
+        if (t < rows.k_max) {
+          ri[t] = rows.idx[t * Ho + k];
+          rw[t] = rows.w[t * Ho + k];
+        }
+      }
+    }
+  };
+  auto meta_store = [&](long long task, int buf, const int (&ri_in)[KR], const T (&rw_in)[KR], int n_in, bool cov) {
+    const int band = static_cast<int>(task % n_bands);
+    const int k0 = band * band_rows, k1 = min(k0 + band_rows, Ho);
+    const int k = k0 + tid;
+    const int n = cov ? n_in : 0;
+    int ri[KR];
+    T rw[KR];
+    int rmin = H;
+#pragma unroll
+    for (int t = 0; t < KR; ++t) {
+      const bool live = t < n && t < rows.k_max;
+      ri[t] = live ? ri_in[t] : (n > 0 ? ri_in[0] : 0);
+      rw[t] = live ? rw_in[t] : T(0);
+      if (k < k1 && n > 0) rmin = min(rmin, ri[t]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+    if (rmin >= H) rmin = 0;
+    if (k < k1) {
+#pragma unroll
+      for (int t = 0; t < KR; ++t) {
+        // host contract (window_rows): < kUpRowCap rows; clamped so a broken table cannot leave the window
+        s_off[buf][tid][t] = (n > 0 ? min(ri[t] - rmin, kUpRowCap - 1) : 0) * W;
+        s_rw[buf][tid][t] = rw[t];
+      }
+      s_state[buf][tid] = !cov ? 0 : (n == 0 ? 1 : 2);
+    }
+    if (tid == 0) s_win0[buf] = rmin;
+  };
+  // the window's source rows -> s_x[buf], asynchronously (one element per request: any alignment)
+  auto rows_issue = [&](long long task, int buf) {
+    const T* xb = x + (task / n_bands) * xbs;
+    const int w0 = s_win0[buf];
+    const int wn = min(kUpRowCap, H - w0);
+    T* dst = s_x + buf * x_elems;
+    for (int r = 0; r < wn; ++r) {
+      const T* src = xb + static_cast<long long>(w0 + r) * xrs;
+      for (int j = tid; j < W; j += NT) {
+        const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * W + j));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src + j), "n"(sizeof(T)) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int cur = 0;
+  bool ready = false;  // is the current band's prologue already in buffer `cur`?
   for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
     const int band = static_cast<int>(task % n_bands);
     const long long b = task / n_bands;
-    const T* xb = x + b * xbs;
     const int k0 = band * band_rows, k1 = min(k0 + band_rows, Ho);
+    const long long next = task + gridDim.x;
+    const bool prefetch = next < tasks && (k1 - k0) > kUpRowsPerSync;  // needs two steps in this band
 
-    // ---- warp 0: row taps of the band -> shared memory; first source row of the band
-    if (tid < 32) {
-      const int k = k0 + tid;
-      int ri[KR];
-      T rw[KR];
-      int n = 0, rmin = H;
-      bool cov = false;
-      if (k < k1) {
-        cov = rows.cover[k] != 0;
-        n = cov ? rows.cnt[k] : 0;
-#pragma unroll
-        for (int t = 0; t < KR; ++t) {
-          const bool live = t < n && t < rows.k_max;
-          ri[t] = live ? rows.idx[t * Ho + k] : (n > 0 ? rows.idx[k] : 0);
-          rw[t] = live ? rows.w[t * Ho + k] : T(0);
-          if (n > 0) rmin = min(rmin, ri[t]);
-        }
+    if (!ready) {  // synchronous prologue (first band of the CTA, or after a one-step band)
+      if (tid < 32) {
+        int ri[KR];
+        T rw[KR];
+        int n;
+        bool cov;
+        meta_load(task, ri, rw, n, cov);
+        meta_store(task, cur, ri, rw, n, cov);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
-      if (rmin >= H) rmin = 0;
-      if (k < k1) {
-#pragma unroll
-        for (int t = 0; t < KR; ++t) {
-          // host contract (window_rows): < kUpRowCap rows; clamped so a broken table cannot leave the window
-          s_off[tid][t] = (n > 0 ? min(ri[t] - rmin, kUpRowCap - 1) : 0) * W;
-          s_rw[tid][t] = rw[t];
-        }
-        s_state[tid] = !cov ? 0 : (n == 0 ? 1 : 2);
-      }
-      if (tid == 0) s_win0 = rmin;
+      __syncthreads();
+      rows_issue(task, cur);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    // ---- stage the band's source rows (coalesced)
-    {
-      const int w0 = s_win0;
-      const int wn = min(kUpRowCap, H - w0);
-      for (int r = 0; r < wn; ++r) {
-        const T* src = xb + static_cast<long long>(w0 + r) * xrs;
-        for (int j = tid; j < W; j += NT) s_x[r * W + j] = __ldg(src + j);
-      }
-    }
-    __syncthreads();
+
+    // next band's row taps: loads issued now (warp 0), consumed after the first step
+    int nri[KR];
+    T nrw[KR];
+    int nn = 0;
+    bool ncov = false;
+    if (prefetch && tid < 32) meta_load(next, nri, nrw, nn, ncov);
 
     T* y_band = y + b * ybs + static_cast<long long>(k0) * Wo;
+    const T* sx = s_x + cur * x_elems;
     for (int kl = 0; kl < k1 - k0; kl += 2 * kUpRowsPerSync) {
-      up_rows<T, KR, KC, G, ZW, NT, 0, WIN>(y_band, kl, min(kUpRowsPerSync, k1 - k0 - kl), W, Wo, s_x, s_z, s_off, s_rw,
-                                   s_state, ci, cw, tid, nan);
+      up_rows<T, KR, KC, G, ZW, NT, 0, WIN>(y_band, kl, min(kUpRowsPerSync, k1 - k0 - kl), W, Wo, sx, s_z, s_off[cur],
+                                            s_rw[cur], s_state[cur], ci, cw, tid, nan);
+      if (kl == 0 && prefetch && tid < 32) meta_store(next, cur ^ 1, nri, nrw, nn, ncov);
       const int kl2 = kl + kUpRowsPerSync;
       if (kl2 < k1 - k0)
-        up_rows<T, KR, KC, G, ZW, NT, 1, WIN>(y_band, kl2, min(kUpRowsPerSync, k1 - k0 - kl2), W, Wo, s_x, s_z, s_off,
-                                     s_rw, s_state, ci, cw, tid, nan);
+        up_rows<T, KR, KC, G, ZW, NT, 1, WIN>(y_band, kl2, min(kUpRowsPerSync, k1 - k0 - kl2), W, Wo, sx, s_z,
+                                              s_off[cur], s_rw[cur], s_state[cur], ci, cw, tid, nan);
+      // the barrier inside the second step ordered warp 0's table writes: everybody can start the row copies
+      if (kl == 0 && prefetch) rows_issue(next, cur ^ 1);
     }
-    __syncthreads();
+    __syncthreads();  // all reads of this band's window and z rows are done
+    ready = prefetch;
+    if (prefetch) cur ^= 1;
   }
 }
 
@@ -301,7 +360,7 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     return RG_ERR_UNSUPPORTED;
   if (W > 1024) return RG_ERR_UNSUPPORTED;
   const int zw = W <= 512 ? 512 : 1024;
-  const size_t smem = (static_cast<size_t>(kUpRowCap) * W + 2 * kUpRowsPerSync * zw) * sizeof(T);
+  const size_t smem = (static_cast<size_t>(2 * kUpRowCap) * W + 2 * kUpRowsPerSync * zw) * sizeof(T);
   if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_UNSUPPORTED;
   const int groups = ((Wo + 3) / 4 + nt - 1) / nt;  // 1..4
   const int kr = rows.k_max <= 1 ? 1 : rows.k_max <= 2 ? 2 : 4;
