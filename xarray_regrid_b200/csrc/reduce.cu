@@ -379,6 +379,48 @@ __device__ __forceinline__ K warp_select(const K (&keys)[CAP], unsigned valid, i
   return prefix;
 }
 
+// Same selection for keys held WITHOUT a validity mask: empty slots carry the all-ones sentinel (no finite, infinite
+// or NaN input maps to it), `n` valid keys in the warp, 0 <= k < n.  The count of a round is taken against the
+// absolute threshold `prefix | 1 << b` (one compare and one add per key); the candidates with the bit clear are that
+// count minus the number of keys below the prefix, which earlier rounds already established.
+template <typename K, int CAP>
+__device__ __forceinline__ K warp_select_dense(const K (&keys)[CAP], int n, int k) {
+  constexpr int BITS = sizeof(K) * 8;
+  K prefix = 0;
+  int below = 0;  // keys < prefix
+  int cand = n;   // keys in [prefix, prefix + 2^(b+1))
+  for (int b = BITS - 1; b >= 0; --b) {
+    const K split = prefix | (static_cast<K>(1) << b);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < CAP; ++i) c += keys[i] < split ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (k >= c) {
+      cand -= c - below;
+      below = c;
+      prefix = split;
+    } else {
+      cand = c - below;
+    }
+    if (cand == 1 && b > 0) {
+      // one key left in [prefix, prefix + 2^b): it is the answer (the top range also holds the sentinels)
+      const K width = static_cast<K>(1) << b;
+      K found = 0;
+#pragma unroll
+      for (int i = 0; i < CAP; ++i)
+        if (static_cast<K>(keys[i] - prefix) < width && keys[i] != ~static_cast<K>(0)) found = keys[i];
+      if constexpr (sizeof(K) == 8) {
+        const unsigned lo = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(found));
+        const unsigned hi = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(found >> 32));
+        return (static_cast<K>(hi) << 32) | lo;
+      } else {
+        return static_cast<K>(__reduce_or_sync(0xffffffffu, static_cast<unsigned>(found)));
+      }
+    }
+  }
+  return prefix;
+}
+
 // ------------------------------------------------------------------------------ stats
 template <typename T>
 __device__ __forceinline__ void bitonic_sort_warp(T* a, int n_pow2, int lane) {
@@ -884,8 +926,8 @@ median_direct_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch
       const int nr = rows.count[k], nc = cols.count[l];  // host contract: nr <= CAP, nc <= 32
       const T* col = x + b * xbs + src_index(cols, cols.start[l] + (lane < nc ? lane : 0));
       int ri = src_index(rows, rows.start[k]);
-      K keys[CAP];
-      unsigned valid = 0;
+      K keys[CAP];  // empty slots (outside the cell, NaN) hold the all-ones sentinel
+      int n_own = 0;
 #pragma unroll
       for (int q = 0; q < CAP; ++q) {
         T v = nan;
@@ -893,26 +935,25 @@ median_direct_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch
         ri += rows.src_step;  // next source row, modulo n_src
         ri = ri >= rows.n_src ? ri - rows.n_src : (ri < 0 ? ri + rows.n_src : ri);
         const bool ok = (v == v);
-        keys[q] = ok ? to_key(v) : K(0);
-        valid |= (ok ? 1u : 0u) << q;
+        keys[q] = ok ? to_key(v) : ~K(0);
+        n_own += ok ? 1 : 0;
       }
-      const int n = __reduce_add_sync(0xffffffffu, __popc(valid));
+      const int n = __reduce_add_sync(0xffffffffu, n_own);
       if ((!skipna && n < nr * nc) || n == 0) {
         out = nan;
       } else {
         const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
-        const K key_lo = warp_select<K, CAP>(keys, valid, k_lo);
+        const K key_lo = warp_select_dense<K, CAP>(keys, n, k_lo);
         K key_hi = key_lo;
         if (k_hi != k_lo) {
           // the next order statistic: the same value if it occurs often enough, else the smallest larger one
+          // (the sentinel is the identity of the minimum and never <= a valid key)
           int le = 0;
           K next = ~K(0);
 #pragma unroll
           for (int i = 0; i < CAP; ++i) {
-            if ((valid >> i) & 1u) {
-              le += keys[i] <= key_lo ? 1 : 0;
-              if (keys[i] > key_lo && keys[i] < next) next = keys[i];
-            }
+            le += keys[i] <= key_lo ? 1 : 0;
+            if (keys[i] > key_lo && keys[i] < next) next = keys[i];
           }
           le = __reduce_add_sync(0xffffffffu, le);
 #pragma unroll
