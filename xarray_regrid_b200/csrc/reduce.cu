@@ -379,6 +379,14 @@ __device__ __forceinline__ K warp_select(const K (&keys)[CAP], unsigned valid, i
   return prefix;
 }
 
+// c += (key < split): one compare and one predicated add, in place (the C++ form costs a register move per key)
+__device__ __forceinline__ void count_below(int& c, unsigned int key, unsigned int split) {
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c) : "r"(key), "r"(split));
+}
+__device__ __forceinline__ void count_below(int& c, unsigned long long key, unsigned long long split) {
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.u64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c) : "l"(key), "l"(split));
+}
+
 // Same selection for keys held WITHOUT a validity mask: empty slots carry the all-ones sentinel (no finite, infinite
 // or NaN input maps to it), `n` valid keys in the warp, 0 <= k < n.  The count of a round is taken against the
 // absolute threshold `prefix | 1 << b` (one compare and one add per key); the candidates with the bit clear are that
@@ -391,10 +399,10 @@ __device__ __forceinline__ K warp_select_dense(const K (&keys)[CAP], int n, int 
   int cand = n;   // keys in [prefix, prefix + 2^(b+1))
   for (int b = BITS - 1; b >= 0; --b) {
     const K split = prefix | (static_cast<K>(1) << b);
-    int c = 0;
+    int c = 0, c1 = 0;  // two chains
 #pragma unroll
-    for (int i = 0; i < CAP; ++i) c += keys[i] < split ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
+    for (int i = 0; i < CAP; ++i) count_below((i & 1) ? c1 : c, keys[i], split);
+    c = __reduce_add_sync(0xffffffffu, c + c1);
     if (k >= c) {
       cand -= c - below;
       below = c;
@@ -925,18 +933,36 @@ median_direct_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch
     if (rows.cover[k] != 0 && cols.cover[l] != 0) {
       const int nr = rows.count[k], nc = cols.count[l];  // host contract: nr <= CAP, nc <= 32
       const T* col = x + b * xbs + src_index(cols, cols.start[l] + (lane < nc ? lane : 0));
-      int ri = src_index(rows, rows.start[k]);
+      const int r_first = src_index(rows, rows.start[k]);
+      const int r_last = r_first + rows.src_step * (nr - 1);
+      const int nr_own = lane < nc ? nr : 0;  // lanes outside the cell load nothing
       K keys[CAP];  // empty slots (outside the cell, NaN) hold the all-ones sentinel
       int n_own = 0;
+      if (r_last >= 0 && r_last < rows.n_src) {
+        // the usual case, the cell's source rows do not wrap around the axis: one pointer increment per row
+        const T* ptr = col + static_cast<long long>(r_first) * xrs;
+        const long long stride = xrs * rows.src_step;
 #pragma unroll
-      for (int q = 0; q < CAP; ++q) {
-        T v = nan;
-        if (q < nr && lane < nc) v = __ldg(col + static_cast<long long>(ri) * xrs);
-        ri += rows.src_step;  // next source row, modulo n_src
-        ri = ri >= rows.n_src ? ri - rows.n_src : (ri < 0 ? ri + rows.n_src : ri);
-        const bool ok = (v == v);
-        keys[q] = ok ? to_key(v) : ~K(0);
-        n_own += ok ? 1 : 0;
+        for (int q = 0; q < CAP; ++q) {
+          T v = nan;
+          if (q < nr_own) v = __ldg(ptr);
+          ptr += stride;
+          const bool ok = (v == v);
+          keys[q] = ok ? to_key(v) : ~K(0);
+          n_own += ok ? 1 : 0;
+        }
+      } else {
+        int ri = r_first;
+#pragma unroll
+        for (int q = 0; q < CAP; ++q) {
+          T v = nan;
+          if (q < nr_own) v = __ldg(col + static_cast<long long>(ri) * xrs);
+          ri += rows.src_step;  // next source row, modulo n_src
+          ri = ri >= rows.n_src ? ri - rows.n_src : (ri < 0 ? ri + rows.n_src : ri);
+          const bool ok = (v == v);
+          keys[q] = ok ? to_key(v) : ~K(0);
+          n_own += ok ? 1 : 0;
+        }
       }
       const int n = __reduce_add_sync(0xffffffffu, n_own);
       if ((!skipna && n < nr * nc) || n == 0) {
@@ -947,14 +973,18 @@ median_direct_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch
         K key_hi = key_lo;
         if (k_hi != k_lo) {
           // the next order statistic: the same value if it occurs often enough, else the smallest larger one
-          // (the sentinel is the identity of the minimum and never <= a valid key)
+          // (the sentinel is never <= a valid key).  Smallest larger key: keys <= key_lo wrap around to
+          // differences larger than any genuine one, so one subtraction and one minimum per key find it.
           int le = 0;
-          K next = ~K(0);
+          const K above = key_lo + 1;  // key_lo is a valid key, hence not the all-ones sentinel
+          K gap = ~K(0);
 #pragma unroll
           for (int i = 0; i < CAP; ++i) {
-            le += keys[i] <= key_lo ? 1 : 0;
-            if (keys[i] > key_lo && keys[i] < next) next = keys[i];
+            count_below(le, keys[i], above);
+            const K d = keys[i] - above;
+            gap = d < gap ? d : gap;
           }
+          K next = above + gap;
           le = __reduce_add_sync(0xffffffffu, le);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
