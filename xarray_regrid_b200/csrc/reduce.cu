@@ -410,19 +410,41 @@ __device__ __forceinline__ K warp_select_dense(const K (&keys)[CAP], int n, int 
     } else {
       cand = c - below;
     }
-    if (cand == 1 && b > 0) {
-      // one key left in [prefix, prefix + 2^b): it is the answer (the top range also holds the sentinels)
-      const K width = static_cast<K>(1) << b;
-      K found = 0;
+    // Early exits: the answer is the SMALLEST key of the remaining range [prefix, prefix + 2^b) (rank k equals the
+    // number of keys below the prefix) or its LARGEST key; both are found with one subtraction and one unsigned
+    // minimum per key, no range test.  Smallest: keys below the prefix wrap around to differences >= 2^BITS - prefix,
+    // larger than any genuine difference.  Largest: keys above the range wrap around to >= prefix + 2^b, keys below it
+    // give >= 2^b, keys inside < 2^b; the top range also holds the sentinels and keeps bisecting instead.
+    // This covers "one candidate left" and ends two to three rounds earlier on average.
+    const int k_rel = k - below;
+    if (b > 0 && (k_rel == 0 || k_rel == cand - 1)) {
+      const K last = prefix | ((static_cast<K>(1) << b) - 1);
+      const bool smallest = k_rel == 0;
+      if (smallest || last != ~static_cast<K>(0)) {
+        K gap = ~static_cast<K>(0);
+        if (smallest) {
 #pragma unroll
-      for (int i = 0; i < CAP; ++i)
-        if (static_cast<K>(keys[i] - prefix) < width && keys[i] != ~static_cast<K>(0)) found = keys[i];
-      if constexpr (sizeof(K) == 8) {
-        const unsigned lo = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(found));
-        const unsigned hi = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(found >> 32));
-        return (static_cast<K>(hi) << 32) | lo;
-      } else {
-        return static_cast<K>(__reduce_or_sync(0xffffffffu, static_cast<unsigned>(found)));
+          for (int i = 0; i < CAP; ++i) {
+            const K d = keys[i] - prefix;
+            gap = d < gap ? d : gap;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CAP; ++i) {
+            const K d = last - keys[i];
+            gap = d < gap ? d : gap;
+          }
+        }
+        if constexpr (sizeof(K) == 8) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const K other = __shfl_xor_sync(0xffffffffu, gap, o);
+            gap = other < gap ? other : gap;
+          }
+        } else {
+          gap = static_cast<K>(__reduce_min_sync(0xffffffffu, static_cast<unsigned>(gap)));
+        }
+        return smallest ? prefix + gap : last - gap;
       }
     }
   }
