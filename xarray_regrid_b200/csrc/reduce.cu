@@ -379,6 +379,15 @@ __device__ __forceinline__ K warp_select(const K (&keys)[CAP], unsigned valid, i
   return prefix;
 }
 
+// gap = min(gap, a - b) with unsigned wrap-around: one fused add-and-minimum (VIADDMNMX) for 32-bit keys
+__device__ __forceinline__ void min_diff(unsigned int& gap, unsigned int a, unsigned int b) {
+  gap = __viaddmin_u32(a, 0u - b, gap);
+}
+__device__ __forceinline__ void min_diff(unsigned long long& gap, unsigned long long a, unsigned long long b) {
+  const unsigned long long d = a - b;
+  gap = d < gap ? d : gap;
+}
+
 // c += (key < split): one compare and one predicated add, in place (the C++ form costs a register move per key)
 __device__ __forceinline__ void count_below(int& c, unsigned int key, unsigned int split) {
   asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c) : "r"(key), "r"(split));
@@ -425,14 +434,12 @@ __device__ __forceinline__ K warp_select_dense(const K (&keys)[CAP], int n, int 
         if (smallest) {
 #pragma unroll
           for (int i = 0; i < CAP; ++i) {
-            const K d = keys[i] - prefix;
-            gap = d < gap ? d : gap;
+            min_diff(gap, keys[i], prefix);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < CAP; ++i) {
-            const K d = last - keys[i];
-            gap = d < gap ? d : gap;
+            min_diff(gap, last, keys[i]);
           }
         }
         if constexpr (sizeof(K) == 8) {
@@ -936,8 +943,10 @@ stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, l
 // per row, all rows in flight, 4 or 8 bytes per lane: a row segment is one coalesced request and neighbouring
 // cells share cache lines through L1 / L2), converts to order-preserving keys and runs the bitwise select
 // in registers.  No shared memory, no CTA barrier: warps are independent and many are resident.
+// CTAs of 4 warps, 7 per SM: 72 registers per thread allow 28 resident warps (3 x 8 warps would stop at 24)
+constexpr int kMedThreads = 128;
 template <typename T, int CAP>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(kMedThreads, sizeof(T) == 8 ? 5 : 7)  // 64-bit keys: 96 registers, 20 warps
 median_direct_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
                      long long ybs, Bins rows, Bins cols, int skipna, T fill) {
   const int lane = threadIdx.x & 31;
@@ -1003,8 +1012,7 @@ median_direct_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch
 #pragma unroll
           for (int i = 0; i < CAP; ++i) {
             count_below(le, keys[i], above);
-            const K d = keys[i] - above;
-            gap = d < gap ? d : gap;
+            min_diff(gap, keys[i], above);
           }
           K next = above + gap;
           le = __reduce_add_sync(0xffffffffu, le);
@@ -1145,13 +1153,13 @@ int stat_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64
             : max_bin_rows <= 25 ? median_direct_kernel<T, 25>
                                  : median_direct_kernel<T, 32>;
     int per_sm_m = 0;
-    RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_m, mk, 256, 0));
+    RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_m, mk, kMedThreads, 0));
     if (per_sm_m >= 1) {
       const long long cells = static_cast<long long>(batch) * rows.n_out * cols.n_out;
       long long grid_m = static_cast<long long>(dev.sm_count) * per_sm_m * 4;
-      const long long need = (cells + 7) / 8;
+      const long long need = (cells + kMedThreads / 32 - 1) / (kMedThreads / 32);
       if (grid_m > need) grid_m = need;
-      mk<<<static_cast<unsigned>(grid_m), 256, 0, stream>>>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna,
+      mk<<<static_cast<unsigned>(grid_m), kMedThreads, 0, stream>>>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna,
                                                             static_cast<T>(fill));
       return static_cast<int>(cudaGetLastError());
     }
