@@ -162,6 +162,45 @@ def test_stats_all_methods(engine, dtype, rtol, skipna):
             np.testing.assert_allclose(y, want, rtol=rtol, atol=rtol * 10, err_msg=method)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("cells", [(25, 25), (4, 3), (1, 1), (32, 32)])
+def test_median_adversarial_values(engine, dtype, cells):
+    """The register-resident select (sentinel keys, threshold counting, smallest / largest-of-range exits) on values
+    that stress the key order: heavy ties, +-inf, signed zeros, denormals, the type's extremes, constant cells,
+    cells whose valid count is odd / even / 1, for every cell shape class of the kernel's templates."""
+    rng = np.random.default_rng(99)
+    nr, nc = cells
+    n_lat, n_lon = 6, 9
+    lat = (np.arange(n_lat * nr) + 0.5) / nr
+    lon = (np.arange(n_lon * nc) + 0.5) / nc
+    tlat, tlon = np.arange(n_lat) + 0.5, np.arange(n_lon) + 0.5
+    fi = np.finfo(dtype)
+    big = fi.max / 4  # (big + big) / 2 stays finite in the data's own type (np.median averages in that type)
+    pool = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, big, -big, fi.tiny, -fi.tiny, fi.tiny / 4,
+                     -fi.tiny / 4, 2.0, 2.0 + 2 * fi.eps, 0.5, 3.0], dtype=dtype)
+    fields = [
+        pool[rng.integers(0, pool.size, (n_lat * nr, n_lon * nc))],             # everything, heavy ties
+        np.round(rng.normal(size=(n_lat * nr, n_lon * nc)) * 2).astype(dtype),  # small integers: long runs of ties
+        np.full((n_lat * nr, n_lon * nc), 7.25, dtype=dtype),                   # constant
+        (250 + 50 * rng.random((n_lat * nr, n_lon * nc))).astype(dtype),        # one binade or two, no sign change
+        np.where(rng.random((n_lat * nr, n_lon * nc)) < 0.5, big, -big).astype(dtype),
+    ]
+    x = np.stack(fields)
+    x[:, rng.random(x.shape[1:]) < 0.15] = np.nan      # odd and even valid counts
+    x[1, :nr, :nc] = np.nan                            # an all-NaN cell
+    x[2, :nr, :nc] = np.nan
+    x[2, 0, 0] = 5.0                                   # a single valid value
+    plan = _plan(engine, lat, lon, tlat, tlon)
+    for skipna in (True, False):
+        y = plan.stat(torch.from_numpy(x).cuda(), "median", skipna=skipna).cpu().numpy()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            want = orr.stat(x, [lat, lon], [tlat, tlon], [-2, -1], "median", skipna=skipna)
+        assert y.dtype == dtype
+        np.testing.assert_array_equal(np.isnan(y), np.isnan(want))
+        np.testing.assert_array_equal(y, want)  # equal values (signed zeros compare equal)
+
+
 def test_var_fp32_large_offset(engine):
     """fp32 var / std use one pass with fp64 moments shifted by the cell's first valid value: a field with
     mean / spread = 1e4 (temperatures in K with 0.03 K noise) must still match np.var within fp32 tolerance."""
