@@ -150,6 +150,27 @@ def test_nearest_dtypes_ties_and_out_of_range(engine, dtype):
     np.testing.assert_array_equal(y.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n_tlat", [36, 33, 68, 32, 5])
+def test_upsampling_band_prefetch_transitions(engine, dtype, n_tlat):
+    """The upsampling kernel prefetches the NEXT band's row taps and source rows while it produces the current one,
+    and falls back to a synchronous prologue after a band of <= 4 rows.  Many slabs on a small grid make every
+    persistent CTA walk through long / short band sequences (32 + 4, 32 + 1, 32 + 32 + 4, a single band, one short
+    band only); every slab is checked, so a row staged into the wrong window buffer cannot hide."""
+    rng = np.random.default_rng(31)
+    lat, lon = np.linspace(-30.0, 30.0, 12), np.linspace(10.0, 100.0, 16)
+    tlat, tlon = np.linspace(-30.0, 30.0, n_tlat), np.linspace(10.0, 100.0, 64)
+    batch = 700  # x bands > resident CTAs: several tasks per CTA
+    x = rng.normal(size=(batch, lat.size, lon.size)).astype(dtype)
+    x[rng.random(x.shape) < 0.01] = np.nan
+    x += np.arange(batch, dtype=dtype)[:, None, None]  # slabs differ by construction
+    plan = engine.InterpPlan(engine.AxisSpec(lat, tlat), engine.AxisSpec(lon, tlon), "linear")
+    y = plan(torch.from_numpy(x).cuda(), out_dtype="same")
+    assert y.dtype == (torch.float32 if dtype == np.float32 else torch.float64)
+    want = oi.regrid(x, [lat, lon], [tlat, tlon], [-2, -1], "linear").astype(dtype)
+    _check(y, want, 1e-5 if dtype == np.float32 else 1e-12, atol=1e-4 if dtype == np.float32 else 1e-10)
+
+
 def test_linear_nan_taps_poison_even_at_zero_weight(engine):
     lat, lon = np.arange(0.0, 6.0, 1.0), np.arange(0.0, 8.0, 1.0)
     tlat, tlon = np.array([0.0, 1.0, 1.5, 2.0, 3.0, 5.0]), np.array([0.0, 2.0, 2.5, 3.0, 4.0, 7.0])
