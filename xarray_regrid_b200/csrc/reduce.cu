@@ -970,26 +970,33 @@ stat_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, l
 // in registers.  No shared memory, no CTA barrier: warps are independent and many are resident.
 // CTAs of 4 warps, 7 per SM: 72 registers per thread allow 28 resident warps (3 x 8 warps would stop at 24)
 constexpr int kMedThreads = 128;
+__device__ __forceinline__ int src_index_near(const Bins& a, int pos) {
+  const int i = a.src_offset + a.src_step * pos;
+  return static_cast<unsigned>(i) < static_cast<unsigned>(a.n_src) ? i : src_index(a, pos);  // modulo only on a wrap
+}
+
 template <typename T, int CAP>
-__global__ void __launch_bounds__(kMedThreads, sizeof(T) == 8 ? 5 : 7)  // 64-bit keys: 96 registers, 20 warps
+__global__ void __launch_bounds__(kMedThreads, sizeof(T) == 8 ? 5 : 8)  // 64-bit keys: 96 registers, 20 warps
 median_direct_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
                      long long ybs, Bins rows, Bins cols, int skipna, T fill) {
   const int lane = threadIdx.x & 31;
-  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  // 32-bit cell arithmetic: the launcher keeps batch * Ho * Wo + the grid's warps below 2^32 per launch
+  const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
   const int Ho = rows.n_out, Wo = cols.n_out;
-  const long long cells = batch * Ho * Wo;
+  const unsigned cells = static_cast<unsigned>(batch) * Ho * Wo;
   const T nan = quiet_nan<T>();
   using K = decltype(to_key(T(0)));
-  for (long long cell = warp_id; cell < cells; cell += n_warps) {
-    const int l = static_cast<int>(cell % Wo);
-    const int k = static_cast<int>((cell / Wo) % Ho);
-    const long long b = cell / (static_cast<long long>(Wo) * Ho);
+  for (unsigned cell = warp_id; cell < cells; cell += n_warps) {
+    const unsigned row_id = cell / Wo;
+    const int l = static_cast<int>(cell - row_id * Wo);
+    const unsigned b = row_id / Ho;
+    const int k = static_cast<int>(row_id - b * Ho);
     T out = fill;
     if (rows.cover[k] != 0 && cols.cover[l] != 0) {
       const int nr = rows.count[k], nc = cols.count[l];  // host contract: nr <= CAP, nc <= 32
-      const T* col = x + b * xbs + src_index(cols, cols.start[l] + (lane < nc ? lane : 0));
-      const int r_first = src_index(rows, rows.start[k]);
+      const T* col = x + b * xbs + src_index_near(cols, cols.start[l] + (lane < nc ? lane : 0));
+      const int r_first = src_index_near(rows, rows.start[k]);
       const int r_last = r_first + rows.src_step * (nr - 1);
       const int nr_own = lane < nc ? nr : 0;  // lanes outside the cell load nothing
       K keys[CAP];  // empty slots (outside the cell, NaN) hold the all-ones sentinel
@@ -1180,13 +1187,23 @@ int stat_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64
     int per_sm_m = 0;
     RG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_m, mk, kMedThreads, 0));
     if (per_sm_m >= 1) {
-      const long long cells = static_cast<long long>(batch) * rows.n_out * cols.n_out;
-      long long grid_m = static_cast<long long>(dev.sm_count) * per_sm_m * 4;
-      const long long need = (cells + kMedThreads / 32 - 1) / (kMedThreads / 32);
-      if (grid_m > need) grid_m = need;
-      mk<<<static_cast<unsigned>(grid_m), kMedThreads, 0, stream>>>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna,
-                                                            static_cast<T>(fill));
-      return static_cast<int>(cudaGetLastError());
+      // the kernel counts cells in 32 bits: slabs are dealt to launches of < 2^31 cells each
+      const long long slab_cells = static_cast<long long>(rows.n_out) * cols.n_out;
+      if (slab_cells < (1ll << 31)) {
+        const long long b_max = std::max<long long>(1, ((1ll << 31) - 1) / slab_cells);
+        for (long long b0 = 0; b0 < batch; b0 += b_max) {
+          const long long nb = std::min<long long>(b_max, batch - b0);
+          const long long cells = nb * slab_cells;
+          long long grid_m = static_cast<long long>(dev.sm_count) * per_sm_m * 4;
+          const long long need = (cells + kMedThreads / 32 - 1) / (kMedThreads / 32);
+          if (grid_m > need) grid_m = need;
+          mk<<<static_cast<unsigned>(grid_m), kMedThreads, 0, stream>>>(x + b0 * xbs, y + b0 * ybs, nb, xbs, xrs, ybs,
+                                                                        rows, cols, skipna, static_cast<T>(fill));
+          const cudaError_t err = cudaGetLastError();
+          if (err != cudaSuccess) return static_cast<int>(err);
+        }
+        return RG_OK;
+      }
     }
   }
   // ---- throughput path (everything but the median): one cell per lane
