@@ -987,11 +987,17 @@ median_direct_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch
   const unsigned cells = static_cast<unsigned>(batch) * Ho * Wo;
   const T nan = quiet_nan<T>();
   using K = decltype(to_key(T(0)));
-  for (unsigned cell = warp_id; cell < cells; cell += n_warps) {
-    const unsigned row_id = cell / Wo;
-    const int l = static_cast<int>(cell - row_id * Wo);
-    const unsigned b = row_id / Ho;
-    const int k = static_cast<int>(row_id - b * Ho);
+  // (b, k, l) of the warp's cell advance by a fixed step with carries: no division per cell
+  const unsigned step_rows = n_warps / Wo;
+  const int dl = static_cast<int>(n_warps - step_rows * Wo);
+  const unsigned db = step_rows / Ho;
+  const int dk = static_cast<int>(step_rows - db * Ho);
+  int l = static_cast<int>(warp_id % Wo);
+  int k = static_cast<int>((warp_id / Wo) % Ho);
+  unsigned b = warp_id / Wo / Ho;
+  for (unsigned cell = warp_id; cell < cells; cell += n_warps, l += dl, k += dk, b += db) {
+    if (l >= Wo) { l -= Wo; ++k; }
+    if (k >= Ho) { k -= Ho; ++b; }
     T out = fill;
     if (rows.cover[k] != 0 && cols.cover[l] != 0) {
       const int nr = rows.count[k], nc = cols.count[l];  // host contract: nr <= CAP, nc <= 32
