@@ -86,7 +86,8 @@ poison_kernel(T* __restrict__ y, long long n, const int32_t* __restrict__ flag) 
 // factors A = L U once per axis (no pivoting: the system is diagonally dominant; the host checks the
 // factorisation against scipy), the device runs the forward / backward substitution: one thread per line,
 // the five factor diagonals in shared memory (broadcast reads), values prefetched 8 at a time so the
-// recurrence is the only serial dependency.  O(n) per line instead of the O(n * 63) of the truncated inverse.
+// recurrence is the only serial dependency (one FMA per element on the critical path: the term of the older
+// value is folded in first).  O(n) per line instead of the O(n * 63) of the truncated inverse.
 //   forward   z_i = y_i - l1_i z_{i-1} - l2_i z_{i-2}
 //   backward  c_i = (z_i - u1_i c_{i+1} - u2_i c_{i+2}) * dinv_i
 template <int AXIS>
@@ -116,7 +117,7 @@ spline_solve_kernel(double* __restrict__ y, long long batch, long long ybs, long
     for (int e = 0; e < 8; ++e) {
       const int i = i0 + e;
       if (i < n) {
-        const double zi = fma(-l2[i], z2, fma(-l1[i], z1, v[e]));
+        const double zi = fma(-l1[i], z1, fma(-l2[i], z2, v[e]));  // the inner term does not wait for z1
         z2 = z1;
         z1 = zi;
         p[i * step] = zi;
@@ -132,7 +133,7 @@ spline_solve_kernel(double* __restrict__ y, long long batch, long long ybs, long
     for (int e = 0; e < 8; ++e) {
       const int i = i0 - e;
       if (i >= 0) {
-        const double ci = fma(-u2[i], c2, fma(-u1[i], c1, v[e])) * dinv[i];
+        const double ci = fma(-u1[i], c1, fma(-u2[i], c2, v[e])) * dinv[i];
         c2 = c1;
         c1 = ci;
         p[i * step] = ci;
@@ -177,7 +178,7 @@ spline_solve_tile_kernel(double* __restrict__ y, long long n_lines, int H, long 
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const double zi = fma(-a2[e], z2, fma(-a1[e], z1, v[e]));
+        const double zi = fma(-a1[e], z1, fma(-a2[e], z2, v[e]));  // the inner term does not wait for z1
         if (i0 + e < n) {
           z2 = z1;
           z1 = zi;
@@ -198,7 +199,7 @@ spline_solve_tile_kernel(double* __restrict__ y, long long n_lines, int H, long 
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const double ci = fma(-a2[e], c2, fma(-a1[e], c1, v[e])) * d[e];
+        const double ci = fma(-a1[e], c1, fma(-a2[e], c2, v[e])) * d[e];
         if (i0 - e >= 0) {
           c2 = c1;
           c1 = ci;
