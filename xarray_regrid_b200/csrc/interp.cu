@@ -156,11 +156,19 @@ spline_solve_tile_kernel(double* __restrict__ y, long long n_lines, int H, long 
   for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_fac[2 * n + i] = upper[i];
   const long long line0 = static_cast<long long>(blockIdx.x) * kTileLines;
   const int lines = static_cast<int>(min(static_cast<long long>(kTileLines), n_lines - line0));
+  // all lines of the tile in flight at once (LDGSTS, 8 bytes per request: the odd pitch allows no wider one); with
+  // plain loads + stores the lines were fetched one after the other and the kernel spent its time on their latency
+  // (ncu: long-scoreboard 9.5 warps per issue, 11 % issue activity)
   for (int l = 0; l < lines; ++l) {
     const long long line = line0 + l;
     const double* src = y + (line / H) * ybs + (line % H) * yrs;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) tile[l * pitch + j] = src[j];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(tile + l * pitch + j));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + j) : "memory");
+    }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (threadIdx.x < lines) {
     const double *l1 = s_fac, *l2 = s_fac + n, *dinv = s_fac + 2 * n, *u1 = s_fac + 3 * n, *u2 = s_fac + 4 * n;
