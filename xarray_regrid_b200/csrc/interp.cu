@@ -108,11 +108,15 @@ spline_solve_kernel(double* __restrict__ y, long long batch, long long ybs, long
   double* p = y + b * ybs + (AXIS == 0 ? static_cast<long long>(j) : static_cast<long long>(j) * yrs);
   const long long step = AXIS == 0 ? yrs : 1;
 
+  // The solve is in place, so the compiler may not move the next 8 loads above this batch's stores: they are issued
+  // by hand one batch ahead (the batches touch disjoint elements), otherwise every batch waits a full DRAM latency.
   double z1 = 0.0, z2 = 0.0;
-  for (int i0 = 0; i0 < n; i0 += 8) {
-    double v[8];
+  double v[8], vn[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (i0 + e < n) ? p[(i0 + e) * step] : 0.0;
+  for (int e = 0; e < 8; ++e) v[e] = (e < n) ? p[e * step] : 0.0;
+  for (int i0 = 0; i0 < n; i0 += 8) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) vn[e] = (i0 + 8 + e < n) ? p[(i0 + 8 + e) * step] : 0.0;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int i = i0 + e;
@@ -123,12 +127,15 @@ spline_solve_kernel(double* __restrict__ y, long long batch, long long ybs, long
         p[i * step] = zi;
       }
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = vn[e];
   }
   double c1 = 0.0, c2 = 0.0;
-  for (int i0 = n - 1; i0 >= 0; i0 -= 8) {
-    double v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (i0 - e >= 0) ? p[(i0 - e) * step] : 0.0;
+  for (int e = 0; e < 8; ++e) v[e] = (n - 1 - e >= 0) ? p[(n - 1 - e) * step] : 0.0;
+  for (int i0 = n - 1; i0 >= 0; i0 -= 8) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) vn[e] = (i0 - 8 - e >= 0) ? p[(i0 - 8 - e) * step] : 0.0;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int i = i0 - e;
@@ -139,6 +146,8 @@ spline_solve_kernel(double* __restrict__ y, long long batch, long long ybs, long
         p[i * step] = ci;
       }
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = vn[e];
   }
 }
 
