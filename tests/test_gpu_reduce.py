@@ -201,6 +201,34 @@ def test_median_adversarial_values(engine, dtype, cells):
         np.testing.assert_array_equal(y, want)  # equal values (signed zeros compare equal)
 
 
+@pytest.mark.parametrize("n_lon", [1001, 1003, 1006])
+@pytest.mark.parametrize("descending", [False, True])
+def test_staging_phase_carried_across_rows(engine, n_lon, descending):
+    """The lane kernels (most_common planes, stat) carry the 16-byte phase of a staged row segment from row to row
+    ((phase + row stride) mod 16).  Row pitches that are not multiples of 16 bytes (odd widths; uint8, fp32 and fp64
+    elements) and a descending source latitude (negative row step) exercise every residue of that update."""
+    rng = np.random.default_rng(41 + n_lon)
+    lat = (np.arange(60) + 0.5) * 0.1
+    lon = (np.arange(n_lon) + 0.5) * 0.1
+    tlat = np.arange(0.5, 6.0, 1.0)                 # 10 source rows per cell
+    tlon = np.arange(0.5, n_lon * 0.1 - 0.5, 1.0)  # 10 source columns per cell
+    if descending:
+        lat = lat[::-1].copy()
+    plan = _plan(engine, lat, lon, tlat, tlon)
+    labels = rng.integers(0, 9, (3, lat.size, lon.size)).astype(np.uint8)
+    values = np.arange(9)
+    y = plan.mode(torch.from_numpy(labels).cuda(), values).cpu().numpy()
+    np.testing.assert_array_equal(y, orr.mode(labels, [lat, lon], [tlat, tlon], [-2, -1], values))
+    for dtype, rtol in ((np.float32, 1e-5), (np.float64, 1e-12)):
+        x = rng.normal(size=(3, lat.size, lon.size)).astype(dtype)
+        x[rng.random(x.shape) < 0.03] = np.nan
+        for method in ("mean", "var", "max"):
+            got = plan.stat(torch.from_numpy(x).cuda(), method, skipna=True).cpu().numpy()
+            want = orr.stat(x, [lat, lon], [tlat, tlon], [-2, -1], method, skipna=True)
+            np.testing.assert_array_equal(np.isnan(got), np.isnan(want), err_msg=method)
+            np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * 10, err_msg=method)
+
+
 def test_var_fp32_large_offset(engine):
     """fp32 var / std use one pass with fp64 moments shifted by the cell's first valid value: a field with
     mean / spread = 1e4 (temperatures in K with 0.03 K noise) must still match np.var within fp32 tolerance."""
