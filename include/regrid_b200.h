@@ -38,7 +38,8 @@ extern "C" {
 #define RG_ERR_UNSUPPORTED (-4)
 #define RG_ERR_ALIGN (-5)
 
-#define RG_ABI_VERSION 2 /* 2: rg_band_t.window_rows, rg_row_ring_t.lane_cols, rg_mode max_bin_rows/cols, rg_spline_solve_f64 */
+#define RG_ABI_VERSION 3 /* 3: rg_pipeline_*, rg_host_copy, pole source rows in rg_row_nanmean_* / rg_conservative_host_*,
+                            rg_conservative_*(skipna = 0) counts NaN as 0 like the reference's fillna(0) */
 
 /* ABI version of the loaded library (== RG_ABI_VERSION of the header it was built from). */
 int rg_abi_version(void);
@@ -145,7 +146,9 @@ typedef struct rg_row_ring {
  *   valid[b,k,l] = sum_ij notnull(x[b,i,j]) * Wlat[i,k] * Wlon[j,l]
  *   out  [b,k,l] = sum_ij fillna0(x[b,i,j]) * Wlat[i,k] * Wlon[j,l]
  *   skipna:  y = out / valid where valid >= valid_thr else NaN
- *   !skipna: y = out (NaN propagates through non-zero taps only)
+ *   !skipna: y = out -- a NaN counts as 0: the reference contracts da.fillna(0) whether or not
+ *            skipna is set (conservative.py:196-198); only the division and the threshold are
+ *            conditional (conservative.py:200-202).  (NaN-propagating contraction: rg_separable_*.)
  *   y = NaN where !(cover_lat[k] && cover_lon[l])
  *
  * Replaces apply_weights (methods/conservative.py:181-208) plus the coverage mask of
@@ -171,41 +174,99 @@ int rg_conservative_f32(const float* x, float* y, int64_t batch,
                         const rg_row_ring_t* ring, void* stream);
 
 /*
- * Longitude-mean (NaN-skipping) of the first and last row of every slab, written as full rows:
- * pole[b,0,:] = nanmean(x[b,0,:]), pole[b,1,:] = nanmean(x[b,H-1,:]); all-NaN -> NaN.  pole is [batch, 2, W].
- * Replaces the `.mean(lon_coord)` of format_lat (utils.py:320-333).
+ * Longitude-mean (NaN-skipping) of the southernmost and northernmost row of every slab, written as full rows:
+ * pole[b,0,:] = nanmean(x[b,south_row,:]), pole[b,1,:] = nanmean(x[b,north_row,:]); all-NaN -> NaN.
+ * pole is [batch, 2, W].  south_row / north_row are positions in the caller's (possibly descending or
+ * unsorted) latitude order: the reference sorts first (ensure_monotonic, utils.py:277) and then takes
+ * isel(lat=0) / isel(lat=-1).  Replaces the `.mean(lon_coord)` of format_lat (utils.py:320-333).
  */
 int rg_row_nanmean_f64(const double* x, double* pole, int64_t batch, int32_t H, int32_t W,
-                       int64_t x_batch_stride, int64_t x_row_stride, void* stream);
+                       int64_t x_batch_stride, int64_t x_row_stride, int32_t south_row, int32_t north_row,
+                       void* stream);
 int rg_row_nanmean_f32(const float* x, float* pole, int64_t batch, int32_t H, int32_t W,
-                       int64_t x_batch_stride, int64_t x_row_stride, void* stream);
+                       int64_t x_batch_stride, int64_t x_row_stride, int32_t south_row, int32_t north_row,
+                       void* stream);
+
+/*
+ * Persistent host <-> device streaming pipeline: three non-blocking streams (H2D, compute, D2H) and one
+ * event triple per slot, created once and reused for any number of chunks and calls.  It stands in for the
+ * reference's dask chunk scheduling (methods/conservative.py:263-302: weights chunked 1:1 with the data;
+ * interp.py:43 and flox_reduce.py:89 run per dask block).  A "slot" is a caller-owned set of device buffers
+ * (input chunk, result chunk, scratch); the pipeline only orders the work on them:
+ *
+ *   rg_pipeline_h2d(p, slot, ...)       the H2D stream waits until the kernels that read the slot's previous
+ *                                       input are done, then ONE cudaMemcpyAsync
+ *   rg_pipeline_compute_begin(p, slot)  the compute stream waits for the slot's H2D and for the D2H of the
+ *                                       slot's previous result; the caller then launches any rg_* calls on
+ *                                       rg_pipeline_stream(p, 1)
+ *   rg_pipeline_compute_end(p, slot)    marks the slot's kernels as queued
+ *   rg_pipeline_d2h(p, slot, ...)       the D2H stream waits for the slot's kernels, then ONE cudaMemcpyAsync
+ *   rg_pipeline_sync(p, stage, slot)    host-blocks until the slot's last H2D (stage 0), kernels (1) or D2H (2)
+ *                                       has finished (e.g. before a pageable staging buffer is refilled)
+ *   rg_pipeline_wait_stream(p, stream)  all pipeline streams wait for the work queued so far on the caller's
+ *                                       stream (buffers produced / recycled there are then safe to use)
+ *   rg_pipeline_drain(p)                host-blocks until all three streams are idle
+ *
+ * Host pointers of rg_pipeline_h2d / _d2h should be page-locked for full PCIe bandwidth.  For pageable arrays
+ * (numpy) rg_pipeline_h2d_pageable / _d2h_pageable cut the chunk into pieces that pass through a caller-owned
+ * page-locked staging buffer (`stage_pinned`, split into 4 pieces; >= 16 KiB) with a multi-threaded memcpy
+ * (rg_host_copy, `n_threads` threads) overlapping the DMA of the neighbouring piece -- still one
+ * cudaMemcpyAsync per piece.  _h2d_pageable blocks the host only when it laps the staging ring;
+ * _d2h_pageable returns when the whole chunk is in `dst_host` (queue the next chunk's work before it).
+ * Not thread-safe per handle.
+ */
+typedef struct rg_pipeline rg_pipeline_t;
+int rg_pipeline_create(rg_pipeline_t** out, int32_t n_slots); /* 1 <= n_slots <= 8 */
+int rg_pipeline_destroy(rg_pipeline_t* p);                   /* drains first; NULL is a no-op */
+int32_t rg_pipeline_slots(const rg_pipeline_t* p);
+void* rg_pipeline_stream(rg_pipeline_t* p, int32_t which);   /* 0: H2D, 1: compute, 2: D2H (cudaStream_t) */
+int rg_pipeline_h2d(rg_pipeline_t* p, int32_t slot, void* dst_device, const void* src_host, size_t bytes);
+int rg_pipeline_compute_begin(rg_pipeline_t* p, int32_t slot);
+int rg_pipeline_compute_end(rg_pipeline_t* p, int32_t slot);
+int rg_pipeline_d2h(rg_pipeline_t* p, int32_t slot, void* dst_host, const void* src_device, size_t bytes);
+int rg_pipeline_h2d_pageable(rg_pipeline_t* p, int32_t slot, void* dst_device, const void* src_host, size_t bytes,
+                             void* stage_pinned, size_t stage_bytes, int32_t n_threads);
+int rg_pipeline_d2h_pageable(rg_pipeline_t* p, int32_t slot, void* dst_host, const void* src_device, size_t bytes,
+                             void* stage_pinned, size_t stage_bytes, int32_t n_threads);
+int rg_pipeline_sync(rg_pipeline_t* p, int32_t stage, int32_t slot);
+int rg_pipeline_wait_stream(rg_pipeline_t* p, void* stream);
+int rg_pipeline_drain(rg_pipeline_t* p);
+int rg_host_copy(void* dst, const void* src, size_t bytes, int32_t n_threads);
 
 /*
  * Host-buffer variant of rg_conservative_*: x_host / y_host are HOST pointers
  * (pinned memory gives full PCIe bandwidth; pageable memory works but is staged by the
  * driver).  The stack is cut into chunks of `chunk_batch` slabs that are copied in,
- * regridded and copied out on three internal streams so that H2D, the kernel and D2H
+ * regridded and copied out on the three streams of `pipeline` so that H2D, the kernel and D2H
  * overlap (stands in for the reference's dask chunk scheduling,
- * methods/conservative.py:263-302).  `workspace` is caller-owned DEVICE memory of at
- * least rg_conservative_host_workspace(...) bytes.  The call returns after the last
- * D2H copy has completed (it synchronises its internal streams, not the device).
- * Host layout is dense: x_host [batch, H, W], y_host [batch, Ho, Wo].
+ * methods/conservative.py:263-302).  `pipeline` is a persistent rg_pipeline_t, or NULL: a
+ * temporary 3-slot pipeline is created and destroyed inside the call.  `workspace` is
+ * caller-owned DEVICE memory of at least rg_conservative_host_workspace(..., n_slots) bytes
+ * (n_slots = rg_pipeline_slots(pipeline), 3 for NULL).  The call returns after the last D2H
+ * copy has completed, unless RG_HOST_NO_DRAIN is set in `flags` (persistent pipelines only): the
+ * caller then queues further calls and finishes with rg_pipeline_drain.  After an error the
+ * pipeline is drained before returning: nothing stays in flight into the caller's buffers.
+ * pole_rows != 0: the rows band references the synthetic pole rows; south_row / north_row as in
+ * rg_row_nanmean_*.  Host layout is dense: x_host [batch, H, W], y_host [batch, Ho, Wo].
  */
+#define RG_HOST_NO_DRAIN 1
 size_t rg_conservative_host_workspace(int64_t chunk_batch, int32_t H, int32_t W, int32_t Ho,
-                                      int32_t Wo, int32_t elem_size);
+                                      int32_t Wo, int32_t elem_size, int32_t n_slots);
 int rg_conservative_host_f64(const double* x_host, double* y_host, int64_t batch,
                              int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
-                             int32_t skipna, double valid_thr, int32_t pole_rows,
-                             const rg_row_ring_t* ring, void* workspace, size_t workspace_bytes);
+                             int32_t skipna, double valid_thr, int32_t pole_rows, int32_t south_row,
+                             int32_t north_row, const rg_row_ring_t* ring, void* workspace,
+                             size_t workspace_bytes, rg_pipeline_t* pipeline, int32_t flags);
 int rg_conservative_host_f32(const float* x_host, float* y_host, int64_t batch,
                              int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
-                             int32_t skipna, float valid_thr, int32_t pole_rows,
-                             const rg_row_ring_t* ring, void* workspace, size_t workspace_bytes);
+                             int32_t skipna, float valid_thr, int32_t pole_rows, int32_t south_row,
+                             int32_t north_row, const rg_row_ring_t* ring, void* workspace,
+                             size_t workspace_bytes, rg_pipeline_t* pipeline, int32_t flags);
 
 /*
  * Separable banded contraction y[b,k,l] = sum_t sum_c wr[t,k] * wc[c,l] * x[b, ri[t,k], ci[c,l]] with NaN
  * propagating through every tap (weight 0 included) and y = NaN where !(cover_r[k] && cover_c[l]).
- * Same kernels as rg_conservative_* with skipna = 0.  It replaces `data.interp(coords, method)`
+ * Same kernels as rg_conservative_*, without any NaN bookkeeping.  It replaces `data.interp(coords, method)`
  * (methods/interp.py:43-46 -> scipy interp1d per axis) for
  *   linear: 2-tap bands (tables.linear_band);
  *   cubic : first the prefilter bands (A^-1 of the not-a-knot collocation system, source grid ->

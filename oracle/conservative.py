@@ -94,19 +94,17 @@ def covered_mask(src, tgt):
 
 
 # ------------------------------------------------------------------------- contraction
-def apply_weights(data, w_by_axis, skipna, nan_threshold, nan_through_zero_weights=True):
+def apply_weights(data, w_by_axis, skipna, nan_threshold):
     """conservative.py:181-208 for 1 or 2 regridded axes.
 
     ``w_by_axis`` maps a (negative) axis of ``data`` to its dense [n_src, n_tgt]
     weights, already cast to ``result_type(float32, data.dtype)``
     (conservative.py:281).
 
-    ``nan_through_zero_weights``: with ``skipna=False`` and NaNs in the input the
-    reference's result depends on which optional packages are installed -- dense
-    numpy weights give 0*NaN = NaN for EVERY target cell of the slab, ``sparse``
-    weights only propagate NaN through structurally non-zero taps.  True selects
-    the dense ("no extras") behaviour, False the sparse one, which is what the
-    engine implements (DESIGN.md "NaN semantics").
+    ``skipna=False``: the reference still contracts ``da.fillna(0)`` (conservative.py:196-198
+    is outside the ``if skipna`` branches); only the division by the valid mass and the
+    threshold mask are conditional (conservative.py:200-202).  A NaN therefore counts as 0
+    and the result is finite, with dense and with ``sparse`` weights alike.
     """
     axes = sorted(w_by_axis)  # e.g. [-2, -1]
     nd = data.ndim
@@ -126,18 +124,8 @@ def apply_weights(data, w_by_axis, skipna, nan_threshold, nan_through_zero_weigh
     notnull = ~np.isnan(data)
     filled = np.where(notnull, data, 0).astype(np.result_type(data.dtype, wdtype))
 
-    if not skipna and not nan_through_zero_weights:
-        # sparse semantics: NaN reaches a target only through non-zero taps
-        poisoned = np.einsum(
-            spec, (~notnull).astype(wdtype), *[(w != 0).astype(wdtype) for w in operands],
-            optimize=True,
-        ) > 0
-        out = np.einsum(spec, filled, *operands, optimize=True)
-        out[poisoned] = np.nan
-        return out
-
     if not skipna:
-        return np.einsum(spec, data.astype(filled.dtype), *operands, optimize=True)
+        return np.einsum(spec, filled, *operands, optimize=True)
 
     valid = np.einsum(spec, notnull, *operands, optimize=True)
     out = np.einsum(spec, filled, *operands, optimize=True)
@@ -156,7 +144,6 @@ def regrid(
     latitude_index=None,
     skipna=True,
     nan_threshold=1.0,
-    nan_through_zero_weights=True,
 ):
     """Everything ``conservative_regrid`` does after ``format_for_regrid``
     (conservative.py:39-178) for the regridded ``axes`` of ``data``.
@@ -183,7 +170,7 @@ def regrid(
         # reindex_like(target): pick, for every original target label, its sorted position
         restore[ax] = np.searchsorted(tgt_sorted, tgt)
 
-    out = apply_weights(data, w_by_axis, skipna, nan_threshold, nan_through_zero_weights)
+    out = apply_weights(data, w_by_axis, skipna, nan_threshold)
     for ax, mask in cover.items():
         shape = [1] * out.ndim
         shape[ax] = mask.size
@@ -195,7 +182,7 @@ def regrid(
 
 def regrid_latlon(
     data, src_lat, src_lon, tgt_lat, tgt_lon, skipna=True, nan_threshold=1.0,
-    latitude_weighting=True, nan_through_zero_weights=True,
+    latitude_weighting=True,
 ):
     """``da.regrid.conservative(target)`` for data laid out ``[..., lat, lon]`` with
     coordinates NAMED latitude/longitude: ``format_for_regrid`` (regrid.py:123) then
@@ -207,5 +194,4 @@ def regrid_latlon(
         data, [lat, lon], [tgt_lat, tgt_lon], [-2, -1],
         latitude_index=0 if latitude_weighting else None,
         skipna=skipna, nan_threshold=nan_threshold,
-        nan_through_zero_weights=nan_through_zero_weights,
     )

@@ -36,5 +36,22 @@ def test_argument_errors_without_a_gpu():
     from xarray_regrid_b200 import _lib
 
     assert _lib.lib.rg_conservative_f64(None, None, 1, 1, 1, 1, None, None, 1, 0.5, None, None, None) == -1
-    assert _lib.lib.rg_conservative_host_workspace(0, 1, 1, 1, 1, 8) == 0
-    assert _lib.lib.rg_conservative_host_workspace(2, 721, 1440, 181, 360, 8) >= 3 * 2 * (721 * 1440 + 181 * 360) * 8
+    assert _lib.lib.rg_conservative_host_workspace(0, 1, 1, 1, 1, 8, 3) == 0
+    assert _lib.lib.rg_conservative_host_workspace(2, 721, 1440, 181, 360, 8, 3) >= 3 * 2 * (721 * 1440 + 181 * 360) * 8
+    assert _lib.lib.rg_pipeline_h2d(None, 0, None, None, 0) == -1
+    assert _lib.lib.rg_pipeline_slots(None) == 0
+    assert _lib.lib.rg_row_nanmean_f64(None, None, 1, 4, 4, 16, 4, 0, 3, None) == -1
+
+
+def test_host_copy_is_a_plain_memcpy():
+    """rg_host_copy (the staging copy of the pageable host paths) needs no GPU: any size, any thread count."""
+    import numpy as np
+
+    from xarray_regrid_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    for n, threads in [(0, 4), (1, 1), (4097, 3), (9 << 20, 1), (33 << 20, 7), ((40 << 20) + 13, 64)]:
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        dst = np.zeros(n + 8, dtype=np.uint8)
+        assert _lib.lib.rg_host_copy(dst.ctypes.data, src.ctypes.data, n, threads) == 0
+        assert np.array_equal(dst[:n], src) and not dst[n:].any()

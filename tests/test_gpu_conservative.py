@@ -126,30 +126,34 @@ def test_lane_owned_columns_variant(eng, dtype, skipna, aligned_edges):
     assert ring is not None and ring.host.lane_cols == 4, "grid should qualify for the lanes variant"
     assert int(ring.host.n_strips) <= int(ring.host.n_warps) <= 12
     y = plan(xt, skipna=skipna, nan_threshold=0.5)
-    # skipna=False: NaN reaches a target only through non-zero taps (the reference's sparse weights)
-    want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=0.5,
-                            nan_through_zero_weights=False)
+    # skipna=False: a NaN counts as 0 (the reference's unconditional fillna(0))
+    want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=0.5)
     _check(y, want, RTOL[dtype])
     plan.use_ring = False
     _check(plan(xt, skipna=skipna, nan_threshold=0.5), want, RTOL[dtype])
     assert tables.lane_owned_columns(plan.cols_band, ring.host.strip_l0, ring.host.n_warps) == 4
 
 
-def test_skipna_false_with_nans_uses_sparse_semantics(eng):
-    """With skipna=False NaN reaches a target cell only through non-zero taps (the reference's
-    `sparse` weights); the dense no-extras install would blank the whole slab."""
+def test_skipna_false_counts_nan_as_zero(eng):
+    """apply_weights contracts da.fillna(0) whether or not skipna is set (reference
+    methods/conservative.py:196-198): with skipna=False a NaN counts as 0 and every target stays finite,
+    on all three kernels and through the host pipeline."""
     engine, syn = eng
     lat, lon = syn.grid_025()
     tlat, tlon = syn.grid_1()
-    x = syn.conservative_stack(1, lat, lon, nan_fraction=0.0)
+    x = syn.conservative_stack(2, lat, lon, nan_fraction=0.0)
     x[0, 360, 720] = float("nan")
-    x[0, 0, 5] = float("nan")  # pole row has zero area weight: must NOT poison anything
+    x[0, 0, 5] = float("nan")
+    x[1, 100:140, 300:420] = float("nan")  # whole target cells missing -> exactly 0
     plan = _latlon_plan(engine, lat, lon, tlat, tlon)
-    y = plan(x, skipna=False)
-    want = oc.regrid_latlon(x.cpu().numpy(), lat, lon, tlat, tlon, skipna=False,
-                            nan_through_zero_weights=False)
-    assert np.isnan(want).sum() == 1
-    _check(y, want, 1e-12)
+    want = oc.regrid_latlon(x.cpu().numpy(), lat, lon, tlat, tlon, skipna=False)
+    assert np.isfinite(want).all() and (want == 0).any()
+    for kernel in KERNELS:
+        _pick(plan, kernel)
+        _check(plan(x, skipna=False), want, 1e-12)
+    _pick(plan, "lanes")
+    _check(plan.apply_host(x.cpu().pin_memory(), skipna=False, chunk_batch=1), want, 1e-12)
+    _check(plan.apply_host(x.cpu().numpy(), skipna=False, chunk_batch=1), want, 1e-12)
 
 
 def test_reference_known_answer_joint_valid_mass(eng):
@@ -200,8 +204,7 @@ def test_cell_centred_grid_with_pole_rows_and_wrap(eng, dtype):
             assert plan._ring(4, lat.size, lon.size, torch.from_numpy(x).dtype) is not None
         for skipna, thr in [(True, 1.0), (True, 0.3), (False, 1.0)]:
             y = plan(torch.from_numpy(x).cuda(), skipna=skipna, nan_threshold=thr)
-            want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr,
-                                    nan_through_zero_weights=False)
+            want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr)
             _check(y, want, RTOL[dtype])
 
 
@@ -250,7 +253,7 @@ def test_pole_rows_with_weight_through_ring_and_host_pipeline(eng, dtype):
     xt = torch.from_numpy(x).cuda()
     for skipna, thr in [(True, 0.5), (False, 1.0)]:
         want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr,
-                                latitude_weighting=False, nan_through_zero_weights=False)
+                                latitude_weighting=False)
         for kernel in ("ring", "generic"):
             _pick(plan, kernel)
             if kernel == "ring":

@@ -87,8 +87,7 @@ def test_conservative_irregular(engine, seed, dtype):
     x[rng.random(x.shape) < 0.1] = np.nan
     thr = float(rng.choice([0.0, 0.3, 0.5, 1.0]))
     plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat), engine.AxisSpec(lon, tlon))
-    want = oc.regrid(x, [lat, lon], [tlat, tlon], [-2, -1], skipna=skipna, nan_threshold=thr,
-                     nan_through_zero_weights=False)
+    want = oc.regrid(x, [lat, lon], [tlat, tlon], [-2, -1], skipna=skipna, nan_threshold=thr)
     rtol = 1e-12 if dtype == np.float64 else 1e-5
     for ring in (True, False):
         plan.use_ring = ring

@@ -1,0 +1,244 @@
+"""Round-2 parity cases: pole rows on descending / shuffled latitudes, latitude-only pole rows (plain copies),
+the streaming host paths of every plan (page-locked and pageable memory) and the accessor's host routing."""
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import conservative as oc  # noqa: E402
+from oracle import formatting as of  # noqa: E402
+from oracle import interp as oi  # noqa: E402
+from oracle import reduce as orr  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xarray_regrid_b200 import engine as e
+
+    return e
+
+
+def _check(got, want, rtol, atol=0.0):
+    got = got.cpu().numpy() if hasattr(got, "cpu") else np.asarray(got)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+def _lat_orders():
+    asc = np.arange(-89.0, 90.0, 2.0)
+    rng = np.random.default_rng(5)
+    return {"descending": asc[::-1].copy(), "shuffled": rng.permutation(asc)}
+
+
+# ------------------------------------------------------------------ pole rows of a re-ordered latitude
+@pytest.mark.parametrize("order", ["descending", "shuffled"])
+@pytest.mark.parametrize("method", ["linear", "nearest", "cubic"])
+def test_pole_rows_descending_and_shuffled_latitude_interp(engine, order, method):
+    """The reference sorts the latitude first (ensure_monotonic, utils.py:277) and takes the pole means from
+    the first / last SORTED row (utils.py:320-333): the south pole is the mean of the southernmost row
+    wherever that row sits in the caller's array."""
+    lat = _lat_orders()[order]
+    lon = np.arange(1.0, 360.0, 2.0)
+    tlat, tlon = np.arange(-90.0, 90.5, 1.5), np.arange(0.0, 360.0, 3.0)
+    rng = np.random.default_rng(17)
+    # a strong latitude gradient: the two pole means differ by ~178, so a swapped pole row cannot hide
+    x = lat[None, :, None] + rng.random((3, lat.size, lon.size))
+    plan = engine.InterpPlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"), method)
+    assert plan.rows_axis.has_pole_rows
+    y = plan(torch.from_numpy(x).cuda())
+    want = oi.regrid_latlon(x, lat, lon, tlat, tlon, method)
+    scale = np.nanmax(np.abs(want))
+    _check(y, want, 0.0 if method == "nearest" else 1e-11, atol=0.0 if method == "nearest" else 1e-11 * scale)
+    # the pole targets themselves
+    south = np.nanmean(x[:, np.argmin(lat), :], axis=-1)
+    if method != "cubic":
+        np.testing.assert_allclose(y[:, 0, :].cpu().numpy(), np.broadcast_to(south[:, None], (3, tlon.size)),
+                                   rtol=1e-12)
+
+
+@pytest.mark.parametrize("order", ["descending", "shuffled"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_pole_rows_descending_latitude_conservative_plain_rows(engine, order, dtype):
+    """Non-spherical conservative keeps a non-zero weight on the pole rows: all kernels and the host pipeline."""
+    lat = _lat_orders()[order]
+    lon = np.arange(1.0, 360.0, 2.0)
+    tlat, tlon = np.arange(-90.0, 91.0, 1.0), np.arange(0.0, 361.0, 1.0)
+    rng = np.random.default_rng(23)
+    x = (lat[None, :, None] + rng.random((4, lat.size, lon.size))).astype(dtype)
+    x[1, np.argmin(lat), :9] = np.nan
+    x[2, np.argmax(lat), :] = np.nan
+    plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"),
+                                   spherical_rows=False)
+    assert plan.pole_rows and plan.pole_src == (int(np.argmin(lat)), int(np.argmax(lat)))
+    rtol = 1e-12 if dtype == np.float64 else 2e-5
+    for skipna, thr in [(True, 0.5), (False, 1.0)]:
+        want = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr,
+                                latitude_weighting=False)
+        for use_ring in (True, False):
+            plan.use_ring = use_ring
+            _check(plan(torch.from_numpy(x).cuda(), skipna=skipna, nan_threshold=thr), want, rtol, atol=rtol)
+        plan.use_ring = True
+        _check(plan.apply_host(torch.from_numpy(x).pin_memory(), skipna=skipna, nan_threshold=thr, chunk_batch=3),
+               want, rtol, atol=rtol)
+        _check(plan.apply_host(x, skipna=skipna, nan_threshold=thr, chunk_batch=3), want, rtol, atol=rtol)
+
+
+@pytest.mark.parametrize("method", ["linear", "nearest", "cubic", "conservative"])
+def test_latitude_only_pole_rows_are_copies(method):
+    """Without a lon / longitude coordinate format_lat pads the poles with a plain COPY of the edge row
+    (utils.py:322-323, 330-331 only average when lon exists): a (time, lat) array must not be averaged over
+    time, and (lat, x) must not be averaged over x."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xarray_regrid_b200.labelled import DataArray, Dataset
+
+    lat = np.arange(89.5, -90.0, -1.0)  # descending, cell-centred, global
+    tlat = np.arange(-90.0, 90.5, 2.5)
+    rng = np.random.default_rng(3)
+    for dims, shape in ((("time", "lat"), (5, lat.size)), (("lat", "x"), (lat.size, 7))):
+        x = rng.random(shape) + 10.0 * np.arange(shape[0])[:, None]
+        coords = {d: (lat if d == "lat" else np.arange(float(n))) for d, n in zip(dims, shape)}
+        da = DataArray(x, dims, coords)
+        tgt = Dataset({}, {"lat": tlat})
+        fn = getattr(da.regrid, method)
+        out = fn(tgt, skipna=False) if method == "conservative" else fn(tgt)
+        ax = dims.index("lat")
+        data, flat, _ = of.format_for_regrid(x, lat, None, tlat, None, lat_axis=ax - 2, lon_axis=None)
+        if method == "conservative":
+            want = oc.regrid(data, [flat], [tlat], [ax], latitude_index=0, skipna=False)
+        else:
+            want = oi.regrid(data, [flat], [tlat], [ax], method)
+        assert out.dims == dims
+        np.testing.assert_array_equal(np.isnan(out.data), np.isnan(want))
+        np.testing.assert_allclose(out.data, want, rtol=1e-10, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------- streaming host paths
+@pytest.mark.parametrize("method", ["linear", "nearest", "cubic"])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_interp_apply_host_matches_device_path(engine, method, pinned):
+    """InterpPlan.apply_host streams chunks through the persistent pipeline; the result is bit-identical to
+    the device path and the device only ever holds `slots` chunks."""
+    lat, lon = np.arange(-90.0, 91.0, 3.0), np.arange(0.0, 360.0, 3.0)
+    tlat, tlon = np.arange(-90.0, 90.1, 0.75), np.arange(0.0, 359.9, 0.75)
+    rng = np.random.default_rng(11)
+    if method == "nearest":
+        x = rng.integers(0, 50, (11, lat.size, lon.size)).astype(np.int32)
+    else:
+        x = (250 + 50 * rng.random((11, lat.size, lon.size))).astype(np.float32)
+    plan = engine.InterpPlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"), method)
+    ref = plan(torch.from_numpy(x).cuda()).cpu()
+    xh = torch.from_numpy(x).pin_memory() if pinned else x
+    pipe = engine.HostPipeline(slots=3)
+    got = plan.apply_host(xh, chunk_batch=4, pipeline=pipe)
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
+    want = oi.regrid_latlon(x, lat, lon, tlat, tlon, method)
+    _check(got, want, 0.0 if method == "nearest" else 1e-10, atol=0.0 if method == "nearest" else 1e-9)
+    # a second call reuses the pipeline, its buffers and (for "same") a caller-provided result buffer
+    out = torch.empty(ref.shape, dtype=ref.dtype)
+    again = plan.apply_host(xh, out_host=out, chunk_batch=5, pipeline=pipe)
+    assert again.data_ptr() == out.data_ptr()
+    assert torch.equal(torch.nan_to_num(again, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
+    pipe.close()
+
+
+def test_cubic_host_path_nan_anywhere_poisons_everything(engine):
+    """scipy's cubic: one NaN anywhere in the array makes the whole result NaN -- also when the NaN sits in a
+    later chunk than the ones already copied out."""
+    lat, lon = np.arange(-60.0, 61.0, 4.0), np.arange(0.0, 100.0, 4.0)
+    tlat, tlon = np.arange(-58.0, 58.0, 1.0), np.arange(2.0, 90.0, 1.0)
+    x = np.random.default_rng(2).random((6, lat.size, lon.size))
+    x[5, 3, 3] = np.nan
+    plan = engine.InterpPlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"), "cubic")
+    got = plan.apply_host(x, chunk_batch=2)
+    assert torch.isnan(got).all()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_reduce_host_paths_match_device_path(engine, pinned):
+    lat, lon = np.arange(-29.95, 30, 0.1), np.arange(0.05, 90, 0.1)
+    tlat, tlon = np.arange(-29.5, 30, 1.0), np.arange(0.5, 90, 1.0)
+    rng = np.random.default_rng(9)
+    lab = rng.integers(0, 12, (3, lat.size, lon.size)).astype(np.uint8)
+    fld = rng.standard_normal((3, lat.size, lon.size)).astype(np.float32)
+    fld[rng.random(fld.shape) < 0.02] = np.nan
+    plan = engine.ReducePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"))
+    wrap = (lambda a: torch.from_numpy(a).pin_memory()) if pinned else (lambda a: a)
+    values = np.arange(12)
+    ref = plan.mode(torch.from_numpy(lab).cuda(), values).cpu()
+    got = plan.mode_host(wrap(lab), values, chunk_batch=2)
+    assert got.dtype == torch.uint8 and torch.equal(got, ref)
+    want = orr.regrid_latlon(lab, lat, lon, tlat, tlon, "most_common", values=values)
+    np.testing.assert_array_equal(got.numpy(), want)
+    for method in ("mean", "var", "median", "max"):
+        ref = plan.stat(torch.from_numpy(fld).cuda(), method, skipna=True).cpu()
+        got = plan.stat_host(wrap(fld), method, skipna=True, chunk_batch=2)
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
+
+
+def test_apply_host_validates_out_host(engine):
+    lat, lon = np.arange(-90.0, 91.0, 1.0), np.arange(0.0, 360.0, 1.0)
+    tlat, tlon = np.arange(-88.0, 89, 4.0), np.arange(0.0, 360, 4.0)
+    plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"))
+    x = torch.rand(4, lat.size, lon.size, dtype=torch.float64).pin_memory()
+    good = (4, tlat.size, tlon.size)
+    with pytest.raises(ValueError, match="dtype"):
+        plan.apply_host(x, out_host=torch.empty(good, dtype=torch.float32))
+    with pytest.raises(ValueError, match="elements"):
+        plan.apply_host(x, out_host=torch.empty((3,) + good[1:], dtype=torch.float64))
+    with pytest.raises(ValueError, match="contiguous"):
+        plan.apply_host(x, out_host=torch.empty(good[::-1], dtype=torch.float64).permute(2, 1, 0))
+    with pytest.raises(ValueError, match="CPU"):
+        plan.apply_host(x, out_host=torch.empty(good, dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError, match="plan was built"):
+        plan.apply_host(torch.rand(2, 10, 10, dtype=torch.float64))
+
+
+def test_deferred_drain_on_a_persistent_pipeline(engine):
+    """Several host calls queued on one pipeline without draining in between, one drain at the end."""
+    lat, lon = np.arange(-90.0, 90.25, 0.5), np.arange(0.0, 360.0, 0.5)
+    tlat, tlon = np.arange(-90.0, 91, 2.0), np.arange(0.0, 360, 2.0)
+    plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"))
+    rng = np.random.default_rng(4)
+    xs = [torch.from_numpy(0.5 + rng.random((7, lat.size, lon.size))).pin_memory() for _ in range(3)]
+    outs = [torch.empty((7, tlat.size, tlon.size), dtype=torch.float64).pin_memory() for _ in range(3)]
+    pipe = engine.HostPipeline(slots=2)
+    for x, o in zip(xs, outs):
+        plan.apply_host(x, out_host=o, chunk_batch=3, pipeline=pipe, drain=False)
+    pipe.drain()
+    for x, o in zip(xs, outs):
+        want = oc.regrid_latlon(x.numpy(), lat, lon, tlat, tlon)
+        _check(o, want, 1e-12)
+    pipe.close()
+
+
+def test_accessor_numpy_route_equals_cuda_route():
+    """The accessor streams numpy input through the host pipeline; same bits as CUDA-tensor input."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xarray_regrid_b200.labelled import DataArray, Dataset
+
+    lat, lon = np.arange(-89.5, 90, 1.0), np.arange(0.5, 360, 1.0)
+    tgt = Dataset({}, {"lat": np.arange(-88.0, 90, 4.0), "lon": np.arange(2.0, 360, 4.0)})
+    rng = np.random.default_rng(8)
+    x = 0.5 + rng.random((9, lat.size, lon.size))
+    x[rng.random(x.shape) < 0.1] = np.nan
+    coords = {"time": np.arange(9), "lat": lat, "lon": lon}
+    host = DataArray(x, ("time", "lat", "lon"), coords)
+    dev = DataArray(torch.from_numpy(x).cuda(), ("time", "lat", "lon"), coords)
+    for call in (lambda d: d.regrid.conservative(tgt, nan_threshold=0.5), lambda d: d.regrid.linear(tgt),
+                 lambda d: d.regrid.cubic(tgt), lambda d: d.regrid.stat(tgt, "mean", skipna=True)):
+        a, b = call(host), call(dev)
+        assert isinstance(a.data, np.ndarray) and b.data.is_cuda
+        np.testing.assert_array_equal(a.data, b.data.cpu().numpy())
+    lab = rng.integers(0, 5, x.shape).astype(np.int32)
+    a = DataArray(lab, ("time", "lat", "lon"), coords).regrid.most_common(tgt, values=np.arange(5))
+    b = DataArray(torch.from_numpy(lab).cuda(), ("time", "lat", "lon"), coords).regrid.most_common(
+        tgt, values=np.arange(5))
+    np.testing.assert_array_equal(a.data, b.data.cpu().numpy())

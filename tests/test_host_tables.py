@@ -315,3 +315,35 @@ def test_band_group_span():
     _, ev3 = tables.cubic_bands(irr, np.linspace(irr.values[0], irr.values[-1], 333))
     want = max(ev3.idx[:, a:a + 4].max() - ev3.idx[:, a:a + 4].min() + 1 for a in range(0, ev3.n_out, 4))
     assert tables.band_group_span(ev3) == want
+
+
+@pytest.mark.parametrize("order", ["ascending", "descending", "shuffled"])
+@pytest.mark.parametrize("lon_mean", [True, False])
+def test_pole_rows_come_from_the_sorted_edge_rows(order, lon_mean):
+    """format_lat pads the poles AFTER sorting (utils.py:277, 313-336): the south pole row is the longitude
+    mean (or, without a lon coordinate, a plain copy) of the SOUTHERNMOST row wherever it sits in the
+    caller's array.  Emulates the kernel's read of the tables in numpy against the oracle."""
+    lat = np.arange(-89.0, 90.0, 2.0)
+    if order == "descending":
+        lat = lat[::-1].copy()
+    elif order == "shuffled":
+        lat = np.random.default_rng(5).permutation(lat)
+    tlat = np.arange(-90.0, 90.5, 1.5)
+    rng = np.random.default_rng(1)
+    x = lat[:, None] + rng.random((lat.size, 12))  # [lat, lon]
+    ax = tables.format_lat_axis(lat, lon_mean=lon_mean)
+    assert ax.pole_src == (int(np.argmin(lat)), int(np.argmax(lat)))
+    assert ax.has_pole_rows == lon_mean
+    band = tables.linear_band(ax, tlat)
+    # what the kernels read: original rows, plus (lon_mean) the two pole rows appended at n_src, n_src + 1
+    rows = x
+    if lon_mean:
+        pole = np.stack([np.broadcast_to(x[ax.pole_src[0]].mean(), (12,)), np.broadcast_to(x[ax.pole_src[1]].mean(), (12,))])
+        rows = np.concatenate([x, pole])
+    got = _apply_band(band, rows.T, n_src=rows.shape[0]).T
+    data, flat, _ = of.format_for_regrid(x, lat, np.arange(12.0) if lon_mean else None, tlat,
+                                         np.arange(12.0) if lon_mean else None)
+    if lon_mean:  # undo the (irrelevant here) longitude formatting: compare on the latitude axis only
+        data, flat = of.format_lat(*of.ensure_monotonic(x, lat, 0), 0, 1)
+    want = oi.regrid(data, [flat], [tlat], [0], "linear")
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)

@@ -12,7 +12,7 @@ from pathlib import Path
 _CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = _CSRC / "libregrid_b200.so"
 
-RG_ABI_VERSION = 2
+RG_ABI_VERSION = 3
 
 
 class RegridB200Error(RuntimeError):
@@ -70,6 +70,7 @@ class rg_bins_t(C.Structure):  # noqa: N801 - mirrors the C name
 
 RG_OK = 0
 RG_ERR_UNSUPPORTED = -4  # include/regrid_b200.h
+RG_HOST_NO_DRAIN = 1
 
 
 def _load():
@@ -89,8 +90,8 @@ def _load():
         "rg_device_sm_count": (C.c_int, []),
         "rg_conservative_f64": (C.c_int, [p, p, i64, i64, i64, i64, band, band, i32, f64, p, ring, p]),
         "rg_conservative_f32": (C.c_int, [p, p, i64, i64, i64, i64, band, band, i32, f32, p, ring, p]),
-        "rg_row_nanmean_f64": (C.c_int, [p, p, i64, i32, i32, i64, i64, p]),
-        "rg_row_nanmean_f32": (C.c_int, [p, p, i64, i32, i32, i64, i64, p]),
+        "rg_row_nanmean_f64": (C.c_int, [p, p, i64, i32, i32, i64, i64, i32, i32, p]),
+        "rg_row_nanmean_f32": (C.c_int, [p, p, i64, i32, i32, i64, i64, i32, i32, p]),
         "rg_separable_f64": (C.c_int, [p, p, i64, i64, i64, i64, band, band, p, ring, p]),
         "rg_separable_f32": (C.c_int, [p, p, i64, i64, i64, i64, band, band, p, ring, p]),
         "rg_nearest": (C.c_int, [p, p, i32, i32, i64, i64, i64, i64, i32, i32, p, p, p, p, f64, p]),
@@ -103,9 +104,25 @@ def _load():
                               i32, i32, i32, f64, p]),
         "rg_stat_f64": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, i32, i32, i32, f64, p]),
         "rg_stat_f32": (C.c_int, [p, p, i64, i64, i64, i64, bins, bins, i32, i32, i32, i32, i32, i32, i32, i32, f64, p]),
-        "rg_conservative_host_workspace": (sz, [i64, i32, i32, i32, i32, i32]),
-        "rg_conservative_host_f64": (C.c_int, [p, p, i64, i64, band, band, i32, f64, i32, ring, p, sz]),
-        "rg_conservative_host_f32": (C.c_int, [p, p, i64, i64, band, band, i32, f32, i32, ring, p, sz]),
+        "rg_conservative_host_workspace": (sz, [i64, i32, i32, i32, i32, i32, i32]),
+        "rg_conservative_host_f64": (C.c_int, [p, p, i64, i64, band, band, i32, f64, i32, i32, i32, ring, p, sz,
+                                               p, i32]),
+        "rg_conservative_host_f32": (C.c_int, [p, p, i64, i64, band, band, i32, f32, i32, i32, i32, ring, p, sz,
+                                               p, i32]),
+        "rg_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p), i32]),
+        "rg_pipeline_destroy": (C.c_int, [p]),
+        "rg_pipeline_slots": (i32, [p]),
+        "rg_pipeline_stream": (C.c_void_p, [p, i32]),
+        "rg_pipeline_h2d": (C.c_int, [p, i32, p, p, sz]),
+        "rg_pipeline_compute_begin": (C.c_int, [p, i32]),
+        "rg_pipeline_compute_end": (C.c_int, [p, i32]),
+        "rg_pipeline_d2h": (C.c_int, [p, i32, p, p, sz]),
+        "rg_pipeline_h2d_pageable": (C.c_int, [p, i32, p, p, sz, p, sz, i32]),
+        "rg_pipeline_d2h_pageable": (C.c_int, [p, i32, p, p, sz, p, sz, i32]),
+        "rg_pipeline_sync": (C.c_int, [p, i32, i32]),
+        "rg_pipeline_wait_stream": (C.c_int, [p, p]),
+        "rg_pipeline_drain": (C.c_int, [p]),
+        "rg_host_copy": (C.c_int, [p, p, sz, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -16,11 +16,19 @@
 
 #include "common.cuh"
 #include "conservative_ring.cuh"
+#include "pipeline.cuh"
 #include "upsample.cuh"
 
 namespace rg {
 
 constexpr int kConsThreads = 256;
+
+// What a NaN in the source does (conservative_launch's nan_mode):
+//   kNanPropagate  poisons every output it touches, weight 0 included (interpolation: scipy's w*y sums)
+//   kNanSkip       apply_weights(skipna=True): fillna(0) + valid-mass normalisation + threshold
+//   kNanZeroFill   apply_weights(skipna=False): the reference contracts da.fillna(0) unconditionally
+//                  (methods/conservative.py:196-198), so a NaN counts as 0 and the result is finite
+constexpr int kNanPropagate = 0, kNanSkip = 1, kNanZeroFill = 2;
 
 // RC = independent row loads in flight per thread (the row taps are walked in chunks of RC; bands with <= 4 row
 // taps use RC = 4: the unrolled, predicated chunk body is half as long).
@@ -28,7 +36,7 @@ template <typename T, bool SKIPNA, int VEC, int RC>
 __global__ void __launch_bounds__(kConsThreads)
 conservative_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch,
                     long long xbs, long long xrs, long long ybs, Band<T> rows, Band<T> cols,
-                    T thr, const T* __restrict__ pole, int w_pad) {
+                    T thr, const T* __restrict__ pole, int w_pad, int zero_fill) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* s_t = reinterpret_cast<T*>(smem_raw);
   T* s_v = s_t + w_pad;  // valid only when SKIPNA
@@ -98,7 +106,9 @@ conservative_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch,
                 acc[e] = fma(w, ok ? xv : T(0), acc[e]);
                 vac[e] += ok ? w : T(0);
               } else {
-                acc[e] = fma(w, xv, acc[e]);
+                // zero_fill: apply_weights(skipna=False) contracts da.fillna(0) (conservative.py:196-198);
+                // otherwise (interpolation callers) a NaN tap poisons the output
+                acc[e] = fma(w, (zero_fill && xv != xv) ? T(0) : xv, acc[e]);
               }
             }
           }
@@ -141,13 +151,13 @@ conservative_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch,
 // ------------------------------------------------------------------ pole rows (format_lat)
 template <typename T>
 __global__ void __launch_bounds__(256)
-row_nanmean_kernel(const T* __restrict__ x, T* __restrict__ pole, long long batch, int H, int W,
-                   long long xbs, long long xrs) {
+row_nanmean_kernel(const T* __restrict__ x, T* __restrict__ pole, long long batch, int W,
+                   long long xbs, long long xrs, int south_row, int north_row) {
   __shared__ double s_sum[8];
   __shared__ long long s_cnt[8];
   const long long b = blockIdx.x >> 1;
   const int which = blockIdx.x & 1;
-  const T* row = x + b * xbs + (which ? static_cast<long long>(H - 1) * xrs : 0);
+  const T* row = x + b * xbs + static_cast<long long>(which ? north_row : south_row) * xrs;
   double sum = 0.0;
   long long n = 0;
   for (int j = threadIdx.x; j < W; j += 256) {
@@ -173,22 +183,26 @@ row_nanmean_kernel(const T* __restrict__ x, T* __restrict__ pole, long long batc
 
 template <typename T>
 int row_nanmean_launch(const T* x, T* pole, int64_t batch, int32_t H, int32_t W, int64_t xbs,
-                       int64_t xrs, cudaStream_t stream) {
+                       int64_t xrs, int32_t south_row, int32_t north_row, cudaStream_t stream) {
   if (!x || !pole) return RG_ERR_NULL;
   if (batch < 0 || H <= 0 || W <= 0 || xrs < W) return RG_ERR_SHAPE;
+  if (south_row < 0 || south_row >= H || north_row < 0 || north_row >= H) return RG_ERR_SHAPE;
   if (batch == 0) return RG_OK;
   if (batch * 2 > 0x7fffffffLL) return RG_ERR_SHAPE;
-  row_nanmean_kernel<T><<<static_cast<unsigned>(batch * 2), 256, 0, stream>>>(x, pole, batch, H, W,
-                                                                              xbs, xrs);
+  row_nanmean_kernel<T><<<static_cast<unsigned>(batch * 2), 256, 0, stream>>>(x, pole, batch, W, xbs, xrs,
+                                                                              south_row, north_row);
   return static_cast<int>(cudaGetLastError());
 }
 
 // --------------------------------------------------------------------------- launcher
 template <typename T>
 int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
-                        const rg_band_t* rows_c, const rg_band_t* cols_c, int32_t skipna, T thr,
+                        const rg_band_t* rows_c, const rg_band_t* cols_c, int32_t nan_mode, T thr,
                         const T* pole, const rg_row_ring_t* ring_c, cudaStream_t stream) {
   if (!x || !y) return RG_ERR_NULL;
+  if (nan_mode < kNanPropagate || nan_mode > kNanZeroFill) return RG_ERR_UNSUPPORTED;
+  const int32_t skipna = nan_mode == kNanSkip;
+  const int zero_fill = nan_mode == kNanZeroFill;
   Band<T> rows, cols;
   int rc = make_band<T>(rows_c, &rows);
   if (rc != RG_OK) return rc;
@@ -212,7 +226,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   if (rc != RG_OK) return rc;
 
   // ---- interpolation onto a much finer grid (write-bound): shared-memory upsampling kernel
-  if (!skipna && !pole) {
+  if (nan_mode == kNanPropagate && !pole) {
     rc = upsample_try_launch<T>(x, y, batch, xbs, xrs, ybs, rows, cols, dev, stream);
     if (rc != RG_ERR_UNSUPPORTED) return rc;
   }
@@ -261,7 +275,8 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
                    ring_c->n_warps,
                    ring_c->lane_cols,
                    pole,
-                   rows.n_src};
+                   rows.n_src,
+                   zero_fill};
       using RingKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev,
                                   T, int, int);
       const int warps = ring.n_warps + 2;  // + producer + sync
@@ -300,7 +315,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_SMEM;
 
   using Kernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>,
-                          Band<T>, T, const T*, int);
+                          Band<T>, T, const T*, int, int);
   Kernel kern;
   const bool few = rows.k_max <= 4;
   if (aligned) {
@@ -321,103 +336,68 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   long long grid = static_cast<long long>(dev.sm_count) * per_sm;
   if (grid > tasks) grid = tasks;
   kern<<<static_cast<unsigned>(grid), kConsThreads, smem, stream>>>(x, y, batch, xbs, xrs, ybs, rows,
-                                                                   cols, thr, pole, w_pad);
+                                                                   cols, thr, pole, w_pad, zero_fill);
   return static_cast<int>(cudaGetLastError());
 }
 
 // ------------------------------------------------------ host-buffer streaming pipeline
-constexpr int kSlots = 3;
-
 inline size_t round256(size_t n) { return (n + 255) / 256 * 256; }
 
-struct PipelineResources {
-  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-  cudaEvent_t in_done[kSlots] = {}, k_done[kSlots] = {}, out_done[kSlots] = {};
-  int create() {
-    RG_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    RG_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-    RG_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < kSlots; ++i) {
-      RG_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
-      RG_CUDA(cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
-      RG_CUDA(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
-    }
-    return RG_OK;
-  }
-  ~PipelineResources() {
-    for (int i = 0; i < kSlots; ++i) {
-      if (in_done[i]) cudaEventDestroy(in_done[i]);
-      if (k_done[i]) cudaEventDestroy(k_done[i]);
-      if (out_done[i]) cudaEventDestroy(out_done[i]);
-    }
-    if (s_in) cudaStreamDestroy(s_in);
-    if (s_k) cudaStreamDestroy(s_k);
-    if (s_out) cudaStreamDestroy(s_out);
-  }
-};
-
+// Chunked H2D -> (pole rows) -> kernel -> D2H over the three streams of an rg_pipeline.  `pipe` may be a
+// caller-owned persistent pipeline (streams / events created once, the caller may defer the final drain with
+// RG_HOST_NO_DRAIN) or NULL (a temporary one is created and destroyed by the call).
 template <typename T>
 int conservative_host(const T* xh, T* yh, int64_t batch, int64_t chunk, const rg_band_t* rows,
-                      const rg_band_t* cols, int32_t skipna, T thr, int32_t pole_rows,
-                      const rg_row_ring_t* ring, void* ws, size_t ws_bytes) {
+                      const rg_band_t* cols, int32_t skipna, T thr, int32_t pole_rows, int32_t south_row,
+                      int32_t north_row, const rg_row_ring_t* ring, void* ws, size_t ws_bytes,
+                      rg_pipeline* pipe, int32_t flags) {
   if (!xh || !yh || !ws || !rows || !cols) return RG_ERR_NULL;
   if (batch < 0 || chunk <= 0) return RG_ERR_SHAPE;
   if (batch == 0) return RG_OK;
+  rg_pipeline local;
+  if (!pipe) {
+    const int rc = local.create(3);
+    if (rc != RG_OK) { local.destroy(); return rc; }
+    pipe = &local;
+  }
+  const int n_slots = pipe->n_slots;
   const int64_t H = rows->n_src, W = cols->n_src, Ho = rows->n_out, Wo = cols->n_out;
   const size_t in_b = round256(static_cast<size_t>(chunk) * H * W * sizeof(T));
   const size_t out_b = round256(static_cast<size_t>(chunk) * Ho * Wo * sizeof(T));
   const size_t pole_b = round256(static_cast<size_t>(chunk) * 2 * W * sizeof(T));
-  if (ws_bytes < kSlots * (in_b + out_b + pole_b)) return RG_ERR_SHAPE;
-  if (reinterpret_cast<uintptr_t>(ws) % 256 != 0) return RG_ERR_ALIGN;
-
-  PipelineResources res;
-  int rc = res.create();
-  if (rc != RG_OK) return rc;
+  int rc = RG_OK;
+  if (ws_bytes < n_slots * (in_b + out_b + pole_b)) rc = RG_ERR_SHAPE;
+  else if (reinterpret_cast<uintptr_t>(ws) % 256 != 0) rc = RG_ERR_ALIGN;
 
   unsigned char* base = static_cast<unsigned char*>(ws);
-  T* d_in[kSlots];
-  T* d_out[kSlots];
-  T* d_pole[kSlots];
-  for (int s = 0; s < kSlots; ++s) {
-    d_in[s] = reinterpret_cast<T*>(base + s * (in_b + out_b + pole_b));
-    d_out[s] = reinterpret_cast<T*>(base + s * (in_b + out_b + pole_b) + in_b);
-    d_pole[s] = reinterpret_cast<T*>(base + s * (in_b + out_b + pole_b) + in_b + out_b);
-  }
-
   const int64_t n_chunks = (batch + chunk - 1) / chunk;
-  for (int64_t i = 0; i < n_chunks; ++i) {
-    const int s = static_cast<int>(i % kSlots);
+  for (int64_t i = 0; i < n_chunks && rc == RG_OK; ++i) {
+    const int s = static_cast<int>(i % n_slots);
+    T* d_in = reinterpret_cast<T*>(base + s * (in_b + out_b + pole_b));
+    T* d_out = reinterpret_cast<T*>(base + s * (in_b + out_b + pole_b) + in_b);
+    T* d_pole = reinterpret_cast<T*>(base + s * (in_b + out_b + pole_b) + in_b + out_b);
     const int64_t b0 = i * chunk;
     const int64_t nb = (batch - b0 < chunk) ? batch - b0 : chunk;
-    // the input slot is free once the kernel that consumed its previous content is done
-    if (i >= kSlots) RG_CUDA(cudaStreamWaitEvent(res.s_in, res.k_done[s], 0));
-    RG_CUDA(cudaMemcpyAsync(d_in[s], xh + b0 * H * W, static_cast<size_t>(nb) * H * W * sizeof(T),
-                            cudaMemcpyHostToDevice, res.s_in));
-    RG_CUDA(cudaEventRecord(res.in_done[s], res.s_in));
-
-    RG_CUDA(cudaStreamWaitEvent(res.s_k, res.in_done[s], 0));
-    // the output slot is free once its previous content has reached the host
-    if (i >= kSlots) RG_CUDA(cudaStreamWaitEvent(res.s_k, res.out_done[s], 0));
-    if (pole_rows) {
-      rc = row_nanmean_launch<T>(d_in[s], d_pole[s], nb, static_cast<int32_t>(H),
-                                 static_cast<int32_t>(W), H * W, W, res.s_k);
-      if (rc != RG_OK) return rc;
-    }
-    rc = conservative_launch<T>(d_in[s], d_out[s], nb, H * W, W, Ho * Wo, rows, cols, skipna, thr,
-                                pole_rows ? d_pole[s] : nullptr, ring, res.s_k);
-    if (rc != RG_OK) return rc;
-    RG_CUDA(cudaEventRecord(res.k_done[s], res.s_k));
-
-    RG_CUDA(cudaStreamWaitEvent(res.s_out, res.k_done[s], 0));
-    RG_CUDA(cudaMemcpyAsync(yh + b0 * Ho * Wo, d_out[s],
-                            static_cast<size_t>(nb) * Ho * Wo * sizeof(T), cudaMemcpyDeviceToHost,
-                            res.s_out));
-    RG_CUDA(cudaEventRecord(res.out_done[s], res.s_out));
+    // ONE copy per chunk and direction (never the batched-copy entry points)
+    rc = pipe->h2d(s, d_in, xh + b0 * H * W, static_cast<size_t>(nb) * H * W * sizeof(T));
+    if (rc == RG_OK) rc = pipe->compute_begin(s);
+    if (rc == RG_OK && pole_rows)
+      rc = row_nanmean_launch<T>(d_in, d_pole, nb, static_cast<int32_t>(H), static_cast<int32_t>(W), H * W, W,
+                                 south_row, north_row, pipe->s_k);
+    if (rc == RG_OK)
+      rc = conservative_launch<T>(d_in, d_out, nb, H * W, W, Ho * Wo, rows, cols,
+                                  skipna ? kNanSkip : kNanZeroFill, thr, pole_rows ? d_pole : nullptr, ring,
+                                  pipe->s_k);
+    if (rc == RG_OK) rc = pipe->compute_end(s);
+    if (rc == RG_OK) rc = pipe->d2h(s, yh + b0 * Ho * Wo, d_out, static_cast<size_t>(nb) * Ho * Wo * sizeof(T));
   }
-  RG_CUDA(cudaStreamSynchronize(res.s_out));
-  RG_CUDA(cudaStreamSynchronize(res.s_k));
-  RG_CUDA(cudaStreamSynchronize(res.s_in));
-  return RG_OK;
+  // after an error nothing may stay in flight into the caller's buffers
+  if (rc != RG_OK || pipe == &local || !(flags & RG_HOST_NO_DRAIN)) {
+    const int rd = pipe->drain();
+    if (rc == RG_OK) rc = rd;
+  }
+  if (pipe == &local) local.destroy();
+  return rc;
 }
 
 }  // namespace rg
@@ -428,66 +408,72 @@ extern "C" {
 int rg_conservative_f64(const double* x, double* y, int64_t batch, int64_t xbs, int64_t xrs,
                         int64_t ybs, const rg_band_t* rows, const rg_band_t* cols, int32_t skipna,
                         double valid_thr, const double* pole, const rg_row_ring_t* ring, void* stream) {
-  return rg::conservative_launch<double>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna, valid_thr,
-                                         pole, ring, static_cast<cudaStream_t>(stream));
+  return rg::conservative_launch<double>(x, y, batch, xbs, xrs, ybs, rows, cols,
+                                         skipna ? rg::kNanSkip : rg::kNanZeroFill, valid_thr, pole, ring,
+                                         static_cast<cudaStream_t>(stream));
 }
 
 int rg_conservative_f32(const float* x, float* y, int64_t batch, int64_t xbs, int64_t xrs,
                         int64_t ybs, const rg_band_t* rows, const rg_band_t* cols, int32_t skipna,
                         float valid_thr, const float* pole, const rg_row_ring_t* ring, void* stream) {
-  return rg::conservative_launch<float>(x, y, batch, xbs, xrs, ybs, rows, cols, skipna, valid_thr,
-                                        pole, ring, static_cast<cudaStream_t>(stream));
+  return rg::conservative_launch<float>(x, y, batch, xbs, xrs, ybs, rows, cols,
+                                        skipna ? rg::kNanSkip : rg::kNanZeroFill, valid_thr, pole, ring,
+                                        static_cast<cudaStream_t>(stream));
 }
 
 int rg_row_nanmean_f64(const double* x, double* pole, int64_t batch, int32_t H, int32_t W,
-                       int64_t xbs, int64_t xrs, void* stream) {
-  return rg::row_nanmean_launch<double>(x, pole, batch, H, W, xbs, xrs,
+                       int64_t xbs, int64_t xrs, int32_t south_row, int32_t north_row, void* stream) {
+  return rg::row_nanmean_launch<double>(x, pole, batch, H, W, xbs, xrs, south_row, north_row,
                                         static_cast<cudaStream_t>(stream));
 }
 
 int rg_row_nanmean_f32(const float* x, float* pole, int64_t batch, int32_t H, int32_t W,
-                       int64_t xbs, int64_t xrs, void* stream) {
-  return rg::row_nanmean_launch<float>(x, pole, batch, H, W, xbs, xrs,
+                       int64_t xbs, int64_t xrs, int32_t south_row, int32_t north_row, void* stream) {
+  return rg::row_nanmean_launch<float>(x, pole, batch, H, W, xbs, xrs, south_row, north_row,
                                        static_cast<cudaStream_t>(stream));
 }
 
 int rg_separable_f64(const double* x, double* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
                      const rg_band_t* rows, const rg_band_t* cols, const double* pole,
                      const rg_row_ring_t* ring, void* stream) {
-  return rg::conservative_launch<double>(x, y, batch, xbs, xrs, ybs, rows, cols, 0, 0.0, pole, ring,
-                                         static_cast<cudaStream_t>(stream));
+  return rg::conservative_launch<double>(x, y, batch, xbs, xrs, ybs, rows, cols, rg::kNanPropagate, 0.0,
+                                         pole, ring, static_cast<cudaStream_t>(stream));
 }
 
 int rg_separable_f32(const float* x, float* y, int64_t batch, int64_t xbs, int64_t xrs, int64_t ybs,
                      const rg_band_t* rows, const rg_band_t* cols, const float* pole,
                      const rg_row_ring_t* ring, void* stream) {
-  return rg::conservative_launch<float>(x, y, batch, xbs, xrs, ybs, rows, cols, 0, 0.0f, pole, ring,
-                                        static_cast<cudaStream_t>(stream));
+  return rg::conservative_launch<float>(x, y, batch, xbs, xrs, ybs, rows, cols, rg::kNanPropagate, 0.0f,
+                                        pole, ring, static_cast<cudaStream_t>(stream));
 }
 
 size_t rg_conservative_host_workspace(int64_t chunk_batch, int32_t H, int32_t W, int32_t Ho,
-                                      int32_t Wo, int32_t elem_size) {
-  if (chunk_batch <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || elem_size <= 0) return 0;
+                                      int32_t Wo, int32_t elem_size, int32_t n_slots) {
+  if (chunk_batch <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || elem_size <= 0 || n_slots <= 0) return 0;
   const size_t in_b = rg::round256(static_cast<size_t>(chunk_batch) * H * W * elem_size);
   const size_t out_b = rg::round256(static_cast<size_t>(chunk_batch) * Ho * Wo * elem_size);
   const size_t pole_b = rg::round256(static_cast<size_t>(chunk_batch) * 2 * W * elem_size);
-  return rg::kSlots * (in_b + out_b + pole_b);
+  return static_cast<size_t>(n_slots) * (in_b + out_b + pole_b);
 }
 
 int rg_conservative_host_f64(const double* x_host, double* y_host, int64_t batch,
                              int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
-                             int32_t skipna, double valid_thr, int32_t pole_rows,
-                             const rg_row_ring_t* ring, void* workspace, size_t workspace_bytes) {
+                             int32_t skipna, double valid_thr, int32_t pole_rows, int32_t south_row,
+                             int32_t north_row, const rg_row_ring_t* ring, void* workspace,
+                             size_t workspace_bytes, rg_pipeline_t* pipeline, int32_t flags) {
   return rg::conservative_host<double>(x_host, y_host, batch, chunk_batch, rows, cols, skipna,
-                                       valid_thr, pole_rows, ring, workspace, workspace_bytes);
+                                       valid_thr, pole_rows, south_row, north_row, ring, workspace,
+                                       workspace_bytes, pipeline, flags);
 }
 
 int rg_conservative_host_f32(const float* x_host, float* y_host, int64_t batch,
                              int64_t chunk_batch, const rg_band_t* rows, const rg_band_t* cols,
-                             int32_t skipna, float valid_thr, int32_t pole_rows,
-                             const rg_row_ring_t* ring, void* workspace, size_t workspace_bytes) {
+                             int32_t skipna, float valid_thr, int32_t pole_rows, int32_t south_row,
+                             int32_t north_row, const rg_row_ring_t* ring, void* workspace,
+                             size_t workspace_bytes, rg_pipeline_t* pipeline, int32_t flags) {
   return rg::conservative_host<float>(x_host, y_host, batch, chunk_batch, rows, cols, skipna,
-                                      valid_thr, pole_rows, ring, workspace, workspace_bytes);
+                                      valid_thr, pole_rows, south_row, north_row, ring, workspace,
+                                      workspace_bytes, pipeline, flags);
 }
 
 }  // extern "C"

@@ -36,6 +36,7 @@ struct RingDev {
   int n_runs, n_sched, max_live, pad_shift, n_strips, strip_cols_max, n_warps, lane_cols;
   const void* __restrict__ pole;  // [batch, 2, W] synthetic pole rows (scheduled as rows n_src_rows, + 1) or NULL
   int n_src_rows;
+  int zero_fill;  // !SKIPNA kernels: a NaN tap counts as 0 (apply_weights with skipna=False) instead of poisoning
 };
 
 constexpr int kRingMaxSlots = 32;  // ring depth cap (a tap reaches at most 15 rows back: 4-bit tap_back)
@@ -158,7 +159,7 @@ template <typename T, bool SKIPNA, int CNT>
 __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row_stride, int ring_slots,
                                             int newest, uint32_t back, const T* __restrict__ wk,
                                             TV<T, SKIPNA>* s_tv, int W, int col0, int ncols, int pad_shift,
-                                            int lane) {
+                                            int lane, int zero_fill) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int N = CNT > 0 ? CNT : 1;
   const unsigned char* rowp[N];
@@ -200,9 +201,9 @@ __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row
 #pragma unroll
       for (int i = 0; i < CNT; ++i) acc[e] = fma(w[i], val[i].v[e], acc[e]);
       vac[e] = wsum;
-      if (SKIPNA) redo |= (acc[e] != acc[e]);
+      if (SKIPNA || zero_fill) redo |= (acc[e] != acc[e]);
     }
-    if (SKIPNA && redo) {
+    if (redo) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) { acc[e] = T(0); vac[e] = T(0); }
 #pragma unroll
@@ -386,13 +387,13 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
 #define RG_P1(C)                                                                                          \
   case C:                                                                                                 \
     ring_phase1<T, SKIPNA, C>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk,   \
-                              s_tv, W, col0, ncols, pad_shift, lane);                                     \
+                              s_tv, W, col0, ncols, pad_shift, lane, ring.zero_fill);                     \
     break;
         switch (cnt) {
           RG_P1(0) RG_P1(1) RG_P1(2) RG_P1(3) RG_P1(4) RG_P1(5) RG_P1(6) RG_P1(7)
           default:
             ring_phase1<T, SKIPNA, 8>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
-                                      wk, s_tv, W, col0, ncols, pad_shift, lane);
+                                      wk, s_tv, W, col0, ncols, pad_shift, lane, ring.zero_fill);
             break;
         }
 #undef RG_P1
@@ -453,7 +454,7 @@ __device__ __forceinline__ Pair2<float> lds_pair(uint32_t addr, float) {
 template <typename T, bool SKIPNA, int CNT>
 __device__ __forceinline__ void lane_phase1(uint32_t ring0, int row_stride, int ring_slots, int newest,
                                             uint32_t back, uint32_t wk_addr, uint32_t offA, uint32_t offB,
-                                            T (&t)[4], T (&v)[4]) {
+                                            T (&t)[4], T (&v)[4], int zero_fill) {
   constexpr int N = CNT > 0 ? CNT : 1;
   T w[N];
 #pragma unroll
@@ -484,7 +485,7 @@ __device__ __forceinline__ void lane_phase1(uint32_t ring0, int row_stride, int 
     t[2] = fma(w[i], xb[i].a, t[2]);
     t[3] = fma(w[i], xb[i].b, t[3]);
   }
-  if constexpr (SKIPNA) {
+  if (SKIPNA || zero_fill) {
     const bool redo = (t[0] != t[0]) | (t[1] != t[1]) | (t[2] != t[2]) | (t[3] != t[3]);
     if (redo) {
 #pragma unroll
@@ -591,13 +592,13 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
 #define RG_L1(C)                                                                                              \
   case C:                                                                                                     \
     lane_phase1<T, SKIPNA, C>(ring0, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk, offA, \
-                              offB, t, v);                                                                    \
+                              offB, t, v, ring.zero_fill);                                                    \
     break;
       switch (cnt) {
         RG_L1(0) RG_L1(1) RG_L1(2) RG_L1(3) RG_L1(4) RG_L1(5) RG_L1(6) RG_L1(7)
         default:
           lane_phase1<T, SKIPNA, 8>(ring0, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk,
-                                    offA, offB, t, v);
+                                    offA, offB, t, v, ring.zero_fill);
           break;
       }
 #undef RG_L1

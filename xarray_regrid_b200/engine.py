@@ -92,6 +92,191 @@ class DeviceRing:
         return C.byref(self.c)
 
 
+# ------------------------------------------------------------------ host <-> device streaming
+class HostPipeline:
+    """A persistent ``rg_pipeline_t`` (three streams + per-slot events, created once) with the per-slot device
+    buffers and page-locked staging buffers that the host-buffer paths of the plans reuse from call to call.
+
+    It stands in for the reference's dask chunk scheduling (methods/conservative.py:263-302): a stack that
+    lives in host memory is cut into chunks along the flattened batch dimension; chunk ``i`` uses slot
+    ``i % slots``, so the H2D copy of chunk ``i + 1``, the kernels of chunk ``i`` and the D2H copy of chunk
+    ``i - 1`` overlap.  Page-locked sources / results are copied directly (one ``cudaMemcpyAsync`` per chunk
+    and direction); pageable ones (numpy arrays) go through page-locked staging chunks filled / emptied by
+    the library's multi-threaded ``rg_host_copy``.
+    """
+
+    def __init__(self, device=None, slots: int = 3, copy_threads: int | None = None):
+        self.device = _require_cuda(device)
+        self.slots = int(slots)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.rg_pipeline_create(C.byref(handle), self.slots), "rg_pipeline_create")
+        self.handle = handle
+        import os
+
+        self.copy_threads = int(copy_threads or max(1, min(16, (os.cpu_count() or 2) // 2)))
+        self.stage_bytes = 4 * (32 << 20)  # staging ring per direction: 4 pieces of 32 MiB
+        self._dev: dict = {}     # name -> per-slot device buffers (uint8)
+        self._pinned: dict = {}  # direction -> page-locked staging ring (uint8)
+        self.compute_stream = torch.cuda.ExternalStream(lib.rg_pipeline_stream(handle, 1), device=self.device)
+
+    # -- buffers (grown on demand, reused afterwards)
+    def device_buffers(self, name: str, nbytes: int, count: int | None = None):
+        """Per-slot device buffers of at least ``nbytes`` (only the first ``count`` slots are needed)."""
+        count = self.slots if count is None else max(1, min(count, self.slots))
+        cur = self._dev.get(name)
+        if cur is None or len(cur) < count or cur[0].numel() < nbytes:
+            size = max(nbytes, 1 if cur is None else cur[0].numel())
+            n = count if cur is None else max(count, len(cur))
+            self._dev.pop(name, None)
+            cur = [torch.empty(size, dtype=torch.uint8, device=self.device) for _ in range(n)]
+            self._dev[name] = cur
+        return cur
+
+    def device_block(self, name: str, nbytes: int) -> torch.Tensor:
+        """One device buffer (not per slot), grown on demand."""
+        cur = self._dev.get(("block", name))
+        if cur is None or cur.numel() < nbytes:
+            self._dev.pop(("block", name), None)
+            cur = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+            self._dev[("block", name)] = cur
+        return cur
+
+    def staging(self, name: str) -> torch.Tensor:
+        """Page-locked staging ring of one direction (4 pieces, see rg_pipeline_h2d_pageable)."""
+        if name not in self._pinned:
+            self._pinned[name] = torch.empty(self.stage_bytes, dtype=torch.uint8, pin_memory=True)
+        return self._pinned[name]
+
+    def wait_current_stream(self):
+        """Order the pipeline after the work queued so far on torch's current stream."""
+        check(lib.rg_pipeline_wait_stream(self.handle, _stream_ptr(self.device)), "rg_pipeline_wait_stream")
+
+    def drain(self):
+        check(lib.rg_pipeline_drain(self.handle), "rg_pipeline_drain")
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            lib.rg_pipeline_destroy(self.handle)
+            self.handle = C.c_void_p()
+        self._dev.clear()
+        self._pinned.clear()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # -- the chunk loop shared by every host-buffer path
+    def stream(self, x_host: torch.Tensor, out_host: torch.Tensor, chunk: int, compute, drain: bool = True):
+        """``x_host`` ``[B, ...]`` and ``out_host`` ``[B, ...]`` are contiguous CPU tensors; for every chunk of
+        ``chunk`` leading items ``compute(x_dev, y_dev)`` is called on the pipeline's compute stream with the
+        slot's device views and must queue kernels that fill ``y_dev``.
+
+        Page-locked tensors are copied directly, one ``cudaMemcpyAsync`` per chunk; pageable ones pass through
+        the staging rings.  A pageable result makes the host wait for chunk ``i - 1`` AFTER chunk ``i`` has been
+        queued, so the device never idles on the host's copy-out."""
+        B = x_host.shape[0]
+        if B == 0:
+            return out_host
+        chunk = int(max(1, min(chunk, B)))
+        n_chunks = -(-B // chunk)
+        in_item = x_host[0].numel() * x_host.element_size()
+        out_item = out_host[0].numel() * out_host.element_size()
+        d_in = self.device_buffers("in", chunk * in_item, n_chunks)
+        d_out = self.device_buffers("out", chunk * out_item, n_chunks)
+        stage_in = None if x_host.is_pinned() else self.staging("in")
+        stage_out = None if out_host.is_pinned() else self.staging("out")
+        h = self.handle
+        nt = self.copy_threads
+
+        def copy_out(slot, b0, nb):
+            dst = out_host[b0:b0 + nb]
+            if stage_out is None:
+                check(lib.rg_pipeline_d2h(h, slot, dst.data_ptr(), d_out[slot].data_ptr(), nb * out_item),
+                      "rg_pipeline_d2h")
+            else:
+                check(lib.rg_pipeline_d2h_pageable(h, slot, dst.data_ptr(), d_out[slot].data_ptr(), nb * out_item,
+                                                   stage_out.data_ptr(), stage_out.numel(), nt),
+                      "rg_pipeline_d2h_pageable")
+
+        with torch.cuda.device(self.device):
+            self.wait_current_stream()
+            try:
+                previous = None
+                for i, b0 in enumerate(range(0, B, chunk)):
+                    s = i % self.slots
+                    nb = min(chunk, B - b0)
+                    src = x_host[b0:b0 + nb]
+                    if stage_in is None:
+                        check(lib.rg_pipeline_h2d(h, s, d_in[s].data_ptr(), src.data_ptr(), nb * in_item),
+                              "rg_pipeline_h2d")
+                    else:
+                        check(lib.rg_pipeline_h2d_pageable(h, s, d_in[s].data_ptr(), src.data_ptr(), nb * in_item,
+                                                           stage_in.data_ptr(), stage_in.numel(), nt),
+                              "rg_pipeline_h2d_pageable")
+                    check(lib.rg_pipeline_compute_begin(h, s), "rg_pipeline_compute_begin")
+                    x_dev = d_in[s][:nb * in_item].view(x_host.dtype).view((nb,) + tuple(x_host.shape[1:]))
+                    y_dev = d_out[s][:nb * out_item].view(out_host.dtype).view((nb,) + tuple(out_host.shape[1:]))
+                    with torch.cuda.stream(self.compute_stream):
+                        compute(x_dev, y_dev)
+                    check(lib.rg_pipeline_compute_end(h, s), "rg_pipeline_compute_end")
+                    if stage_out is None:
+                        copy_out(s, b0, nb)
+                    else:
+                        if previous is not None:
+                            copy_out(*previous)
+                        previous = (s, b0, nb)
+                if previous is not None:
+                    copy_out(*previous)
+            except BaseException:
+                lib.rg_pipeline_drain(h)  # nothing may stay in flight into the caller's buffers
+                raise
+            if drain:
+                self.drain()
+        return out_host
+
+
+_PIPELINES: dict = {}
+
+
+def default_pipeline(device) -> HostPipeline:
+    """One shared pipeline per device for callers that do not manage their own."""
+    device = _require_cuda(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _PIPELINES:
+        _PIPELINES[key] = HostPipeline(device)
+    return _PIPELINES[key]
+
+
+def _host_tensor(x) -> torch.Tensor:
+    """numpy array / CPU tensor -> contiguous CPU tensor sharing memory where possible."""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            raise ValueError("host path takes host arrays; call the plan directly for CUDA tensors")
+        return x if x.is_contiguous() else x.contiguous()
+    arr = np.asarray(x)
+    if arr.dtype.byteorder not in ("=", "|"):
+        arr = arr.astype(arr.dtype.newbyteorder("="))
+    return torch.from_numpy(np.ascontiguousarray(arr))
+
+
+def _check_out_host(out_host: torch.Tensor, shape: tuple, dtype: torch.dtype) -> torch.Tensor:
+    if not isinstance(out_host, torch.Tensor) or out_host.is_cuda:
+        raise ValueError("out_host must be a CPU tensor")
+    if out_host.dtype != dtype:
+        raise ValueError(f"out_host has dtype {out_host.dtype}, the result is {dtype}")
+    if not out_host.is_contiguous():
+        raise ValueError("out_host must be contiguous")
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if out_host.numel() != n:
+        raise ValueError(f"out_host has {out_host.numel()} elements, the result has {n} ({tuple(shape)})")
+    return out_host.view(shape)
+
+
 @dataclass
 class AxisSpec:
     """One regridded axis: source / target coordinate values and how the reference would
@@ -124,12 +309,18 @@ def _as_batch(x: torch.Tensor, dtype: torch.dtype):
     return x3, lead
 
 
+# What a NaN in the source does in ``BandOp.run``:
+NAN_PROPAGATE = 0  # poisons every output it touches (interpolation; rg_separable_*)
+NAN_SKIP = 1       # apply_weights(skipna=True): valid-mass normalisation + threshold
+NAN_ZERO = 2       # apply_weights(skipna=False): the reference contracts da.fillna(0) (conservative.py:196-198)
+
+
 class BandOp:
     """Two per-axis bands resident on the device + the launch of the separable band kernels.
 
     ``run`` computes ``y[b,k,l] = sum_t sum_c wr[t,k] wc[c,l] x[b, ri[t,k], ci[c,l]]`` with the
-    conservative NaN bookkeeping (``skipna``) or plain NaN propagation; it is the common back end of the
-    conservative, linear and cubic regridders.
+    conservative NaN bookkeeping (``NAN_SKIP`` / ``NAN_ZERO``) or plain NaN propagation
+    (``NAN_PROPAGATE``); it is the common back end of the conservative, linear and cubic regridders.
     """
 
     def __init__(self, rows_band: tables.Band | None, cols_band: tables.Band | None, device):
@@ -138,6 +329,8 @@ class BandOp:
         self.pole_rows = rows_band is not None and bool(rows_band.meta.get("pole_rows")) and bool(
             (rows_band.idx >= rows_band.n_src).any()
         )
+        # original rows whose longitude-mean fills the south / north pole row (sorted-first / sorted-last)
+        self.pole_src = (0, 0) if rows_band is None else tuple(rows_band.meta.get("pole_src", (0, 0)))
         self._dev: dict = {}
         self._rings: dict = {}
         self.use_ring = True  # tests flip this to exercise the generic kernel
@@ -175,8 +368,10 @@ class BandOp:
         return (n_rows if self.rows_band is None else self.rows_band.n_out,
                 n_cols if self.cols_band is None else self.cols_band.n_out)
 
-    def run(self, x3: torch.Tensor, skipna: bool, thr: float, out: torch.Tensor | None = None) -> torch.Tensor:
-        """``x3``: CUDA ``[B, H, W]`` float32/float64 with unit column stride -> ``[B, Ho, Wo]``."""
+    def run(self, x3: torch.Tensor, nan_mode: int, thr: float, out: torch.Tensor | None = None,
+            pole: torch.Tensor | None = None) -> torch.Tensor:
+        """``x3``: CUDA ``[B, H, W]`` float32/float64 with unit column stride -> ``[B, Ho, Wo]``.
+        ``pole``: optional caller-owned ``[B, 2, W]`` scratch for the synthetic pole rows."""
         dtype = x3.dtype
         B, H, W = x3.shape
         rows, cols = self._bands(dtype, H, W)
@@ -194,30 +389,38 @@ class BandOp:
         if B == 0:
             return y
         stream = _stream_ptr(x3.device)
-        pole = None
-        if self.pole_rows:
-            pole = torch.empty((B, 2, W), dtype=dtype, device=x3.device)  # full rows: rg_row_nanmean_*
+        if not self.pole_rows:
+            pole = None
+        else:
+            if pole is None:
+                pole = torch.empty((B, 2, W), dtype=dtype, device=x3.device)  # full rows: rg_row_nanmean_*
             fn = lib.rg_row_nanmean_f64 if dtype == torch.float64 else lib.rg_row_nanmean_f32
-            check(fn(x3.data_ptr(), pole.data_ptr(), B, H, W, x3.stride(0), x3.stride(1), stream),
-                  "rg_row_nanmean")
-        fn = lib.rg_conservative_f64 if dtype == torch.float64 else lib.rg_conservative_f32
+            check(fn(x3.data_ptr(), pole.data_ptr(), B, H, W, x3.stride(0), x3.stride(1),
+                     int(self.pole_src[0]), int(self.pole_src[1]), stream), "rg_row_nanmean")
         ring = self._ring(B, H, W, dtype)
-        check(
-            fn(x3.data_ptr(), y.data_ptr(), B, x3.stride(0) if B > 1 else H * x3.stride(1),
-               x3.stride(1), Ho * Wo, rows.ref, cols.ref, int(bool(skipna)), thr,
-               None if pole is None else pole.data_ptr(), None if ring is None else ring.ref, stream),
-            "rg_conservative",
-        )
+        xbs = x3.stride(0) if B > 1 else H * x3.stride(1)
+        pole_ptr = None if pole is None else pole.data_ptr()
+        ring_ref = None if ring is None else ring.ref
+        if nan_mode == NAN_PROPAGATE:
+            fn = lib.rg_separable_f64 if dtype == torch.float64 else lib.rg_separable_f32
+            check(fn(x3.data_ptr(), y.data_ptr(), B, xbs, x3.stride(1), Ho * Wo, rows.ref, cols.ref,
+                     pole_ptr, ring_ref, stream), "rg_separable")
+        else:
+            fn = lib.rg_conservative_f64 if dtype == torch.float64 else lib.rg_conservative_f32
+            check(fn(x3.data_ptr(), y.data_ptr(), B, xbs, x3.stride(1), Ho * Wo, rows.ref, cols.ref,
+                     int(nan_mode == NAN_SKIP), thr, pole_ptr, ring_ref, stream), "rg_conservative")
         return y
 
 
-def _axis(spec: AxisSpec | None, is_rows: bool):
+def _axis(spec: AxisSpec | None, is_rows: bool, lon_mean: bool = True):
+    """``lon_mean``: whether the data has a lon / longitude coordinate, i.e. whether the synthetic pole rows
+    are the longitude-mean of the edge rows (utils.py:322-323) or plain copies of them."""
     if spec is None:
         return None
     if is_rows and spec.kind == "lon" or (not is_rows and spec.kind == "lat"):
         raise ValueError("layout must be [..., lat, lon]: transpose the data first")
     if spec.kind == "lat":
-        return tables.format_lat_axis(spec.src)
+        return tables.format_lat_axis(spec.src, lon_mean=lon_mean)
     if spec.kind == "lon":
         return tables.format_lon_axis(spec.src, spec.tgt)
     return tables.plain_axis(spec.src)
@@ -238,7 +441,8 @@ class ConservativePlan(BandOp):
             raise ValueError("at least one axis must be regridded")
         if spherical_rows is None:
             spherical_rows = rows is not None and rows.kind == "lat"
-        rows_band = None if rows is None else tables.conservative_band(_axis(rows, True), rows.tgt,
+        lon_mean = cols is not None and cols.kind == "lon"
+        rows_band = None if rows is None else tables.conservative_band(_axis(rows, True, lon_mean), rows.tgt,
                                                                       spherical=spherical_rows)
         cols_band = None if cols is None else tables.conservative_band(_axis(cols, False), cols.tgt)
         super().__init__(rows_band, cols_band, device)
@@ -250,41 +454,93 @@ class ConservativePlan(BandOp):
         if not x.is_cuda:
             raise ValueError("device path takes CUDA tensors; use apply_host() for host buffers")
         x3, lead = _as_batch(x, _result_dtype(x))
-        y = self.run(x3, skipna, tables.valid_threshold(nan_threshold), out)
+        y = self.run(x3, NAN_SKIP if skipna else NAN_ZERO, tables.valid_threshold(nan_threshold), out)
         return y.view(tuple(lead) + tuple(y.shape[-2:]))
 
     # ------------------------------------------------------------------------------
-    def apply_host(self, x_host: torch.Tensor, skipna: bool = True, nan_threshold: float = 1.0,
+    def apply_host(self, x_host, skipna: bool = True, nan_threshold: float = 1.0,
                    out_host: torch.Tensor | None = None, chunk_batch: int = 32,
-                   workspace: torch.Tensor | None = None) -> torch.Tensor:
-        """Host-buffer path (the reference-facing call for data that lives in host memory):
-        chunked H2D -> kernel -> D2H on three streams inside the C library."""
-        if x_host.is_cuda:
-            raise ValueError("apply_host takes host tensors")
+                   workspace: torch.Tensor | None = None, pipeline: HostPipeline | None = None,
+                   drain: bool = True) -> torch.Tensor:
+        """Host-buffer path (the reference-facing call for data that lives in host memory): chunked
+        H2D -> kernel -> D2H on the three streams of a persistent pipeline.
+
+        Page-locked source AND result: one C call, ``rg_conservative_host_*``.  Pageable memory (numpy):
+        the same chunk loop driven through ``HostPipeline.stream`` with page-locked staging chunks.
+        ``drain=False`` (page-locked buffers, explicit ``pipeline``) returns with copies still in flight;
+        finish with ``pipeline.drain()``."""
+        if not 0.0 <= nan_threshold <= 1.0:
+            raise ValueError("nan_threshold must be between [0, 1]]")
+        x_host = _host_tensor(x_host)
         if x_host.dtype not in (torch.float32, torch.float64):
             x_host = x_host.to(_result_dtype(x_host))
         dtype = x_host.dtype
-        x3 = x_host.reshape((-1,) + tuple(x_host.shape[-2:])).contiguous()
+        if x_host.dim() < 2:
+            raise ValueError("data must have at least the two regridded dims [rows, cols]")
+        x3 = x_host.reshape((-1,) + tuple(x_host.shape[-2:]))
         lead = x_host.shape[:-2]
         B, H, W = x3.shape
+        chunk_batch = int(max(1, chunk_batch))
+        thr = tables.valid_threshold(nan_threshold)
         with torch.cuda.device(self.device):
             rows, cols = self._bands(dtype, H, W)
+            if H != rows.host.n_src or W != cols.host.n_src:
+                raise ValueError(
+                    f"data is [{H}, {W}] but the plan was built for [{rows.host.n_src}, {cols.host.n_src}]")
             Ho, Wo = rows.host.n_out, cols.host.n_out
             if out_host is None:
                 out_host = torch.empty((B, Ho, Wo), dtype=dtype, pin_memory=x3.is_pinned())
-            need = lib.rg_conservative_host_workspace(chunk_batch, H, W, Ho, Wo, x3.element_size())
-            if workspace is None or workspace.numel() * workspace.element_size() < need:
-                workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-            fn = lib.rg_conservative_host_f64 if dtype == torch.float64 else lib.rg_conservative_host_f32
-            ring = self._ring(min(chunk_batch, B), H, W, dtype)
-            check(
-                fn(x3.data_ptr(), out_host.data_ptr(), B, chunk_batch, rows.ref, cols.ref,
-                   int(bool(skipna)), tables.valid_threshold(nan_threshold), int(self.pole_rows),
-                   None if ring is None else ring.ref,
-                   workspace.data_ptr(), workspace.numel() * workspace.element_size()),
-                "rg_conservative_host",
-            )
+            else:
+                out_host = _check_out_host(out_host, (B, Ho, Wo), dtype)
+            if B == 0:
+                return out_host.view(tuple(lead) + (Ho, Wo))
+            pipe = pipeline if pipeline is not None else default_pipeline(self.device)
+            if x3.is_pinned() and out_host.is_pinned():
+                need = lib.rg_conservative_host_workspace(chunk_batch, H, W, Ho, Wo, x3.element_size(), pipe.slots)
+                if workspace is None:
+                    workspace = pipe.device_block("conservative", need)  # one block holding every slot
+                if workspace.is_cuda is False or workspace.numel() * workspace.element_size() < need:
+                    raise ValueError(f"workspace must be a CUDA buffer of at least {need} bytes")
+                fn = lib.rg_conservative_host_f64 if dtype == torch.float64 else lib.rg_conservative_host_f32
+                ring = self._ring(min(chunk_batch, B), H, W, dtype)
+                # the workspace and the host buffers may have been produced on torch's current stream
+                pipe.wait_current_stream()
+                check(
+                    fn(x3.data_ptr(), out_host.data_ptr(), B, chunk_batch, rows.ref, cols.ref,
+                       int(bool(skipna)), thr, int(self.pole_rows), int(self.pole_src[0]), int(self.pole_src[1]),
+                       None if ring is None else ring.ref, workspace.data_ptr(),
+                       workspace.numel() * workspace.element_size(), pipe.handle,
+                       0 if drain else _lib.RG_HOST_NO_DRAIN),
+                    "rg_conservative_host",
+                )
+            else:
+                mode = NAN_SKIP if skipna else NAN_ZERO
+                pole = (pipe.device_buffers("pole", min(chunk_batch, B) * 2 * W * x3.element_size(),
+                                            -(-B // chunk_batch)) if self.pole_rows else None)
+                state = {"i": 0}
+
+                def compute(x_dev, y_dev):
+                    pb = None
+                    if pole is not None:
+                        pb = pole[state["i"] % len(pole)][: x_dev.shape[0] * 2 * W * x3.element_size()]
+                        pb = pb.view(dtype).view(x_dev.shape[0], 2, W)
+                    state["i"] += 1
+                    self.run(x_dev, mode, thr, out=y_dev, pole=pb)
+
+                pipe.stream(x3, out_host, chunk_batch, compute)
         return out_host.view(tuple(lead) + (Ho, Wo))
+
+
+def _out_or_new(out, shape: tuple, dtype: torch.dtype, device) -> torch.Tensor:
+    """The caller's result buffer (validated) viewed as ``shape``, or a fresh tensor."""
+    if out is None:
+        return torch.empty(shape, dtype=dtype, device=device)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if out.dtype != dtype or not out.is_contiguous() or out.numel() != n or out.device != torch.device(device):
+        raise ValueError(f"out must be a contiguous {dtype} tensor of {n} elements on {device}")
+    return out.view(shape)
 
 
 _TYPE_CODE = {
@@ -316,7 +572,8 @@ class InterpPlan:
             raise ValueError("at least one axis must be regridded")
         self.method = method
         self.device = _require_cuda(device)
-        rows_axis, cols_axis = _axis(rows, True), _axis(cols, False)
+        rows_axis = _axis(rows, True, cols is not None and cols.kind == "lon")
+        cols_axis = _axis(cols, False)
         self.rows_axis, self.cols_axis = rows_axis, cols_axis
         if method == "linear":
             self.op = BandOp(None if rows is None else tables.linear_band(rows_axis, rows.tgt),
@@ -400,7 +657,8 @@ class InterpPlan:
                                               rb.n_src, cb.n_src)
         return self._gather[(n_rows, n_cols)]
 
-    def _nearest_gather(self, x: torch.Tensor, out_dtype: torch.dtype, fill: float) -> torch.Tensor:
+    def _nearest_gather(self, x: torch.Tensor, out_dtype: torch.dtype, fill: float,
+                        out: torch.Tensor | None = None) -> torch.Tensor:
         lead = x.shape[:-2]
         x3 = x.reshape((-1,) + tuple(x.shape[-2:]))
         if x3.stride(2) != 1:
@@ -410,7 +668,7 @@ class InterpPlan:
         if H != n_rows or W != n_cols:
             raise ValueError(f"data is [{H}, {W}] but the plan was built for [{n_rows}, {n_cols}]")
         Ho, Wo = ri.numel(), ci.numel()
-        y = torch.empty((B, Ho, Wo), dtype=out_dtype, device=x3.device)
+        y = _out_or_new(out, (B, Ho, Wo), out_dtype, x3.device)
         if B:
             check(
                 lib.rg_nearest(x3.data_ptr(), y.data_ptr(), _TYPE_CODE[x3.dtype], _TYPE_CODE[out_dtype], B,
@@ -421,9 +679,35 @@ class InterpPlan:
             )
         return y.view(tuple(lead) + (Ho, Wo))
 
-    def __call__(self, x: torch.Tensor, out_dtype: str = "reference", fill: float = float("nan")) -> torch.Tensor:
+    def result_dtype(self, in_dtype: torch.dtype, out_dtype: str = "reference") -> torch.dtype:
+        """Dtype of the result for data of ``in_dtype`` (the reference's rule, or ``out_dtype="same"``)."""
+        if out_dtype not in ("reference", "same"):
+            raise ValueError("out_dtype must be 'reference' or 'same'")
+        if self.method == "nearest":
+            if in_dtype not in _TYPE_CODE:
+                in_dtype = torch.float32 if in_dtype in (torch.float16, torch.bfloat16) else torch.int32
+            is_float = in_dtype in (torch.float32, torch.float64)
+            if self.op.pole_rows:
+                return in_dtype if is_float else torch.float64
+            return in_dtype if (is_float or out_dtype == "same") else torch.float64
+        if self.method == "linear" and out_dtype == "same" and in_dtype in (torch.float32, torch.float16,
+                                                                           torch.bfloat16):
+            return torch.float32
+        return torch.float64
+
+    def out_hw(self, n_rows: int, n_cols: int):
+        """Shape of the regridded ``[rows, cols]`` for a source slab of ``[n_rows, n_cols]``."""
+        if self.method == "cubic":
+            Hf, Wf = self.pre._out_hw(n_cols, n_rows)
+            return self.op._out_hw(Wf, Hf)
+        return self.op._out_hw(n_cols, n_rows)
+
+    def __call__(self, x: torch.Tensor, out_dtype: str = "reference", fill: float = float("nan"),
+                 out: torch.Tensor | None = None, nan_flag: torch.Tensor | None = None) -> torch.Tensor:
+        """``nan_flag`` (cubic, used by the chunked host path): a device int32 the NaN rule ORs into INSTEAD of
+        poisoning this call's result; the caller applies scipy's "any NaN -> everything NaN" over all chunks."""
         if not x.is_cuda:
-            raise ValueError("InterpPlan takes CUDA tensors")
+            raise ValueError("InterpPlan takes CUDA tensors; use apply_host() for host buffers")
         if out_dtype not in ("reference", "same"):
             raise ValueError("out_dtype must be 'reference' or 'same'")
         is_float = x.dtype in (torch.float32, torch.float64)
@@ -433,27 +717,28 @@ class InterpPlan:
                 is_float = x.dtype == torch.float32
             if self.op.pole_rows:  # a synthetic pole row can be the nearest neighbour: needs the mean
                 x3, lead = _as_batch(x, x.dtype if is_float else torch.float64)
-                y = self.op.run(x3, False, 0.0)
+                y = self.op.run(x3, NAN_PROPAGATE, 0.0, out=out)
                 return y.view(tuple(lead) + tuple(y.shape[-2:]))
             target = x.dtype if (is_float or out_dtype == "same") else torch.float64
-            return self._nearest_gather(x, target, fill)
+            return self._nearest_gather(x, target, fill, out=out)
 
         work = torch.float64
         if self.method == "linear" and out_dtype == "same" and x.dtype in (torch.float32, torch.float16, torch.bfloat16):
             work = torch.float32
         x3, lead = _as_batch(x, work)
         if self.method == "linear":
-            y = self.op.run(x3, False, 0.0)
+            y = self.op.run(x3, NAN_PROPAGATE, 0.0, out=out)
             return y.view(tuple(lead) + tuple(y.shape[-2:]))
 
         # cubic: NaN flag -> prefilter (source grid) -> evaluate (target grid) -> poison
         B, H, W = x3.shape
         Hf, Wf = self.pre._out_hw(W, H)
         Ho, Wo = self.op._out_hw(Wf, Hf)
+        y = _out_or_new(out, (B, Ho, Wo), work, x3.device)
         if self.all_nan:
-            return torch.full(tuple(lead) + (Ho, Wo), float("nan"), dtype=work, device=x3.device)
-        y = torch.empty((B, Ho, Wo), dtype=work, device=x3.device)
-        flag = torch.zeros(1, dtype=torch.int32, device=x3.device)
+            y.fill_(float("nan"))
+            return y.view(tuple(lead) + (Ho, Wo))
+        flag = nan_flag if nan_flag is not None else torch.zeros(1, dtype=torch.int32, device=x3.device)
         stream = _stream_ptr(x3.device)
         if B:
             check(lib.rg_nan_flag_f64(x3.data_ptr(), B, H, W, x3.stride(0) if B > 1 else H * x3.stride(1),
@@ -462,11 +747,54 @@ class InterpPlan:
             xs = x3[s0:s0 + self.chunk]
             coeff = self._coefficients_lu(xs, Hf, Wf) if (self._lu is not None and self.use_lu) else None
             if coeff is None:
-                coeff = self.pre.run(xs, False, 0.0)
-            self.op.run(coeff, False, 0.0, out=y[s0:s0 + self.chunk])
-        if B:
+                coeff = self.pre.run(xs, NAN_PROPAGATE, 0.0)
+            self.op.run(coeff, NAN_PROPAGATE, 0.0, out=y[s0:s0 + self.chunk])
+        if B and nan_flag is None:
             check(lib.rg_poison_if_f64(y.data_ptr(), y.numel(), flag.data_ptr(), stream), "rg_poison_if")
         return y.view(tuple(lead) + (Ho, Wo))
+
+    def apply_host(self, x_host, out_host: torch.Tensor | None = None, out_dtype: str = "reference",
+                   fill: float = float("nan"), chunk_batch: int | None = None,
+                   pipeline: HostPipeline | None = None) -> torch.Tensor:
+        """Host-buffer path: the stack is streamed in chunks of ``chunk_batch`` slabs through a persistent
+        pipeline (H2D, kernels and D2H overlap; the device holds only ``slots`` chunks, so results far larger
+        than HBM -- config 3 is 1.4 TB -- pass through a reused block).  Takes numpy arrays or CPU tensors
+        (page-locked ones are copied without staging) and returns a CPU tensor."""
+        x_host = _host_tensor(x_host)
+        if self.method == "nearest" and x_host.dtype not in _TYPE_CODE:
+            x_host = x_host.to(torch.float32 if x_host.dtype in (torch.float16, torch.bfloat16) else torch.int32)
+        if self.method != "nearest" and x_host.dtype not in (torch.float32, torch.float64):
+            x_host = x_host.to(torch.float64)  # scipy computes linear / cubic in float64
+        if x_host.dim() < 2:
+            raise ValueError("data must have at least the two regridded dims [rows, cols]")
+        res_dtype = self.result_dtype(x_host.dtype, out_dtype)
+        x3 = x_host.reshape((-1,) + tuple(x_host.shape[-2:]))
+        lead = x_host.shape[:-2]
+        B, H, W = x3.shape
+        Ho, Wo = self.out_hw(H, W)
+        if out_host is None:
+            out_host = torch.empty((B, Ho, Wo), dtype=res_dtype, pin_memory=x3.is_pinned())
+        else:
+            out_host = _check_out_host(out_host, (B, Ho, Wo), res_dtype)
+        if B == 0:
+            return out_host.view(tuple(lead) + (Ho, Wo))
+        if chunk_batch is None:  # ~256 MB of the larger side per chunk
+            per_slab = max(H * W * x3.element_size(), Ho * Wo * out_host.element_size())
+            chunk_batch = max(1, min(B, (256 << 20) // per_slab))
+        pipe = pipeline if pipeline is not None else default_pipeline(self.device)
+        with torch.cuda.device(self.device):
+            flag = None
+            if self.method == "cubic":
+                flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+                torch.cuda.current_stream(self.device).synchronize()
+
+            def compute(x_dev, y_dev):
+                self(x_dev, out_dtype=out_dtype, fill=fill, out=y_dev, nan_flag=flag)
+
+            pipe.stream(x3, out_host, chunk_batch, compute)
+            if flag is not None and int(flag.item()) != 0:  # scipy: one NaN anywhere -> everything NaN
+                out_host.fill_(float("nan"))
+        return out_host.view(tuple(lead) + (Ho, Wo))
 
 
 class DeviceBins:
@@ -579,30 +907,43 @@ class ReducePlan:
             )
         return x3, lead, rows, cols
 
-    def mode(self, x: torch.Tensor, values, fill_value=None, anti_mode: bool = False) -> torch.Tensor:
-        """``compute_mode`` (methods/flox_reduce.py:122-187)."""
-        if not x.is_cuda:
-            raise ValueError("ReducePlan takes CUDA tensors")
-        if x.dtype not in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+    def out_hw(self, n_rows: int, n_cols: int):
+        rows, cols = self._bins(n_rows, n_cols)
+        return rows.host.n_out, cols.host.n_out
+
+    @staticmethod
+    def _check_mode_dtype(dtype):
+        if dtype not in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
             raise ValueError(
                 "Your input data has to be of an integer datatype for this method.\n"
-                f"    instead, your data is of type '{x.dtype}'."
+                f"    instead, your data is of type '{dtype}'."
             )
+
+    def mode_result(self, dtype: torch.dtype, fill_value, warn: bool = True):
+        """(result dtype, fill) of ``mode`` for data of ``dtype`` (methods/_shared.py:56-72)."""
+        if fill_value is None and not self.fully_covered:
+            if warn:
+                import warnings
+
+                warnings.warn(
+                    "No fill_value is provided; data will be cast to floating point dtype to be able to use "
+                    "NaN for missing values.", stacklevel=1,
+                )
+            return torch.float64, float("nan")
+        return dtype, 0.0 if fill_value is None else float(fill_value)
+
+    def mode(self, x: torch.Tensor, values, fill_value=None, anti_mode: bool = False,
+             out: torch.Tensor | None = None, _warn: bool = True) -> torch.Tensor:
+        """``compute_mode`` (methods/flox_reduce.py:122-187)."""
+        if not x.is_cuda:
+            raise ValueError("ReducePlan takes CUDA tensors; use mode_host() for host buffers")
+        self._check_mode_dtype(x.dtype)
         x3, lead, rows, cols = self._prepare(x)
         np_dtype = np.dtype(str(x.dtype).replace("torch.", ""))
         vals, dense, v_dev, vs_dev, rank_dev = self._label_tables(np_dtype, values)
-        if fill_value is None and not self.fully_covered:
-            import warnings
-
-            warnings.warn(
-                "No fill_value is provided; data will be cast to floating point dtype to be able to use "
-                "NaN for missing values.", stacklevel=1,
-            )
-            out_dtype, fill = torch.float64, float("nan")
-        else:
-            out_dtype, fill = x.dtype, 0.0 if fill_value is None else float(fill_value)
+        out_dtype, fill = self.mode_result(x.dtype, fill_value, _warn)
         B, Ho, Wo = x3.shape[0], rows.host.n_out, cols.host.n_out
-        y = torch.empty((B, Ho, Wo), dtype=out_dtype, device=x3.device)
+        y = _out_or_new(out, (B, Ho, Wo), out_dtype, x3.device)
         cpc, tile, strip, max_rows, max_cols = self._geometry(rows, cols, x3.element_size(), 8 * vals.size * 4)
         if B:
             check(
@@ -616,17 +957,18 @@ class ReducePlan:
             )
         return y.view(tuple(lead) + (Ho, Wo))
 
-    def stat(self, x: torch.Tensor, method: str, skipna: bool = False, fill_value=None) -> torch.Tensor:
+    def stat(self, x: torch.Tensor, method: str, skipna: bool = False, fill_value=None,
+             out: torch.Tensor | None = None) -> torch.Tensor:
         """``statistic_reduce`` (methods/flox_reduce.py:40-100)."""
         if method not in VALID_STAT_METHODS:
             raise ValueError(f"Invalid method. Please choose from '{VALID_STAT_METHODS}'.")
         if not x.is_cuda:
-            raise ValueError("ReducePlan takes CUDA tensors")
+            raise ValueError("ReducePlan takes CUDA tensors; use stat_host() for host buffers")
         if x.dtype not in (torch.float32, torch.float64):
             x = x.to(torch.float64)
         x3, lead, rows, cols = self._prepare(x)
         B, Ho, Wo = x3.shape[0], rows.host.n_out, cols.host.n_out
-        y = torch.empty((B, Ho, Wo), dtype=x3.dtype, device=x3.device)
+        y = _out_or_new(out, (B, Ho, Wo), x3.dtype, x3.device)
         sort_cap = 0
         if method == "median":
             _, _, _, max_rows, max_cols = self._geometry(rows, cols, x3.element_size(), 0)
@@ -643,6 +985,53 @@ class ReducePlan:
                 "rg_stat",
             )
         return y.view(tuple(lead) + (Ho, Wo))
+
+    # ------------------------------------------------------------------------ host-buffer paths
+    def _host(self, x_host, res_dtype, out_host, chunk_batch, pipeline, compute):
+        if x_host.dim() < 2:
+            raise ValueError("data must have at least the two regridded dims [rows, cols]")
+        x3 = x_host.reshape((-1,) + tuple(x_host.shape[-2:]))
+        lead = x_host.shape[:-2]
+        B, H, W = x3.shape
+        Ho, Wo = self.out_hw(H, W)
+        if out_host is None:
+            out_host = torch.empty((B, Ho, Wo), dtype=res_dtype, pin_memory=x3.is_pinned())
+        else:
+            out_host = _check_out_host(out_host, (B, Ho, Wo), res_dtype)
+        if B:
+            if chunk_batch is None:  # ~256 MB of source per chunk
+                chunk_batch = max(1, min(B, (256 << 20) // max(H * W * x3.element_size(), 1)))
+            pipe = pipeline if pipeline is not None else default_pipeline(self.device)
+            pipe.stream(x3, out_host, chunk_batch, compute)
+        return out_host.view(tuple(lead) + (Ho, Wo))
+
+    def mode_host(self, x_host, values, fill_value=None, anti_mode: bool = False,
+                  out_host: torch.Tensor | None = None, chunk_batch: int | None = None,
+                  pipeline: HostPipeline | None = None) -> torch.Tensor:
+        """``mode`` for data in host memory (numpy / CPU tensor), streamed through a persistent pipeline."""
+        x_host = _host_tensor(x_host)
+        self._check_mode_dtype(x_host.dtype)
+        res_dtype, _ = self.mode_result(x_host.dtype, fill_value)
+
+        def compute(x_dev, y_dev):
+            self.mode(x_dev, values, fill_value=fill_value, anti_mode=anti_mode, out=y_dev, _warn=False)
+
+        return self._host(x_host, res_dtype, out_host, chunk_batch, pipeline, compute)
+
+    def stat_host(self, x_host, method: str, skipna: bool = False, fill_value=None,
+                  out_host: torch.Tensor | None = None, chunk_batch: int | None = None,
+                  pipeline: HostPipeline | None = None) -> torch.Tensor:
+        """``stat`` for data in host memory (numpy / CPU tensor), streamed through a persistent pipeline."""
+        if method not in VALID_STAT_METHODS:
+            raise ValueError(f"Invalid method. Please choose from '{VALID_STAT_METHODS}'.")
+        x_host = _host_tensor(x_host)
+        if x_host.dtype not in (torch.float32, torch.float64):
+            x_host = x_host.to(torch.float64)
+
+        def compute(x_dev, y_dev):
+            self.stat(x_dev, method, skipna=skipna, fill_value=fill_value, out=y_dev)
+
+        return self._host(x_host, x_host.dtype, out_host, chunk_batch, pipeline, compute)
 
 
 def sm_count() -> int:

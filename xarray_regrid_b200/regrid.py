@@ -6,8 +6,10 @@ is registered as the ``regrid`` accessor of ``xarray.DataArray`` / ``xarray.Data
 reference does (regrid.py:11-12), converting through ``labelled.from_xarray`` / ``to_xarray``.
 
 What stays on the host is label bookkeeping only: which coordinates are regridded, their names
-(lat / lon formatting), dimension order, attributes.  Arrays that arrive as numpy are moved to the GPU,
-regridded and returned as numpy; CUDA tensors stay on the device.
+(lat / lon formatting), dimension order, attributes.  Arrays that arrive in host memory (numpy, CPU
+tensors) are streamed through the engine's persistent host pipeline in chunks along the non-regridded dims
+(``engine.HostPipeline``: page-locked staging, H2D / kernels / D2H overlapped -- the stand-in for the
+reference's dask chunk scheduling) and come back as numpy / CPU tensors; CUDA tensors stay on the device.
 """
 
 from __future__ import annotations
@@ -120,9 +122,19 @@ def _from_device(y: torch.Tensor, how: str):
     return y.cpu().numpy()
 
 
+def _device_of(x: torch.Tensor) -> torch.device:
+    return x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+
+def _is_host(data) -> bool:
+    return not (isinstance(data, torch.Tensor) and data.is_cuda)
+
+
 def _apply(da: DataArray, target: Dataset, names, run, coord_attrs_from: str, prefer_rows=None) -> DataArray:
-    """Shared driver: permute to ``[..., rows, cols]``, call ``run(x, rows_name, rows_spec, cols_spec)``,
-    permute back, relabel.  ``run`` receives CUDA data and the two ``engine.AxisSpec`` (or None)."""
+    """Shared driver: permute to ``[..., rows, cols]``, call ``run(x, rows_name, rows_spec, cols_spec, host)``,
+    permute back, relabel.  ``run`` receives the two ``engine.AxisSpec`` (or None) and either CUDA data
+    (``host=False``) or, when the data lives in host memory and already has the kernels' layout, a CPU tensor
+    sharing the caller's memory (``host=True``: the plan's streaming host path)."""
     lay = _layout(da, names, prefer_rows)
     if lay is None:
         return da
@@ -137,13 +149,22 @@ def _apply(da: DataArray, target: Dataset, names, run, coord_attrs_from: str, pr
         order, pad = batch + [cols], -2
     else:
         order = batch + [rows, cols]
-    x, how = _to_device(da.data)
-    x = x.permute([da.dims.index(d) for d in order])
-    if pad is not None:
-        x = x.unsqueeze(pad)
+    perm = [da.dims.index(d) for d in order]
     spec = {n: engine.AxisSpec(np.asarray(da.coords[n]), np.asarray(target.coords[n]), _kind(n))
             for n in (rows, cols) if n is not None}
-    y = run(x, rows, spec.get(rows), spec.get(cols))
+    if _is_host(da.data) and perm == list(range(len(perm))):
+        # host memory in the kernels' own layout: stream chunks of the leading dims, no whole-array copy
+        x = engine._host_tensor(da.data)
+        how = "cpu-tensor" if isinstance(da.data, torch.Tensor) else "numpy"
+        if pad is not None:
+            x = x.unsqueeze(pad)
+        y = run(x, rows, spec.get(rows), spec.get(cols), True)
+    else:
+        x, how = _to_device(da.data)
+        x = x.permute(perm)
+        if pad is not None:
+            x = x.unsqueeze(pad)
+        y = run(x, rows, spec.get(rows), spec.get(cols), False)
     if pad is not None:
         y = y.squeeze(pad)
     y = y.permute([order.index(d) for d in da.dims])
@@ -186,12 +207,13 @@ class Regridder:
         names = [c for c in target.coords if c in self._obj.coords]
 
         def one(da):
-            def run(x, rows_name, rs, cs):
+            def run(x, rows_name, rs, cs, host):
+                dev = _device_of(x)
                 key = _key("interp", method, None if rs is None else rs.src, None if rs is None else rs.tgt,
                            None if rs is None else rs.kind, None if cs is None else cs.src,
-                           None if cs is None else cs.tgt, None if cs is None else cs.kind, str(x.device))
-                plan = _cached(key, lambda: engine.InterpPlan(rs, cs, method, device=x.device))
-                return plan(x)
+                           None if cs is None else cs.tgt, None if cs is None else cs.kind, str(dev))
+                plan = _cached(key, lambda: engine.InterpPlan(rs, cs, method, device=dev))
+                return plan.apply_host(x) if host else plan(x)
 
             return _apply(da, target, names, run, "data")
 
@@ -226,16 +248,19 @@ class Regridder:
         names = [c for c in target.coords if c in self._obj.coords]
 
         def one(da):
-            def run(x, rows_name, rs, cs):
+            def run(x, rows_name, rs, cs, host):
                 spherical = rows_name is not None and rows_name == latitude_coord
                 if latitude_coord in names and latitude_coord in da.dims and not spherical:
                     raise NotImplementedError("the latitude coordinate must be the row axis of the kernel")
+                dev = _device_of(x)
                 key = _key("conservative", spherical, None if rs is None else rs.src,
                            None if rs is None else rs.tgt, None if rs is None else rs.kind,
                            None if cs is None else cs.src, None if cs is None else cs.tgt,
-                           None if cs is None else cs.kind, str(x.device))
+                           None if cs is None else cs.kind, str(dev))
                 plan = _cached(key, lambda: engine.ConservativePlan(rs, cs, spherical_rows=spherical,
-                                                                    device=x.device))
+                                                                    device=dev))
+                if host:
+                    return plan.apply_host(x, skipna=skipna, nan_threshold=nan_threshold)
                 return plan(x, skipna=skipna, nan_threshold=nan_threshold)
 
             return _apply(da, target, names, run, "data", prefer_rows=latitude_coord)
@@ -254,11 +279,14 @@ class Regridder:
             )
         names = [c for c in target.coords if c in self._obj.coords and c != time_dim]
 
-        def run(x, rows_name, rs, cs):
+        def run(x, rows_name, rs, cs, host):
+            dev = _device_of(x)
             key = _key("reduce", None if rs is None else rs.src, None if rs is None else rs.tgt,
                        None if rs is None else rs.kind, None if cs is None else cs.src,
-                       None if cs is None else cs.tgt, None if cs is None else cs.kind, str(x.device))
-            plan = _cached(key, lambda: engine.ReducePlan(rs, cs, device=x.device))
+                       None if cs is None else cs.tgt, None if cs is None else cs.kind, str(dev))
+            plan = _cached(key, lambda: engine.ReducePlan(rs, cs, device=dev))
+            if host:
+                return plan.mode_host(x, values, fill_value=fill_value, anti_mode=anti_mode)
             return plan.mode(x, values, fill_value=fill_value, anti_mode=anti_mode)
 
         return _apply(self._obj, target, names, run, "target")
@@ -280,11 +308,14 @@ class Regridder:
         names = [c for c in target.coords if c in self._obj.coords and c != time_dim]
 
         def one(da):
-            def run(x, rows_name, rs, cs):
+            def run(x, rows_name, rs, cs, host):
+                dev = _device_of(x)
                 key = _key("reduce", None if rs is None else rs.src, None if rs is None else rs.tgt,
                            None if rs is None else rs.kind, None if cs is None else cs.src,
-                           None if cs is None else cs.tgt, None if cs is None else cs.kind, str(x.device))
-                plan = _cached(key, lambda: engine.ReducePlan(rs, cs, device=x.device))
+                           None if cs is None else cs.tgt, None if cs is None else cs.kind, str(dev))
+                plan = _cached(key, lambda: engine.ReducePlan(rs, cs, device=dev))
+                if host:
+                    return plan.stat_host(x, method, skipna=skipna, fill_value=fill_value)
                 return plan.stat(x, method, skipna=skipna, fill_value=fill_value)
 
             return _apply(da, target, names, run, "target")

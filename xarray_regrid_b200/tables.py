@@ -57,6 +57,9 @@ class FormattedAxis:
     values: np.ndarray
     source: np.ndarray
     n_src: int
+    # ORIGINAL positions of the southernmost / northernmost source row (after sorting): the rows whose
+    # longitude-mean fills the synthetic pole rows ``n_src`` / ``n_src + 1`` (utils.py:320-333)
+    pole_src: tuple = (0, 0)
 
     @property
     def has_pole_rows(self) -> bool:
@@ -77,22 +80,30 @@ def plain_axis(coord) -> FormattedAxis:
     return FormattedAxis(coord[src], src, coord.size)
 
 
-def format_lat_axis(lat) -> FormattedAxis:
+def format_lat_axis(lat, lon_mean: bool = True) -> FormattedAxis:
     """utils.py:313-336: add -90 / +90 rows when the edge row is within one (maximum)
-    spacing of the pole but not on it."""
+    spacing of the pole but not on it.
+
+    The reference sorts first (``ensure_monotonic``, utils.py:277) and then takes the FIRST / LAST row of the
+    sorted data, so for a descending or shuffled latitude the south pole row comes from the original row
+    ``source[0]`` (not row 0).  ``lon_mean``: the pole row is the longitude-mean of that edge row only when
+    the object has a lon / longitude coordinate (utils.py:322-323, 330-331); without one it is a plain copy
+    of the edge row, which needs no virtual row -- the pole position simply reads the edge row itself."""
     ax = plain_axis(lat)
     vals, src = ax.values, ax.source
+    pole_src = (0, 0)
     if vals.size > 1:
         dy = np.diff(vals).max()
         south = dy - 90 >= vals[0] > -90
         north = 90 - dy <= vals[-1] < 90
+        pole_src = (int(src[0]), int(src[-1]))
         if south:
             vals = np.concatenate([[-90], vals])
-            src = np.concatenate([[ax.n_src], src])
+            src = np.concatenate([[ax.n_src if lon_mean else pole_src[0]], src])
         if north:
             vals = np.concatenate([vals, [90]])
-            src = np.concatenate([src, [ax.n_src + 1]])
-    return FormattedAxis(vals, src, ax.n_src)
+            src = np.concatenate([src, [ax.n_src + 1 if lon_mean else pole_src[1]]])
+    return FormattedAxis(vals, src, ax.n_src, pole_src)
 
 
 def format_lon_axis(lon, tgt_lon) -> FormattedAxis:
@@ -264,7 +275,7 @@ def conservative_band(axis: FormattedAxis, tgt, spherical: bool = False) -> Band
         idx_src, w_c, cnt, cover = idx_src[:, restore], w_c[:, restore], cnt[restore], cover[restore]
     return Band(np.ascontiguousarray(idx_src), np.ascontiguousarray(w_c), np.ascontiguousarray(cnt),
                 np.ascontiguousarray(cover), axis.n_src, restore,
-                {"formatted_size": int(src.size), "pole_rows": axis.has_pole_rows})
+                {"formatted_size": int(src.size), "pole_rows": axis.has_pole_rows, "pole_src": axis.pole_src})
 
 
 def identity_band(n: int) -> Band:
@@ -562,7 +573,7 @@ def linear_band(axis: FormattedAxis, tgt) -> Band:
     idx = np.stack([axis.source[lo], axis.source[hi]]).astype(np.int32)
     w = np.stack([w_lo, w_hi]).astype(np.float64)
     return Band(idx, w, np.full(t.size, 2, np.int32), cover.astype(np.uint8), axis.n_src, None,
-                {"pole_rows": axis.has_pole_rows, "method": "linear"})
+                {"pole_rows": axis.has_pole_rows, "pole_src": axis.pole_src, "method": "linear"})
 
 
 def nearest_index(axis: FormattedAxis, tgt):
@@ -583,7 +594,7 @@ def nearest_index(axis: FormattedAxis, tgt):
 def nearest_band(axis: FormattedAxis, tgt) -> Band:
     idx, cover = nearest_index(axis, tgt)
     return Band(idx[None, :], np.ones((1, idx.size)), np.ones(idx.size, np.int32), cover, axis.n_src,
-                None, {"pole_rows": axis.has_pole_rows, "method": "nearest"})
+                None, {"pole_rows": axis.has_pole_rows, "pole_src": axis.pole_src, "method": "nearest"})
 
 
 def cubic_bands(axis: FormattedAxis, tgt, rel_cut: float = 1e-18):
@@ -617,7 +628,7 @@ def cubic_bands(axis: FormattedAxis, tgt, rel_cut: float = 1e-18):
     src = axis.source[np.where(dead, order[:, :1], order)]
     pre = Band(np.ascontiguousarray(src.T.astype(np.int32)), np.ascontiguousarray(w.T),
                cnt, np.ones(n, np.uint8), axis.n_src, None,
-               {"pole_rows": axis.has_pole_rows, "method": "cubic-prefilter"})
+               {"pole_rows": axis.has_pole_rows, "pole_src": axis.pole_src, "method": "cubic-prefilter"})
 
     cover = ~((t < x[0]) | (t > x[-1]))
     tc = np.clip(t, x[0], x[-1])
