@@ -53,7 +53,8 @@ def test_pole_rows_descending_and_shuffled_latitude_interp(engine, order, method
     y = plan(torch.from_numpy(x).cuda())
     want = oi.regrid_latlon(x, lat, lon, tlat, tlon, method)
     scale = np.nanmax(np.abs(want))
-    _check(y, want, 0.0 if method == "nearest" else 1e-11, atol=0.0 if method == "nearest" else 1e-11 * scale)
+    # (nearest is exact except for the pole MEANS, whose summation order differs from numpy's by an ulp)
+    _check(y, want, 1e-14 if method == "nearest" else 1e-11, atol=0.0 if method == "nearest" else 1e-11 * scale)
     # the pole targets themselves
     south = np.nanmean(x[:, np.argmin(lat), :], axis=-1)
     if method != "cubic":
