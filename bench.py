@@ -295,11 +295,16 @@ def run_reference_arm(args) -> None:
 
 
 # ----------------------------------------------------------------------------- parity checks
-def _parity(got, want, rtol, atol=0.0, exact=False) -> bool:
+def _parity(got, want, rtol, atol=0.0, exact=False, ignore=None) -> bool:
+    """NaN placement equal and values within tolerance; cells flagged in ``ignore`` are skipped."""
     import numpy as np
 
     got, want = np.asarray(got), np.asarray(want)
-    if got.shape != want.shape or not np.array_equal(np.isnan(got), np.isnan(want)):
+    if got.shape != want.shape:
+        return False
+    if ignore is not None:
+        got, want = np.where(ignore, 0, got), np.where(ignore, 0, want)
+    if not np.array_equal(np.isnan(got), np.isnan(want)):
         return False
     if exact:
         return bool(np.array_equal(got, want, equal_nan=True))
@@ -312,11 +317,18 @@ def check_conservative_slabs(x, y, steps, lat, lon, tlat, tlon, skipna=True, thr
 
     from oracle import conservative as oc
 
+    import numpy as np
+
     idx = torch.tensor(sorted(set(int(s) for s in steps)), device=x.device)
     xs = x.index_select(0, idx).cpu().numpy()
     ys = y.index_select(0, idx).cpu().numpy()
-    want = oc.regrid_latlon(xs, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr)
-    return _parity(ys, want, rtol, atol=rtol * 1e-3)
+    want, valid = oc.regrid_latlon(xs, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr, return_valid=True)
+    # a valid mass that equals the threshold to within rounding is a coin toss in the reference itself (it
+    # depends on the summation order of the BLAS behind einsum): such cells are not compared
+    ties = np.abs(valid - oc.valid_threshold(thr)) <= 1e-13
+    if ties.sum() > 1e-3 * ties.size:
+        return False
+    return _parity(ys, want, rtol, atol=rtol * 1e-3, ignore=ties)
 
 
 # --------------------------------------------------------------------------------- ops block

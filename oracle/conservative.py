@@ -94,8 +94,13 @@ def covered_mask(src, tgt):
 
 
 # ------------------------------------------------------------------------- contraction
-def apply_weights(data, w_by_axis, skipna, nan_threshold):
+def apply_weights(data, w_by_axis, skipna, nan_threshold, return_valid=False):
     """conservative.py:181-208 for 1 or 2 regridded axes.
+
+    ``return_valid`` (checker convenience, not part of the reference): also return the valid mass
+    ``valid_frac`` so that a comparison can tell apart the cells whose mass equals the threshold to
+    within rounding -- there the reference's own NaN placement depends on the summation order of the
+    BLAS behind ``einsum``.
 
     ``w_by_axis`` maps a (negative) axis of ``data`` to its dense [n_src, n_tgt]
     weights, already cast to ``result_type(float32, data.dtype)``
@@ -125,14 +130,15 @@ def apply_weights(data, w_by_axis, skipna, nan_threshold):
     filled = np.where(notnull, data, 0).astype(np.result_type(data.dtype, wdtype))
 
     if not skipna:
-        return np.einsum(spec, filled, *operands, optimize=True)
+        out = np.einsum(spec, filled, *operands, optimize=True)
+        return (out, np.ones_like(out)) if return_valid else out
 
     valid = np.einsum(spec, notnull, *operands, optimize=True)
     out = np.einsum(spec, filled, *operands, optimize=True)
     with np.errstate(invalid="ignore", divide="ignore"):
         out = out / valid
     out = np.where(valid >= valid_threshold(nan_threshold), out, np.nan)
-    return out
+    return (out, valid) if return_valid else out
 
 
 # ---------------------------------------------------------------------------- pipeline
@@ -144,6 +150,7 @@ def regrid(
     latitude_index=None,
     skipna=True,
     nan_threshold=1.0,
+    return_valid=False,
 ):
     """Everything ``conservative_regrid`` does after ``format_for_regrid``
     (conservative.py:39-178) for the regridded ``axes`` of ``data``.
@@ -170,19 +177,20 @@ def regrid(
         # reindex_like(target): pick, for every original target label, its sorted position
         restore[ax] = np.searchsorted(tgt_sorted, tgt)
 
-    out = apply_weights(data, w_by_axis, skipna, nan_threshold)
+    out, valid = apply_weights(data, w_by_axis, skipna, nan_threshold, return_valid=True)
     for ax, mask in cover.items():
         shape = [1] * out.ndim
         shape[ax] = mask.size
         out = np.where(mask.reshape(shape), out, np.nan)
     for ax, idx in restore.items():
         out = np.take(out, idx, axis=ax)
-    return out
+        valid = np.take(valid, idx, axis=ax)
+    return (out, valid) if return_valid else out
 
 
 def regrid_latlon(
     data, src_lat, src_lon, tgt_lat, tgt_lon, skipna=True, nan_threshold=1.0,
-    latitude_weighting=True,
+    latitude_weighting=True, return_valid=False,
 ):
     """``da.regrid.conservative(target)`` for data laid out ``[..., lat, lon]`` with
     coordinates NAMED latitude/longitude: ``format_for_regrid`` (regrid.py:123) then
@@ -193,5 +201,5 @@ def regrid_latlon(
     return regrid(
         data, [lat, lon], [tgt_lat, tgt_lon], [-2, -1],
         latitude_index=0 if latitude_weighting else None,
-        skipna=skipna, nan_threshold=nan_threshold,
+        skipna=skipna, nan_threshold=nan_threshold, return_valid=return_valid,
     )

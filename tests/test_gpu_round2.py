@@ -243,3 +243,52 @@ def test_accessor_numpy_route_equals_cuda_route():
     b = DataArray(torch.from_numpy(lab).cuda(), ("time", "lat", "lon"), coords).regrid.most_common(
         tgt, values=np.arange(5))
     np.testing.assert_array_equal(a.data, b.data.cpu().numpy())
+
+
+def test_c5_most_common_full_scale_18000x36000(engine):
+    """BASELINE config 5 at its full size: 18000 x 36000 uint8 land cover, 32 classes -> 0.25 deg (720 x 1440).
+    The oracle runs on 4 latitude bands of 10 target rows (incl. both polar edge bands); sharding.latitude_band
+    gives the source rows a band needs."""
+    from xarray_regrid_b200 import sharding
+
+    lat, lon = np.round(np.arange(-89.995, 90, 0.01), 3), np.round(np.arange(0.005, 360, 0.01), 3)
+    tlat, tlon = np.arange(-89.875, 90, 0.25), np.arange(0.125, 360, 0.25)
+    g = torch.Generator(device="cuda").manual_seed(13)
+    coarse = torch.randint(0, 32, (18000 // 64 + 1, 36000 // 64 + 1), device="cuda", generator=g)
+    x = coarse.repeat_interleave(64, 0).repeat_interleave(64, 1)[:18000, :36000].to(torch.uint8).contiguous()
+    noise = torch.rand((18000, 36000), device="cuda", generator=g) < 0.05
+    x[noise] = torch.randint(0, 32, (int(noise.sum()),), device="cuda", generator=g, dtype=torch.uint8)
+    del noise, coarse
+    plan = engine.ReducePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"))
+    values = np.arange(32)
+    y = plan.mode(x, values)
+    assert y.shape == (720, 1440) and y.dtype == torch.uint8
+    for r in (0, 23, 48, 71):
+        tgt_idx, src = sharding.latitude_band(lat, tlat, 72, r)
+        want = orr.regrid_latlon(x[src].cpu().numpy(), lat[src], lon, tlat[tgt_idx], tlon, "most_common", values=values)
+        np.testing.assert_array_equal(y[tgt_idx.min():tgt_idx.max() + 1].cpu().numpy(), want)
+    # size-independent property: regridding a constant field returns the constant, and permuting the label
+    # values permutes the result (ties aside: use least_common's complement only where counts are distinct)
+    const = torch.full_like(x, 7)
+    assert bool((plan.mode(const, values) == 7).all())
+
+
+def test_threshold_ties_are_the_only_nan_placement_differences(engine):
+    """On 2:1 coarsening with nan_threshold=0.5 the valid mass of a cell can equal the threshold EXACTLY in
+    real arithmetic (e.g. the centre column, weight 1/2, missing in every row).  Which side of the comparison
+    such a cell lands on depends on the summation order -- in the reference on the BLAS behind einsum -- so
+    NaN placement is compared outside those ties, and the ties must be rare."""
+    lat, lon = np.arange(-90.0, 90.25, 0.25), np.arange(0.0, 360.0, 0.25)
+    tlat, tlon = np.arange(-90.0, 90.1, 0.5), np.arange(0.0, 360, 0.5)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand((2, lat.size, lon.size), device="cuda", dtype=torch.float64, generator=g) + 0.5
+    x[torch.rand(x.shape, device="cuda", generator=g) < 0.05] = float("nan")
+    plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"))
+    y = plan(x, skipna=True, nan_threshold=0.5).cpu().numpy()
+    want, valid = oc.regrid_latlon(x.cpu().numpy(), lat, lon, tlat, tlon, skipna=True, nan_threshold=0.5,
+                                   return_valid=True)
+    ties = np.abs(valid - 0.5) <= 1e-13
+    assert ties.sum() < 1e-3 * ties.size
+    np.testing.assert_array_equal(np.isnan(y)[~ties], np.isnan(want)[~ties])
+    both = ~np.isnan(y) & ~np.isnan(want)
+    np.testing.assert_allclose(y[both], want[both], rtol=1e-12)
