@@ -241,8 +241,9 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       ring_c->strip_l0 && ring_c->strip_c0 && ring_c->strip_nc) {
     const int kw = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : cols.k_max <= 3 ? 3 : cols.k_max <= 5 ? 5 : 8;
     // lane-owned columns variant (4 source columns + 1 per target, see conservative_ring.cuh): no strip buffers
+    // (the staged per-row record packs need / release into 16 bits each)
     const bool lanes = ring_c->lane_cols == 4 && cols.k_max <= 5 && ring_c->n_strips <= ring_c->n_warps &&
-                       ring_c->n_warps + 2 <= 14 && W % 2 == 0;
+                       ring_c->n_warps + 2 <= 14 && W % 2 == 0 && ring_c->n_sched < 65536;
     const RingLayout probe =
         lanes ? ring_layout<T>(W, 31, false, 0, 0, 0)
               : ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, 0);
@@ -298,7 +299,9 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       long long grid = dev.sm_count;
       if (grid > tasks) grid = tasks;
       if (lanes) {
-        auto lk = skipna ? conservative_lanes_kernel<T, true, 14> : conservative_lanes_kernel<T, false, 14>;
+        auto lk = rows.k_max <= 5
+                      ? (skipna ? conservative_lanes_kernel<T, true, 14, 5> : conservative_lanes_kernel<T, false, 14, 5>)
+                      : (skipna ? conservative_lanes_kernel<T, true, 14, 8> : conservative_lanes_kernel<T, false, 14, 8>);
         const size_t smem_l = L.total + row_tables;
         RG_CUDA(cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_l)));
         lk<<<static_cast<unsigned>(grid), warps * 32, smem_l, stream>>>(x, y, batch, xbs, xrs, ybs, cols, ring, thr,

@@ -111,6 +111,13 @@ __device__ __forceinline__ uint32_t ld_relaxed_smem(uint32_t addr) {
   return v;
 }
 __device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+// Progress flag of a consumer warp whose ring reads have already been CONSUMED (their values fed instructions
+// that precede this store in program order, so the loads have completed): a relaxed store is enough and, unlike
+// st.release (MEMBAR.ALL.CTA + STS), it does not wait for the warp's output stores still in flight.  The
+// producer turns its poll into an acquire with one fence before it lets the TMA overwrite a slot.
+__device__ __forceinline__ void st_relaxed_smem(uint32_t addr, uint32_t v) {
+  asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_smem(uint32_t addr, uint32_t v) {
   asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -143,13 +150,37 @@ template <typename T, bool SKIPNA> struct TV;
 template <typename T> struct alignas(2 * sizeof(T)) TV<T, true> { T t, v; };
 template <typename T> struct TV<T, false> { T t; };
 
-// acc += w * x and vac += w, both skipped when x is NaN: bit-identical to the reference's
-// fillna(0) / notnull() contributions (w * 0 adds nothing).
-template <typename T>
-__device__ __forceinline__ void accum_valid(T& acc, T& vac, T w, T x) {
+// acc += w * x and vac += w, both skipped when x is NaN: the reference's fillna(0) / notnull() contributions
+// (w * 0 adds nothing).  fp64: five instructions per element -- one NaN test, one 32-bit select per operand
+// (ptxas turns predicated DFMA / DADD, and the C++ `ok ? x : 0`, into a full-width select pair: 7) and the two
+// accumulates.  Only the HIGH word of a skipped value is cleared: a canonical NaN (low word 0) becomes exactly
+// 0.0; a NaN carrying payload bits in its low word becomes a denormal below 2^-1042 that can never reach the
+// rounding of a result.
+__device__ __forceinline__ void accum_valid(double& acc, double& vac, double w, double x, double& one) {
+  // valid mass: vac += w * (ok ? 1.0 : 0.0).  `one` is a caller-held scratch whose LOW word stays 0: only its
+  // high word is rewritten (one 32-bit select), so the 0 / 1 factor costs no register moves (w * 1.0 is exact)
+  asm("{\n .reg .pred p;\n .reg .b32 lo, hi, ol, oh;\n .reg .f64 xc;\n"
+      " setp.num.f64 p, %3, %3;\n"
+      " mov.b64 {lo, hi}, %3;\n selp.b32 hi, hi, 0, p;\n mov.b64 xc, {lo, hi};\n"
+      " mov.b64 {ol, oh}, %2;\n selp.b32 oh, 0x3ff00000, 0, p;\n mov.b64 %2, {ol, oh};\n"
+      " fma.rn.f64 %0, %4, xc, %0;\n fma.rn.f64 %1, %4, %2, %1;\n}"
+      : "+d"(acc), "+d"(vac), "+d"(one) : "d"(x), "d"(w));
+}
+__device__ __forceinline__ void accum_valid(float& acc, float& vac, float w, float x, float&) {
   const bool ok = (x == x);
-  acc = fma(w, ok ? x : T(0), acc);
-  vac += ok ? w : T(0);
+  acc = fmaf(w, ok ? x : 0.0f, acc);
+  vac += ok ? w : 0.0f;
+}
+// acc += w * x unless x is NaN (apply_weights with skipna=False contracts fillna(0)).
+__device__ __forceinline__ void accum_clean(double& acc, double w, double x) {
+  asm("{\n .reg .pred p;\n .reg .b32 lo, hi;\n .reg .f64 xc;\n"
+      " setp.num.f64 p, %1, %1;\n"
+      " mov.b64 {lo, hi}, %1;\n selp.b32 hi, hi, 0, p;\n mov.b64 xc, {lo, hi};\n"
+      " fma.rn.f64 %0, %2, xc, %0;\n}"
+      : "+d"(acc) : "d"(x), "d"(w));
+}
+__device__ __forceinline__ void accum_clean(float& acc, float w, float x) {
+  acc = fmaf(w, (x == x) ? x : 0.0f, acc);
 }
 
 // Latitude contraction of the CNT taps of one output for one strip of source columns
@@ -178,11 +209,6 @@ __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row
     if (slot < 0) slot += ring_slots;
     rowp[i] = s_ring + slot * row_stride;
   }
-  // valid mass of a column without NaNs: the taps' weights summed in tap order
-  T wsum = T(0);
-#pragma unroll
-  for (int i = 0; i < CNT; ++i) wsum += w[i];
-
   for (int q = lane * VEC; q < ncols; q += 32 * VEC) {
     int j = col0 + q;
     if (j >= W) j -= W;  // strips may wrap around the date line
@@ -190,26 +216,27 @@ __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row
 #pragma unroll
     for (int i = 0; i < CNT; ++i)
       val[i] = *reinterpret_cast<const Pack<T, VEC>*>(rowp[i] + j * static_cast<int>(sizeof(T)));
-    // Fast path: contract as if nothing were missing.  The result is NaN iff some tap is NaN (or
-    // infinities cancel); only then redo the group with per-tap NaN handling.  For NaN-free groups
-    // this is bit-identical to the slow path (a valid tap adds w * x and w in the same order).
-    T acc[VEC], vac[VEC];
-    bool redo = false;
+    // One pass: a NaN tap is skipped by predication (value mass and valid mass), see accum_valid.
+    T acc[VEC], vac[VEC], one[VEC];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      acc[e] = T(0);
-#pragma unroll
-      for (int i = 0; i < CNT; ++i) acc[e] = fma(w[i], val[i].v[e], acc[e]);
-      vac[e] = wsum;
-      if (SKIPNA || zero_fill) redo |= (acc[e] != acc[e]);
-    }
-    if (redo) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) { acc[e] = T(0); vac[e] = T(0); }
+    for (int e = 0; e < VEC; ++e) { acc[e] = T(0); vac[e] = T(0); one[e] = T(0); }
+    if constexpr (SKIPNA) {
 #pragma unroll
       for (int i = 0; i < CNT; ++i) {
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) accum_valid(acc[e], vac[e], w[i], val[i].v[e]);
+        for (int e = 0; e < VEC; ++e) accum_valid(acc[e], vac[e], w[i], val[i].v[e], one[e]);
+      }
+    } else if (zero_fill) {
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) accum_clean(acc[e], w[i], val[i].v[e]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = fma(w[i], val[i].v[e], acc[e]);
       }
     }
 #pragma unroll
@@ -432,11 +459,16 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
 // the two contractions fuse in registers: lane m of a strip's warp contracts ITS OWN 4 source columns along
 // latitude (two 2-column vector loads per row tap straight out of the TMA ring), fetches the 5th column's
 // {t, v} from lane m + 1 with a shuffle, and finishes the longitude contraction, normalisation, mask and
-// store.  No strip buffer, no __syncwarp, one pass per target row: ~1/3 of the instructions and 2/3 of the
-// shared-memory traffic of the two-phase kernel.  Lane nl (one past the strip's last target) only produces
+// store.  No strip buffer, one pass per target row.  Lane nl (one past the strip's last target) only produces
 // the halo column.  Lanes alternate which of their two column pairs they read first (bit SWZ of the lane id)
 // so that a 2-column load of 8 (fp64) / 16 (fp32) neighbouring lanes touches every bank exactly once.
 // Eligibility is decided on the host (rg_row_ring_t.lane_cols == 4).
+//
+// Per target row and lane (round 2): 3 instructions per source element (NaN test + predicated FMA + predicated
+// add, no second "redo" pass: with 1 % scattered NaNs practically every warp took it), ring slots of the row
+// taps read from a per-row byte table staged at kernel start (slot = table byte + the task's ring rotation,
+// one PRMT + one VIADDMNMX per tap instead of nine integer instructions), RMAX row taps at most (5 for the
+// 4:1 grids: 8-tap bands use the RMAX = 8 instance; the 5-tap one has no spills).
 template <typename T> struct Pair2 { T a, b; };
 __device__ __forceinline__ Pair2<double> lds_pair(uint32_t addr, double) {
   Pair2<double> r;
@@ -449,12 +481,16 @@ __device__ __forceinline__ Pair2<float> lds_pair(uint32_t addr, float) {
   return r;
 }
 
-// Latitude contraction of CNT row taps for the lane's two column pairs (A at offA, B at offB bytes into a
-// ring row).  t* = sum w x (NaN-cleaned when SKIPNA), v* = valid mass.
-template <typename T, bool SKIPNA, int CNT>
-__device__ __forceinline__ void lane_phase1(uint32_t ring0, int row_stride, int ring_slots, int newest,
-                                            uint32_t back, uint32_t wk_addr, uint32_t offA, uint32_t offB,
-                                            T (&t)[4], T (&v)[4], int zero_fill) {
+constexpr int kLaneNanPropagate = 0, kLaneNanSkip = 1, kLaneNanZero = 2;
+
+// Latitude contraction of CNT row taps for the lane's two column pairs (A at baseA, B at baseB: ring base +
+// the lane's byte offset into a ring row).  slots03 / slots47: ring slot of tap i in byte i (before wrap: the
+// table byte + the task's rotation, < 2 * ring_slots).  t* = sum w x (NaN-cleaned unless MODE propagates),
+// v* = valid mass (MODE skip only).
+template <typename T, int MODE, int CNT>
+__device__ __forceinline__ void lane_phase1(uint32_t baseA, uint32_t baseB, uint32_t row_stride,
+                                            uint32_t ring_slots, uint32_t slots03, uint32_t slots47,
+                                            uint32_t wk_addr, T (&t)[4], T (&v)[4], T (&one)[4]) {
   constexpr int N = CNT > 0 ? CNT : 1;
   T w[N];
 #pragma unroll
@@ -466,42 +502,61 @@ __device__ __forceinline__ void lane_phase1(uint32_t ring0, int row_stride, int 
   Pair2<T> xa[N], xb[N];
 #pragma unroll
   for (int i = 0; i < CNT; ++i) {
-    int slot = newest - static_cast<int>((back >> (4 * i)) & 15u);  // rows back from the newest landed row
-    if (slot < 0) slot += ring_slots;
-    const uint32_t row = ring0 + static_cast<uint32_t>(slot * row_stride);
-    xa[i] = lds_pair(row + offA, T(0));
-    xb[i] = lds_pair(row + offB, T(0));
+    uint32_t slot = __byte_perm(i < 4 ? slots03 : slots47, 0u, 0x4440u + static_cast<uint32_t>(i & 3));
+    slot = min(slot, slot - ring_slots);  // unsigned: wraps to slot when slot < ring_slots
+    xa[i] = lds_pair(baseA + slot * row_stride, T(0));
+    xb[i] = lds_pair(baseB + slot * row_stride, T(0));
   }
-  T wsum = T(0);
 #pragma unroll
-  for (int i = 0; i < CNT; ++i) wsum += w[i];
-  // fast path: contract as if nothing were missing; a NaN result flags a missing tap (or inf - inf)
-#pragma unroll
-  for (int e = 0; e < 4; ++e) { t[e] = T(0); v[e] = wsum; }
+  for (int e = 0; e < 4; ++e) { t[e] = T(0); v[e] = T(0); }
 #pragma unroll
   for (int i = 0; i < CNT; ++i) {
-    t[0] = fma(w[i], xa[i].a, t[0]);
-    t[1] = fma(w[i], xa[i].b, t[1]);
-    t[2] = fma(w[i], xb[i].a, t[2]);
-    t[3] = fma(w[i], xb[i].b, t[3]);
-  }
-  if (SKIPNA || zero_fill) {
-    const bool redo = (t[0] != t[0]) | (t[1] != t[1]) | (t[2] != t[2]) | (t[3] != t[3]);
-    if (redo) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { t[e] = T(0); v[e] = T(0); }
-#pragma unroll
-      for (int i = 0; i < CNT; ++i) {
-        accum_valid(t[0], v[0], w[i], xa[i].a);
-        accum_valid(t[1], v[1], w[i], xa[i].b);
-        accum_valid(t[2], v[2], w[i], xb[i].a);
-        accum_valid(t[3], v[3], w[i], xb[i].b);
-      }
+    if constexpr (MODE == kLaneNanSkip) {
+      accum_valid(t[0], v[0], w[i], xa[i].a, one[0]);
+      accum_valid(t[1], v[1], w[i], xa[i].b, one[1]);
+      accum_valid(t[2], v[2], w[i], xb[i].a, one[2]);
+      accum_valid(t[3], v[3], w[i], xb[i].b, one[3]);
+    } else if constexpr (MODE == kLaneNanZero) {
+      accum_clean(t[0], w[i], xa[i].a);
+      accum_clean(t[1], w[i], xa[i].b);
+      accum_clean(t[2], w[i], xb[i].a);
+      accum_clean(t[3], w[i], xb[i].b);
+    } else {
+      t[0] = fma(w[i], xa[i].a, t[0]);
+      t[1] = fma(w[i], xa[i].b, t[1]);
+      t[2] = fma(w[i], xb[i].a, t[2]);
+      t[3] = fma(w[i], xb[i].b, t[3]);
     }
   }
 }
 
-template <typename T, bool SKIPNA, int MAXWARPS>
+template <typename T, int MODE, int RMAX>
+__device__ __forceinline__ void lane_phase1_dispatch(int cnt, uint32_t baseA, uint32_t baseB, uint32_t row_stride,
+                                                     uint32_t ring_slots, uint32_t slots03, uint32_t slots47,
+                                                     uint32_t wk, T (&t)[4], T (&v)[4], T (&one)[4]) {
+#define RG_L1(C)                                                                                         \
+  case C:                                                                                                \
+    lane_phase1<T, MODE, C>(baseA, baseB, row_stride, ring_slots, slots03, slots47, wk, t, v, one);      \
+    break;
+  if constexpr (RMAX <= 5) {
+    switch (cnt) {
+      RG_L1(0) RG_L1(1) RG_L1(2) RG_L1(3) RG_L1(4)
+      default:
+        lane_phase1<T, MODE, 5>(baseA, baseB, row_stride, ring_slots, slots03, slots47, wk, t, v, one);
+        break;
+    }
+  } else {
+    switch (cnt) {
+      RG_L1(0) RG_L1(1) RG_L1(2) RG_L1(3) RG_L1(4) RG_L1(5) RG_L1(6) RG_L1(7)
+      default:
+        lane_phase1<T, MODE, 8>(baseA, baseB, row_stride, ring_slots, slots03, slots47, wk, t, v, one);
+        break;
+    }
+  }
+#undef RG_L1
+}
+
+template <typename T, bool SKIPNA, int MAXWARPS, int RMAX>
 __global__ void __launch_bounds__(MAXWARPS * 32, 1)
 conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
                           long long xrs, long long ybs, Band<T> cols, RingDev ring, T thr, int ring_slots,
@@ -523,7 +578,20 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
     fence_mbar_init();
   }
   if (tid < 32) s_flags[tid] = 0;
-  for (int i = tid; i < n_rows_out; i += blockDim.x) s_krec[i] = ring.krec[i];
+  // the host record {need, release, kcnt, 8 x 4-bit rows-back} becomes {need | release << 16, kcnt,
+  // 8 x 8-bit ring slot of the tap relative to the run's first row}: the per-row path only adds the rotation
+  for (int i = tid; i < n_rows_out; i += blockDim.x) {
+    const int4 r = ring.krec[i];
+    const int cnt = r.z > 0 ? r.z : 0;
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int tp = 0; tp < kRingMaxTaps; ++tp) {
+      const int pos = r.x - 1 - static_cast<int>((static_cast<uint32_t>(r.w) >> (4 * tp)) & 15u);
+      const uint32_t sl = (tp < cnt && pos >= 0) ? static_cast<uint32_t>(pos % ring_slots) : 0u;
+      if (tp < 4) lo |= sl << (8 * tp); else hi |= sl << (8 * (tp - 4));
+    }
+    s_krec[i] = make_int4(r.x | (r.y << 16), r.z, static_cast<int>(lo), static_cast<int>(hi));
+  }
   for (int i = tid; i < n_rows_out * kRingMaxTaps; i += blockDim.x) s_wrec[i] = static_cast<const T*>(ring.wrec)[i];
   int32_t* s_sched = reinterpret_cast<int32_t*>(s_wrec + static_cast<size_t>(n_rows_out) * kRingMaxTaps);
   for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
@@ -558,7 +626,8 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   int jA = cfirst + 2 * swz, jB = cfirst + 2 * (1 - swz);
   jA %= W;
   jB %= W;
-  const uint32_t offA = static_cast<uint32_t>(jA) * sizeof(T), offB = static_cast<uint32_t>(jB) * sizeof(T);
+  const uint32_t baseA = ring0 + static_cast<uint32_t>(jA) * sizeof(T);
+  const uint32_t baseB = ring0 + static_cast<uint32_t>(jB) * sizeof(T);
   // longitude taps of this lane's target: weights in register order {A.a, A.b, B.a, B.b, neighbour}
   const int ccnt = (has_strip && lane < nl && cols.cover[l]) ? cols.cnt[l] : -1;
   T tw[5];
@@ -567,44 +636,56 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   const T twA0 = swz ? tw[2] : tw[0], twA1 = swz ? tw[3] : tw[1];
   const T twB0 = swz ? tw[0] : tw[2], twB1 = swz ? tw[1] : tw[3];
   const T tw4 = tw[4];
-  const bool padded = ccnt >= 0 && ccnt < 5;  // zero-weight taps must not see the data (0 * NaN)
+  // zero-weight taps must not see the data (0 * NaN) -- only where NaNs survive the latitude pass
+  const bool padded = !SKIPNA && !ring.zero_fill && ccnt >= 0 && ccnt < 5;
+  const bool zero_fill = !SKIPNA && ring.zero_fill;
+  const bool writer = lane < nl;
+  T* const ylane = y + l0 + lane;
 
   const uint32_t wrec0 = smem_u32(s_wrec);
-  uint32_t gbase = 0;    // ring position of the current run's first row
-  uint32_t newest_g = 0; // ring position + 1 of the newest row needed so far
-  int newest = ring_slots - 1;
+  const uint32_t row_stride = static_cast<uint32_t>(L.row_stride), slots = static_cast<uint32_t>(ring_slots);
+  // 0 / 1 factors of accum_valid, one register pair per column for the whole kernel.  Their low words are zeros
+  // READ from shared memory (an unused flag word): a zero the compiler cannot see through stays in its register
+  // instead of being rematerialised in front of every use.
+  T one[4];
+  {
+    uint32_t z;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(z) : "r"(flags0 + 124u));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if constexpr (sizeof(T) == 8) one[e] = __hiloint2double(static_cast<int>(z), static_cast<int>(z));
+      else one[e] = __uint_as_float(z);
+    }
+  }
+  uint32_t gbase = 0;  // ring position of the current run's first row
+  uint32_t rot = 0;    // gbase % ring_slots
 
   for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
     const int run = static_cast<int>(task % ring.n_runs);
     const long long b = task / ring.n_runs;
     const int k0 = ring.run_first[run], k1 = ring.run_first[run + 1];
-    for (int k = k0; k < k1; ++k) {
-      const int4 rec = s_krec[k];  // {need, release, kcnt (-1: latitude not covered), packed tap_back}
-      const uint32_t need_g = gbase + static_cast<uint32_t>(rec.x);
-      const int cnt = rec.z > 0 ? rec.z : 0;
+    const uint32_t rot4 = rot * 0x01010101u;
+    T* yrow = ylane + b * ybs + static_cast<long long>(k0) * Wo;
+    for (int k = k0; k < k1; ++k, yrow += Wo) {
+      const int4 rec = s_krec[k];  // {need | release << 16, kcnt (-1: latitude not covered), slots 0-3, slots 4-7}
+      const uint32_t need_g = gbase + (static_cast<uint32_t>(rec.x) & 0xffffu);
+      const int cnt = rec.y > 0 ? rec.y : 0;
       while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(100);
-      newest += static_cast<int>(need_g - newest_g);
-      newest_g = need_g;
-      if (newest >= ring_slots) newest -= ring_slots;
 
       const uint32_t wk = wrec0 + static_cast<uint32_t>(k) * (kRingMaxTaps * sizeof(T));
+      const uint32_t s03 = static_cast<uint32_t>(rec.z) + rot4, s47 = static_cast<uint32_t>(rec.w) + rot4;
       T t[4], v[4];
-#define RG_L1(C)                                                                                              \
-  case C:                                                                                                     \
-    lane_phase1<T, SKIPNA, C>(ring0, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk, offA, \
-                              offB, t, v, ring.zero_fill);                                                    \
-    break;
-      switch (cnt) {
-        RG_L1(0) RG_L1(1) RG_L1(2) RG_L1(3) RG_L1(4) RG_L1(5) RG_L1(6) RG_L1(7)
-        default:
-          lane_phase1<T, SKIPNA, 8>(ring0, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk,
-                                    offA, offB, t, v, ring.zero_fill);
-          break;
+      if constexpr (SKIPNA) {
+        lane_phase1_dispatch<T, kLaneNanSkip, RMAX>(cnt, baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);
+      } else {
+        if (zero_fill)
+          lane_phase1_dispatch<T, kLaneNanZero, RMAX>(cnt, baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);
+        else
+          lane_phase1_dispatch<T, kLaneNanPropagate, RMAX>(cnt, baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);
       }
-#undef RG_L1
       // every value this warp needs from the rows that die after this output is now in registers
       __syncwarp();
-      if (lane == 0) st_release_smem(flags0 + 4u * (1 + warp), gbase + static_cast<uint32_t>(rec.y));
+      if (lane == 0) st_relaxed_smem(flags0 + 4u * (1 + warp), gbase + (static_cast<uint32_t>(rec.x) >> 16));
 
       // the 5th tap is the first column of the next lane's group
       const T t_first = swz ? t[2] : t[0];
@@ -614,9 +695,9 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
         const T v_first = swz ? v[2] : v[0];
         vn = __shfl_down_sync(0xffffffffu, v_first, 1);
       }
-      if (lane < nl) {
+      if (writer) {
         T out = nan;
-        if (rec.z >= 0 && ccnt >= 0) {
+        if (rec.y >= 0 && ccnt >= 0) {
           T e0 = t[0], e1 = t[1], e2 = t[2], e3 = t[3], e4 = tn;
           if (padded) {
             e0 = twA0 != T(0) ? e0 : T(0);
@@ -641,10 +722,12 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
             out = so;
           }
         }
-        st_stream(y + b * ybs + static_cast<long long>(k) * Wo + l0 + lane, out);
+        st_stream(yrow, out);
       }
     }
-    gbase += static_cast<uint32_t>(ring.run_sched[run + 1] - ring.run_sched[run]);
+    const uint32_t run_len = static_cast<uint32_t>(ring.run_sched[run + 1] - ring.run_sched[run]);
+    gbase += run_len;
+    rot = (rot + run_len) % slots;
   }
 }
 
