@@ -16,6 +16,7 @@ int device_info(DeviceInfo* out) {
   DeviceInfo info;
   RG_CUDA(cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev));
   RG_CUDA(cudaDeviceGetAttribute(&info.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  RG_CUDA(cudaDeviceGetAttribute(&info.max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
   if (dev >= 0 && dev < 64) {
     cache[dev] = info;
     have[dev] = true;

@@ -18,7 +18,8 @@ namespace rg {
 // ---------------------------------------------------------------- device info (cached)
 struct DeviceInfo {
   int sm_count;
-  int max_smem_optin;
+  int max_smem_optin;  // per CTA
+  int max_smem_sm;     // per SM
 };
 int device_info(DeviceInfo* out);  // defined in api.cu
 

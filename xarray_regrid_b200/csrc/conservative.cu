@@ -251,8 +251,13 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     // load order (4 bytes per scheduled row) in shared memory
     const size_t row_tables = static_cast<size_t>(rows.n_out) * (16 + kRingMaxTaps * sizeof(T)) +
                               static_cast<size_t>(ring_c->n_sched) * sizeof(int32_t);
-    const long long room = static_cast<long long>(dev.max_smem_optin) - static_cast<long long>(probe.total) -
-                           static_cast<long long>(row_tables);
+    // fp32 rows carry half the bytes of fp64 ones, so a target row leaves only half the time to walk the same
+    // per-row dependency chain: the register-resident kernel then runs TWO CTAs per SM (two independent row
+    // pipelines, each with half of the shared memory: its 64 registers per thread allow it)
+    const bool two_ctas = lanes && sizeof(T) == 4;
+    const long long smem_budget = two_ctas ? (static_cast<long long>(dev.max_smem_sm) / 2 - 1024)
+                                           : static_cast<long long>(dev.max_smem_optin);
+    const long long room = smem_budget - static_cast<long long>(probe.total) - static_cast<long long>(row_tables);
     int slots = room > 0 ? static_cast<int>(room / probe.row_stride) : 0;
     if (slots > kRingMaxSlots) slots = kRingMaxSlots;
     if (slots >= ring_c->max_live + 1 && slots >= 2) {
@@ -296,7 +301,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       }
 #undef RG_PICK
       const long long tasks = static_cast<long long>(batch) * ring.n_runs;
-      long long grid = dev.sm_count;
+      long long grid = static_cast<long long>(dev.sm_count) * (two_ctas ? 2 : 1);
       if (grid > tasks) grid = tasks;
       if (lanes) {
         auto lk = rows.k_max <= 5

@@ -653,9 +653,43 @@ __device__ __forceinline__ uint32_t onehot(uint32_t label) {
 
 #include "csa_networks.inc"  // csa_sum<N>(m, s): generated Wallace trees (tools/gen_csa.py)
 
-constexpr int kPlanes = 12;  // counters up to 4095 per label and cell (the launcher checks the cell size)
+// Round 2: (1) byte labels get their one-hot mask from a 256-entry shared-memory table (an LDS on the
+// otherwise idle load pipe instead of a shift on the ALU pipe, which bounds this kernel; the table also maps
+// ANY list of <= 32 byte labels to positions, not just 0..n-1); (2) two rows of the cell feed ONE adder tree,
+// so the ripple into the counter planes runs once per two rows; (3) PLANES = 10 when a cell holds <= 1023
+// elements (12 otherwise).
+constexpr int kPlanesMax = 12;  // counters up to 4095 per label and cell (the launcher checks the cell size)
 
-template <typename Tin, typename Tout, int NIN>
+// one-hot masks of one row segment of this lane's cell (columns past the cell's width contribute nothing)
+template <typename Tin, int NIN>
+__device__ __forceinline__ void row_masks(const Tin* rowbase, const Tin* trow, int nc, const uint32_t* pad,
+                                          const uint32_t* s_tab, uint32_t* m) {
+  if constexpr (sizeof(Tin) == 1) {
+    // byte labels: read the segment as aligned words, realign with funnel shifts, pick bytes at compile-time
+    // positions and look the mask up; bytes outside the label list (and the 0xff padding) map to 0
+    const int pos = static_cast<int>(trow - rowbase);
+    const uint32_t* wrow = reinterpret_cast<const uint32_t*>(rowbase) + (pos >> 2);
+    const int shb = (pos & 3) * 8;
+    constexpr int NW = (NIN + 3) / 4;
+    uint32_t wv[NW + 1];
+#pragma unroll
+    for (int q = 0; q <= NW; ++q) wv[q] = wrow[q];
+    uint32_t al[NW];
+#pragma unroll
+    for (int q = 0; q < NW; ++q) al[q] = __funnelshift_r(wv[q], wv[q + 1], shb) | pad[q];
+#pragma unroll
+    for (int c = 0; c < NIN; ++c) m[c] = s_tab[__byte_perm(al[c >> 2], 0, 0x4440 + (c & 3))];
+  } else {
+#pragma unroll
+    for (int c = 0; c < NIN; ++c) {
+      const Tin t = trow[c];
+      const uint32_t v = (t >= Tin(0) && t < Tin(32)) ? static_cast<uint32_t>(t) : 32u;
+      m[c] = (c < nc) ? onehot(v) : 0u;
+    }
+  }
+}
+
+template <typename Tin, typename Tout, int NIN, int PLANES>
 __global__ void __launch_bounds__(kLaneThreads, 3)
 mode_planes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long batch, long long xbs, long long xrs,
                    long long ybs, Bins rows, Bins cols, const Tin* __restrict__ values, int n_values, int anti,
@@ -663,6 +697,16 @@ mode_planes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long ba
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Tin* stage = reinterpret_cast<Tin*>(smem) + static_cast<size_t>(warp) * 2 * stage_rows * stage_elems;
+  // label byte -> one-hot of its position in `values` (0 for bytes that are not listed), after the staging buffers
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(
+      smem + (static_cast<size_t>(kLaneWarps) * 2 * stage_rows * stage_elems * sizeof(Tin) + 15) / 16 * 16);
+  if constexpr (sizeof(Tin) == 1) {
+    for (int i = tid; i < 256; i += kLaneThreads) s_tab[i] = 0u;
+    __syncthreads();
+    if (tid == 0)
+      for (int i = 0; i < n_values && i < 32; ++i) s_tab[static_cast<uint8_t>(values[i])] = 1u << i;
+    __syncthreads();
+  }
   const int Wo = cols.n_out;
   const int strips = (Wo + 31) / 32;
   const long long tasks = batch * rows.n_out * strips;
@@ -688,9 +732,9 @@ mode_planes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long ba
     const bool contiguous = cols.src_step == 1 && s0 + ncol <= cols.n_src;
     const int row_first = src_index(rows, r0);
 
-    uint32_t plane[kPlanes];
+    uint32_t plane[PLANES];
 #pragma unroll
-    for (int q = 0; q < kPlanes; ++q) plane[q] = 0;
+    for (int q = 0; q < PLANES; ++q) plane[q] = 0;
     // byte labels: columns past this lane's cell width are forced to 0xff (one-hot of 255 = 0), one OR per
     // word instead of a compare + select per element
     constexpr int kPadWords = (NIN + 3) / 4;
@@ -747,46 +791,34 @@ mode_planes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long ba
       __syncwarp();
       const Tin* buf = stage + (ch & 1) * stage_rows * stage_elems;
       const int rb = ch * stage_rows, nrb = min(stage_rows, nr - rb);
-      for (int r = 0; r < nrb; ++r) {
-        int sh = 0;  // the row's 16-byte phase (see stage_row)
+      for (int r = 0; r < nrb; r += 2) {
+        const bool two = r + 1 < nrb;
+        int sh0 = 0, sh1 = 0;  // the rows' 16-byte phases (see stage_row)
         if (contiguous) {
-          sh = pb_cons / static_cast<int>(sizeof(Tin));
+          sh0 = pb_cons / static_cast<int>(sizeof(Tin));
           pb_cons = (pb_cons + rsb16) & 15;
-        }
-        const Tin* trow = buf + r * stage_elems + sh + c0;
-        // one-hot masks of this lane's row segment (columns past the cell's width contribute nothing)
-        uint32_t m[NIN];
-        if constexpr (sizeof(Tin) == 1) {
-          // byte labels: read the segment as aligned words, realign with funnel shifts, pick bytes at
-          // compile-time positions; a byte >= 32 (or a negative int8) shifts the 1 out: no range checks
-          const int pos = static_cast<int>(trow - (buf + r * stage_elems));
-          const uint32_t* wrow = reinterpret_cast<const uint32_t*>(buf + r * stage_elems) + (pos >> 2);
-          const int shb = (pos & 3) * 8;
-          constexpr int NW = (NIN + 3) / 4;
-          uint32_t wv[NW + 1];
-#pragma unroll
-          for (int q = 0; q <= NW; ++q) wv[q] = wrow[q];
-          uint32_t al[NW];
-#pragma unroll
-          for (int q = 0; q < NW; ++q) al[q] = __funnelshift_r(wv[q], wv[q + 1], shb) | pad[q];
-#pragma unroll
-          for (int c = 0; c < NIN; ++c) m[c] = onehot(__byte_perm(al[c >> 2], 0, 0x4440 + (c & 3)));
-        } else {
-#pragma unroll
-          for (int c = 0; c < NIN; ++c) {
-            const Tin t = trow[c];
-            const uint32_t v = (t >= Tin(0) && t < Tin(32)) ? static_cast<uint32_t>(t) : 32u;
-            m[c] = (c < nc) ? onehot(v) : 0u;
+          if (two) {
+            sh1 = pb_cons / static_cast<int>(sizeof(Tin));
+            pb_cons = (pb_cons + rsb16) & 15;
           }
         }
-        // carry-save adder tree: 6-bit sums per label position
-        uint32_t s[6];
-        csa_sum<NIN>(m, s);
-        // ripple the 6-bit column sums into the planes
+        const Tin* base0 = buf + r * stage_elems;
+        uint32_t sum[7];
+        if (two) {  // two rows of the cell through one carry-save adder tree: 7-bit sums per label position
+          uint32_t m[2 * NIN];
+          row_masks<Tin, NIN>(base0, base0 + sh0 + c0, nc, pad, s_tab, m);
+          row_masks<Tin, NIN>(base0 + stage_elems, base0 + stage_elems + sh1 + c0, nc, pad, s_tab, m + NIN);
+          csa_sum<2 * NIN>(m, sum);
+        } else {
+          uint32_t m[NIN];
+          row_masks<Tin, NIN>(base0, base0 + sh0 + c0, nc, pad, s_tab, m);
+          csa_sum<NIN>(m, sum);
+        }
+        // ripple the column sums into the planes
         uint32_t carry = 0;
 #pragma unroll
-        for (int q = 0; q < kPlanes; ++q) {
-          const uint32_t add = q < 6 ? s[q] : 0u;
+        for (int q = 0; q < PLANES; ++q) {
+          const uint32_t add = q < 7 ? sum[q] : 0u;
           const uint32_t nc_ = maj3(plane[q], add, carry);
           plane[q] = xor3(plane[q], add, carry);
           carry = nc_;
@@ -802,7 +834,7 @@ mode_planes_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long ba
     if (row_ok && in && cols.cover[l]) {
       uint32_t cand = label_mask;
 #pragma unroll
-      for (int q = kPlanes - 1; q >= 0; --q) {
+      for (int q = PLANES - 1; q >= 0; --q) {
         const uint32_t t = cand & (anti ? ~plane[q] : plane[q]);
         cand = t ? t : cand;
       }
@@ -1098,22 +1130,30 @@ int mode_launch(const void* x, void* y, int64_t batch, int64_t xbs, int64_t xrs,
   DeviceInfo dev;
   rc = device_info(&dev);
   if (rc != RG_OK) return rc;
-  // ---- fastest path: <= 32 dense labels, cells of <= 32 columns: bit-sliced counters in registers
-  if (dense && n_values <= 32 && strip_elems > 0 && max_bin_cols > 0 && max_bin_cols <= 32 && max_bin_rows > 0 &&
-      static_cast<long long>(max_bin_rows) * max_bin_cols <= (1 << kPlanes) - 1) {
+  // ---- fastest path: <= 32 labels (dense 0..n-1, or ANY list when the labels are bytes: the kernel's lookup
+  //      table maps them), cells of <= 32 columns: bit-sliced counters in registers
+  const long long cell_pop = static_cast<long long>(max_bin_rows) * max_bin_cols;
+  if ((dense || sizeof(Tin) == 1) && n_values <= 32 && strip_elems > 0 && max_bin_cols > 0 && max_bin_cols <= 32 &&
+      max_bin_rows > 0 && cell_pop <= (1 << kPlanesMax) - 1) {
     const int stage_elems = (strip_elems + 48 + 15) / 16 * 16;
-    // two staging buffers per warp; three CTAs per SM (80 registers) share the shared memory
+    // two staging buffers per warp; three CTAs per SM share the shared memory; an even number of rows per buffer
+    // (the kernel feeds row pairs into one adder tree)
     int stage_rows = static_cast<int>((56 * 1024) / (static_cast<size_t>(kLaneWarps) * 2 * stage_elems * sizeof(Tin)));
     if (stage_rows > 8) stage_rows = 8;
+    if (stage_rows > 1) stage_rows &= ~1;
     if (stage_rows >= 1) {
-      const size_t smem_p = static_cast<size_t>(kLaneWarps) * 2 * stage_rows * stage_elems * sizeof(Tin);
+      const size_t smem_p = (static_cast<size_t>(kLaneWarps) * 2 * stage_rows * stage_elems * sizeof(Tin) + 15) / 16 * 16 +
+                            256 * sizeof(uint32_t);
       using PK = void (*)(const Tin*, Tout*, long long, long long, long long, long long, Bins, Bins, const Tin*,
                           int, int, Tout, int, int);
-      PK kp = max_bin_cols <= 8    ? mode_planes_kernel<Tin, Tout, 8>
-              : max_bin_cols <= 16 ? mode_planes_kernel<Tin, Tout, 16>
-              : max_bin_cols <= 25 ? mode_planes_kernel<Tin, Tout, 25>
-              : max_bin_cols <= 26 ? mode_planes_kernel<Tin, Tout, 26>
-                                   : mode_planes_kernel<Tin, Tout, 32>;
+      const bool few = cell_pop <= 1023;
+#define RG_MP(N) (few ? mode_planes_kernel<Tin, Tout, N, 10> : mode_planes_kernel<Tin, Tout, N, 12>)
+      PK kp = max_bin_cols <= 8    ? RG_MP(8)
+              : max_bin_cols <= 16 ? RG_MP(16)
+              : max_bin_cols <= 25 ? RG_MP(25)
+              : max_bin_cols <= 26 ? RG_MP(26)
+                                   : RG_MP(32);
+#undef RG_MP
       if (smem_p > 48 * 1024)
         RG_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_p)));
       int per_sm_p = 0;
