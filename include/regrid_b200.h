@@ -351,6 +351,8 @@ typedef struct rg_bins {
   int32_t n_src;
   int32_t src_offset;
   int32_t src_step;
+  int32_t uniform_count; /* the count of EVERY covered bin when they are all equal (regular grids), else 0:
+                            lets the register-resident mode kernel drop its per-cell width masks */
 } rg_bins_t;
 
 /*

@@ -65,6 +65,7 @@ class rg_bins_t(C.Structure):  # noqa: N801 - mirrors the C name
         ("n_src", C.c_int32),
         ("src_offset", C.c_int32),
         ("src_step", C.c_int32),
+        ("uniform_count", C.c_int32),
     ]
 
 

@@ -809,8 +809,11 @@ class DeviceBins:
         self.start, self.count = up(bins.start, np.int32), up(bins.count, np.int32)
         self.cover, self.out_index = up(bins.cover, np.uint8), up(bins.out_index, np.int32)
         self.gather = None if bins.gather is None else up(bins.gather, np.int64)
+        covered = bins.count[bins.cover > 0]
+        uniform = int(covered[0]) if covered.size and bool((covered == covered[0]).all()) else 0
         self.c = rg_bins_t(self.start.data_ptr(), self.count.data_ptr(), self.cover.data_ptr(),
-                           self.out_index.data_ptr(), bins.n_out, bins.n_src, bins.src_offset, bins.src_step)
+                           self.out_index.data_ptr(), bins.n_out, bins.n_src, bins.src_offset, bins.src_step,
+                           uniform)
 
     @property
     def ref(self):
