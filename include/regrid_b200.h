@@ -116,6 +116,15 @@ typedef struct rg_band {
  *                                    both are multiples of 16 / sizeof(element)
  *   strip_cols_max                   max over s of strip_nc[s]
  *
+ * Column panels (two-phase kernel): the strips are grouped into `n_panels` panels of consecutive strips; a CTA
+ * works on ONE panel of a (slab, run) unit, its ring rows hold only the panel's source columns
+ *   panel_c0[p] .. panel_c0[p] + panel_nc[p] - 1   (modulo n_src; two bulk copies when the range wraps)
+ * and consumer warp w owns strip panel_strip0[p] + w (n_warps = the largest number of strips in a panel).
+ * strip_c0 is RELATIVE to the panel's first column.  Short panel rows let several CTAs -- independent row
+ * pipelines -- share an SM, which is what grids with few source rows per target row (coarsening ratios of
+ * 2 - 2.5) and rows wider than one CTA's shared memory (0.1 degree) need.  One panel covering the whole row
+ * (panel_c0 = 0, panel_nc = n_src) is the classic layout; the register-resident kernel requires it.
+ *
  * Passing NULL selects the generic kernel (any band, pole rows, unaligned rows).
  */
 typedef struct rg_row_ring {
@@ -138,6 +147,11 @@ typedef struct rg_row_ring {
                         even and grows by exactly 4 from one target to the next inside a strip, every strip has
                         <= 31 targets, all covered, and n_strips <= n_warps: the kernel then keeps both
                         contractions in registers (one lane per target column).  0: no such structure. */
+  const int32_t* panel_strip0; /* device, [n_panels + 1] */
+  const int32_t* panel_c0;     /* device, [n_panels]     */
+  const int32_t* panel_nc;     /* device, [n_panels]     */
+  int32_t n_panels;            /* >= 1 */
+  int32_t panel_cols_max;      /* max over p of panel_nc[p] */
 } rg_row_ring_t;
 
 /*

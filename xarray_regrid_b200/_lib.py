@@ -52,6 +52,11 @@ class rg_row_ring_t(C.Structure):  # noqa: N801 - mirrors the C name
         ("strip_cols_max", C.c_int32),
         ("n_warps", C.c_int32),
         ("lane_cols", C.c_int32),
+        ("panel_strip0", C.c_void_p),
+        ("panel_c0", C.c_void_p),
+        ("panel_nc", C.c_void_p),
+        ("n_panels", C.c_int32),
+        ("panel_cols_max", C.c_int32),
     ]
 
 

@@ -240,30 +240,45 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       ring_c->sched_row && ring_c->krec && ring_c->wrec && ring_c->run_first && ring_c->run_sched &&
       ring_c->strip_l0 && ring_c->strip_c0 && ring_c->strip_nc) {
     const int kw = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : cols.k_max <= 3 ? 3 : cols.k_max <= 5 ? 5 : 8;
+    // column panels (a missing table = one panel covering the whole row)
+    const bool have_panels = ring_c->n_panels >= 1 && ring_c->panel_strip0 && ring_c->panel_c0 && ring_c->panel_nc;
+    const int n_panels = have_panels ? ring_c->n_panels : 1;
+    const int wp = have_panels ? ring_c->panel_cols_max : W;  // columns of a ring row
     // lane-owned columns variant (4 source columns + 1 per target, see conservative_ring.cuh): no strip buffers
     // (the staged per-row record packs need / release into 16 bits each)
     const bool lanes = ring_c->lane_cols == 4 && cols.k_max <= 5 && ring_c->n_strips <= ring_c->n_warps &&
-                       ring_c->n_warps + 2 <= 14 && W % 2 == 0 && ring_c->n_sched < 65536;
+                       ring_c->n_warps + 2 <= 14 && W % 2 == 0 && ring_c->n_sched < 65536 && n_panels == 1 && wp == W;
+    // panel layouts of the two-phase kernel: 6 consumer warps, several CTAs per SM
+    const bool panel_cta = !lanes && have_panels && ring_c->n_warps <= 6;
+    const int min_ctas = lanes ? (sizeof(T) == 4 ? 2 : 1) : panel_cta ? (rows.k_max <= 4 ? 3 : 2) : 1;
     const RingLayout probe =
         lanes ? ring_layout<T>(W, 31, false, 0, 0, 0)
-              : ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, 0);
-    // both variants stage the per-row records and weights (16 + 8 * sizeof(T) bytes per target row) and the row
+              : ring_layout<T>(wp, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, 0);
+    // all variants stage the per-row records and weights (16 + 8 * sizeof(T) bytes per target row) and the row
     // load order (4 bytes per scheduled row) in shared memory
     const size_t row_tables = static_cast<size_t>(rows.n_out) * (16 + kRingMaxTaps * sizeof(T)) +
                               static_cast<size_t>(ring_c->n_sched) * sizeof(int32_t);
-    // fp32 rows carry half the bytes of fp64 ones, so a target row leaves only half the time to walk the same
-    // per-row dependency chain: the register-resident kernel then runs TWO CTAs per SM (two independent row
-    // pipelines, each with half of the shared memory: its 64 registers per thread allow it)
-    const bool two_ctas = lanes && sizeof(T) == 4;
-    const long long smem_budget = two_ctas ? (static_cast<long long>(dev.max_smem_sm) / 2 - 1024)
-                                           : static_cast<long long>(dev.max_smem_optin);
-    const long long room = smem_budget - static_cast<long long>(probe.total) - static_cast<long long>(row_tables);
-    int slots = room > 0 ? static_cast<int>(room / probe.row_stride) : 0;
-    if (slots > kRingMaxSlots) slots = kRingMaxSlots;
+    // Several CTAs per SM = several independent row pipelines.  fp32 rows carry half the bytes of fp64 ones and
+    // low coarsening ratios bring only two new source rows per target row: either way a target row leaves too
+    // little time for ONE CTA's per-row dependency chain, so the shared memory is split between 2 - 3 CTAs when
+    // a ring deep enough for the band (rows alive + 3 in flight) still fits
+    int ctas = 1, slots = 0;
+    for (int c = min_ctas; c >= 1; --c) {
+      const long long budget = c > 1 ? (static_cast<long long>(dev.max_smem_sm) / c - 1024)
+                                     : static_cast<long long>(dev.max_smem_optin);
+      const long long room = budget - static_cast<long long>(probe.total) - static_cast<long long>(row_tables);
+      int sl = room > 0 ? static_cast<int>(room / probe.row_stride) : 0;
+      if (sl > kRingMaxSlots) sl = kRingMaxSlots;
+      if (sl >= ring_c->max_live + (c > 1 ? 3 : 1) && sl >= 2) {
+        ctas = c;
+        slots = sl;
+        break;
+      }
+    }
     if (slots >= ring_c->max_live + 1 && slots >= 2) {
       const RingLayout L =
           lanes ? ring_layout<T>(W, 31, false, 0, 0, slots)
-                : ring_layout<T>(W, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, slots);
+                : ring_layout<T>(wp, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, slots);
       RingDev ring{ring_c->sched_row,
                    reinterpret_cast<const int4*>(ring_c->krec),
                    ring_c->wrec,
@@ -282,7 +297,13 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
                    ring_c->lane_cols,
                    pole,
                    rows.n_src,
-                   zero_fill};
+                   zero_fill,
+                   ring_c->panel_strip0,
+                   ring_c->panel_c0,
+                   ring_c->panel_nc,
+                   n_panels,
+                   wp};
+      if (!have_panels) return RG_ERR_NULL;  // (the host layer always provides the panel tables)
       using RingKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev,
                                   T, int, int);
       const int warps = ring.n_warps + 2;  // + producer + sync
@@ -290,18 +311,25 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       RingKernel kern = nullptr;
 #define RG_PICK(KW)                                                                                   \
   case KW:                                                                                            \
-    kern = skipna ? (small ? conservative_ring_kernel<T, true, KW, 14>                                \
-                           : conservative_ring_kernel<T, true, KW, 26>)                               \
-                  : (small ? conservative_ring_kernel<T, false, KW, 14>                               \
-                           : conservative_ring_kernel<T, false, KW, 26>);                             \
+    if (panel_cta && rows.k_max <= 4)                                                                 \
+      kern = skipna ? conservative_ring_kernel<T, true, KW, 8, 4, 3>                                  \
+                    : conservative_ring_kernel<T, false, KW, 8, 4, 3>;                                \
+    else if (panel_cta)                                                                               \
+      kern = skipna ? conservative_ring_kernel<T, true, KW, 8, 8, 2>                                  \
+                    : conservative_ring_kernel<T, false, KW, 8, 8, 2>;                                \
+    else                                                                                              \
+      kern = skipna ? (small ? conservative_ring_kernel<T, true, KW, 14, 8, 1>                        \
+                             : conservative_ring_kernel<T, true, KW, 26, 8, 1>)                       \
+                    : (small ? conservative_ring_kernel<T, false, KW, 14, 8, 1>                       \
+                             : conservative_ring_kernel<T, false, KW, 26, 8, 1>);                     \
     break;
       switch (kw) {
         RG_PICK(1) RG_PICK(2) RG_PICK(3) RG_PICK(5) RG_PICK(8)
         default: break;
       }
 #undef RG_PICK
-      const long long tasks = static_cast<long long>(batch) * ring.n_runs;
-      long long grid = static_cast<long long>(dev.sm_count) * (two_ctas ? 2 : 1);
+      const long long tasks = static_cast<long long>(batch) * ring.n_runs * n_panels;
+      long long grid = static_cast<long long>(dev.sm_count) * ctas;
       if (grid > tasks) grid = tasks;
       if (lanes) {
         auto lk = rows.k_max <= 5

@@ -37,6 +37,11 @@ struct RingDev {
   const void* __restrict__ pole;  // [batch, 2, W] synthetic pole rows (scheduled as rows n_src_rows, + 1) or NULL
   int n_src_rows;
   int zero_fill;  // !SKIPNA kernels: a NaN tap counts as 0 (apply_weights with skipna=False) instead of poisoning
+  // column panels: a task is (slab, run, panel); the ring rows hold the panel's source columns only
+  const int32_t* __restrict__ panel_strip0;
+  const int32_t* __restrict__ panel_c0;
+  const int32_t* __restrict__ panel_nc;
+  int n_panels, panel_cols_max;
 };
 
 constexpr int kRingMaxSlots = 32;  // ring depth cap (a tap reaches at most 15 rows back: 4-bit tap_back)
@@ -261,18 +266,26 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
                                               uint32_t ring0, int n_warps) {
   uint32_t g = 0, freed = 0;  // rows issued / rows released by every consumer warp
   int slot = 0;
+  const int W = static_cast<int>(row_bytes / sizeof(T));  // source columns of a full row
   for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
-    const int run = static_cast<int>(task % ring.n_runs);
-    const long long b = task / ring.n_runs;
+    const int panel = static_cast<int>(task % ring.n_panels);
+    const long long unit = task / ring.n_panels;
+    const int run = static_cast<int>(unit % ring.n_runs);
+    const long long b = unit / ring.n_runs;
     const T* xb = x + b * xbs;
-    const T* pb = static_cast<const T*>(ring.pole) + b * 2 * static_cast<long long>(row_bytes / sizeof(T));
+    const T* pb = static_cast<const T*>(ring.pole) + b * 2 * static_cast<long long>(W);
+    // the panel's source columns [pc0, pc0 + pnc) modulo W: one bulk copy, or two when the range wraps
+    const int pc0 = ring.panel_c0[panel], pnc = ring.panel_nc[panel];
+    const int first = pnc < W - pc0 ? pnc : W - pc0;
+    const uint32_t bytes1 = static_cast<uint32_t>(first) * sizeof(T);
+    const uint32_t bytes2 = static_cast<uint32_t>(pnc - first) * sizeof(T);
     const int p1 = ring.run_sched[run + 1];
     for (int p = ring.run_sched[run]; p < p1; ++p) {
       const int row = sched_row[p];  // shared memory: no global load per row
       // rows >= n_src_rows are the synthetic pole rows of format_lat: full rows in the pole buffer
       const T* src = row < ring.n_src_rows
                          ? xb + static_cast<long long>(row) * xrs
-                         : pb + static_cast<long long>(row - ring.n_src_rows) * (row_bytes / sizeof(T));
+                         : pb + static_cast<long long>(row - ring.n_src_rows) * W;
       while (static_cast<int>(g - freed) >= ring_slots) {  // ring full: wait for the slowest warp
         // relaxed loads pipeline (acquire loads would serialise: 12-24 round trips per poll); one fence
         // below turns the poll into an acquire before the slot is overwritten
@@ -285,8 +298,10 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
         if (static_cast<int>(g - freed) >= ring_slots) __nanosleep(32);
         else fence_acq_rel_cta();
       }
-      mbar_arrive_expect_tx(full0 + 8u * slot, row_bytes);
-      tma_load_row(ring0 + static_cast<uint32_t>(slot) * row_stride, src, row_bytes, full0 + 8u * slot);
+      const uint32_t dst = ring0 + static_cast<uint32_t>(slot) * row_stride;
+      mbar_arrive_expect_tx(full0 + 8u * slot, bytes1 + bytes2);
+      tma_load_row(dst, src + pc0, bytes1, full0 + 8u * slot);
+      if (bytes2) tma_load_row(dst + bytes1, src, bytes2, full0 + 8u * slot);
       ++g;
       if (++slot == ring_slots) slot = 0;
     }
@@ -299,7 +314,7 @@ __device__ __forceinline__ void ring_sync(const RingDev& ring, long long tasks, 
   uint32_t g = 0, parity = 0;
   int slot = 0;
   for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
-    const int run = static_cast<int>(task % ring.n_runs);
+    const int run = static_cast<int>((task / ring.n_panels) % ring.n_runs);
     const int n = ring.run_sched[run + 1] - ring.run_sched[run];
     for (int i = 0; i < n; ++i) {
       while (!mbar_try_wait(full0 + 8u * slot, parity)) __nanosleep(32);  // do not steal issue slots
@@ -309,16 +324,19 @@ __device__ __forceinline__ void ring_sync(const RingDev& ring, long long tasks, 
   }
 }
 
-template <typename T, bool SKIPNA, int KW, int MAXWARPS>
-__global__ void __launch_bounds__(MAXWARPS * 32, 1)
+// MAXWARPS / RMAX / MINB: launch shape.  (14 or 26, 8, 1) is the classic one-CTA-per-SM layout; (8, 4, 3) and
+// (8, 8, 2) are the column-panel layouts (6 consumer warps, bands of <= 4 / <= 8 row taps, 3 / 2 CTAs per SM).
+template <typename T, bool SKIPNA, int KW, int MAXWARPS, int RMAX, int MINB>
+__global__ void __launch_bounds__(MAXWARPS * 32, MINB)
 conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
                          long long xrs, long long ybs, Band<T> cols, RingDev ring, T thr, int ring_slots,
                          int n_rows_out) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int W = cols.n_src, Wo = cols.n_out;
+  const int Wp = ring.panel_cols_max;  // columns of a ring row (the whole source row when there is one panel)
   const int pad_shift = ring.pad_shift;
   const int n_warps = ring.n_warps;  // consumer warps; then one producer warp and one sync warp
-  const RingLayout L = ring_layout<T>(W, pad_shift, SKIPNA, ring.strip_cols_max, n_warps, ring_slots);
+  const RingLayout L = ring_layout<T>(Wp, pad_shift, SKIPNA, ring.strip_cols_max, n_warps, ring_slots);
   unsigned long long* s_full = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
   uint32_t* s_flags = reinterpret_cast<uint32_t*>(smem + L.off_flags);
 
@@ -338,7 +356,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
   for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
   __syncthreads();
 
-  const long long tasks = batch * ring.n_runs;
+  const long long tasks = batch * ring.n_runs * ring.n_panels;
   const uint32_t row_bytes = static_cast<uint32_t>(W) * sizeof(T);
   const uint32_t full0 = smem_u32(s_full), flags0 = smem_u32(s_flags), ring0 = smem_u32(smem);
 
@@ -363,37 +381,44 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
   uint32_t newest_g = 0; // ring position + 1 of the newest row needed so far
   int newest = ring_slots - 1;
 
-  // The longitude taps of the output this lane produces stay in registers (reloaded only if a warp
-  // owns more than one strip).  Indices are mapped to padded slots of the strip buffer; taps beyond
-  // the output's own count get weight 0 on its first index, so the longitude pass is branch-free.
+  // The longitude taps of the output this lane produces stay in registers (reloaded only when the warp's strip
+  // changes: a new panel, or a warp that owns several strips of the classic layout).  Indices are mapped to
+  // padded slots of the strip buffer; taps beyond the output's own count get weight 0 on its first index, so
+  // the longitude pass is branch-free.
   int cur = -1, l0 = 0, nl = 0, col0 = 0, ncols = 0, ccnt = -1;
   T tw[KW];
   int ci[KW];
-  auto load_strip = [&](int st) {
+  auto load_strip = [&](int st, int pc0) {
     cur = st;
     l0 = ring.strip_l0[st];
     nl = ring.strip_l0[st + 1] - l0;
-    col0 = ring.strip_c0[st];
+    col0 = ring.strip_c0[st];  // relative to the panel's first column
     ncols = ring.strip_nc[st];
+    int abs0 = pc0 + col0;     // the strip's first source column in the full row
+    if (abs0 >= W) abs0 -= W;
     const int l = l0 + (lane < nl ? lane : 0);
     const int n = cols.cnt[l];
     ccnt = (lane < nl && cols.cover[l]) ? n : -1;
 #pragma unroll
     for (int i = 0; i < KW; ++i) {
       const bool live = i < n && i < cols.k_max;
-      int j = live ? cols.idx[i * Wo + l] : (n > 0 ? cols.idx[l] : col0);
-      j -= col0;
+      int j = live ? cols.idx[i * Wo + l] : (n > 0 ? cols.idx[l] : abs0);
+      j -= abs0;
       if (j < 0) j += W;
       ci[i] = j + (pad_shift < 31 ? (j >> pad_shift) : 0);
       tw[i] = live ? cols.w[i * Wo + l] : T(0);
     }
   };
-  if (warp < ring.n_strips) load_strip(warp);
 
   for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
-    const int run = static_cast<int>(task % ring.n_runs);
-    const long long b = task / ring.n_runs;
+    const int panel = static_cast<int>(task % ring.n_panels);
+    const long long unit = task / ring.n_panels;
+    const int run = static_cast<int>(unit % ring.n_runs);
+    const long long b = unit / ring.n_runs;
     const int k0 = ring.run_first[run], k1 = ring.run_first[run + 1];
+    const int s_first = ring.panel_strip0[panel], s_end = ring.panel_strip0[panel + 1];
+    const int pc0 = ring.panel_c0[panel];
+    const int pw = ring.panel_nc[panel];  // strips wrap inside a full-circle panel only (pw == W)
     for (int k = k0; k < k1; ++k) {
       const int4 rec = s_krec[k];  // {need, release, kcnt (-1: latitude not covered), packed tap_back}
       const uint32_t need_g = gbase + static_cast<uint32_t>(rec.x);
@@ -407,27 +432,41 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
 
       T* yrow = y + b * ybs + static_cast<long long>(k) * Wo;
       const T* wk = wrec + static_cast<long long>(k) * kRingMaxTaps;
-      for (int st = warp; st < ring.n_strips; st += n_warps) {
-        if (st != cur) load_strip(st);
+      if (s_first + warp >= s_end) {  // a panel with fewer strips than consumer warps: only report progress
+        if (lane == 0) st_release_smem(flags0 + 4u * (1 + warp), gbase + static_cast<uint32_t>(rec.y));
+        continue;
+      }
+      for (int st = s_first + warp; st < s_end; st += n_warps) {
+        if (st != cur) load_strip(st, pc0);
         __syncwarp();  // the previous longitude pass is done reading the strip buffer
         // ---- phase 1: latitude contraction out of the ring
 #define RG_P1(C)                                                                                          \
   case C:                                                                                                 \
     ring_phase1<T, SKIPNA, C>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk,   \
-                              s_tv, W, col0, ncols, pad_shift, lane, ring.zero_fill);                     \
+                              s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);                    \
     break;
-        switch (cnt) {
-          RG_P1(0) RG_P1(1) RG_P1(2) RG_P1(3) RG_P1(4) RG_P1(5) RG_P1(6) RG_P1(7)
-          default:
-            ring_phase1<T, SKIPNA, 8>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
-                                      wk, s_tv, W, col0, ncols, pad_shift, lane, ring.zero_fill);
-            break;
+        if constexpr (RMAX <= 4) {
+          switch (cnt) {
+            RG_P1(0) RG_P1(1) RG_P1(2) RG_P1(3)
+            default:
+              ring_phase1<T, SKIPNA, 4>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
+                                        wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);
+              break;
+          }
+        } else {
+          switch (cnt) {
+            RG_P1(0) RG_P1(1) RG_P1(2) RG_P1(3) RG_P1(4) RG_P1(5) RG_P1(6) RG_P1(7)
+            default:
+              ring_phase1<T, SKIPNA, 8>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
+                                        wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);
+              break;
+          }
         }
 #undef RG_P1
         __syncwarp();
         // rows that are dead after this output are no longer read once the LAST strip's latitude
         // pass is done: publish this warp's progress so the producer can recycle them early
-        if (st + n_warps >= ring.n_strips && lane == 0)
+        if (st + n_warps >= s_end && lane == 0)
           st_release_smem(flags0 + 4u * (1 + warp), gbase + static_cast<uint32_t>(rec.y));
         // ---- phase 2: longitude contraction, normalise, mask, store
         if (lane < nl) {

@@ -306,6 +306,12 @@ class RowRing:
     strip_nc: np.ndarray = None  # int32 [n_strips]
     n_warps: int = 0
     lane_cols: int = 0  # 4: lane-owned columns structure (see ``lane_owned_columns``), else 0
+    # column panels (two-phase ring kernel): panel p owns strips panel_strip0[p] .. panel_strip0[p+1]-1 and the
+    # source columns panel_c0[p] .. + panel_nc[p] - 1 (modulo n_src); strip_c0 is RELATIVE to the panel's first
+    # column.  One panel covering the whole row = the classic layout.
+    panel_strip0: np.ndarray = None  # int32 [n_panels + 1]
+    panel_c0: np.ndarray = None  # int32 [n_panels]
+    panel_nc: np.ndarray = None  # int32 [n_panels]
 
     @property
     def n_strips(self) -> int:
@@ -329,6 +335,20 @@ class RowRing:
     @property
     def strip_cols_max(self) -> int:
         return int(self.strip_nc.max())
+
+    @property
+    def n_panels(self) -> int:
+        return 0 if self.panel_c0 is None else int(self.panel_c0.size)
+
+    @property
+    def panel_cols_max(self) -> int:
+        return int(self.panel_nc.max()) if self.n_panels else 0
+
+    def single_panel(self, n_src: int) -> None:
+        """The whole row as one panel (strip_c0 relative to column 0 = absolute)."""
+        self.panel_strip0 = np.asarray([0, self.n_strips], np.int32)
+        self.panel_c0 = np.asarray([0], np.int32)
+        self.panel_nc = np.asarray([n_src], np.int32)
 
     @property
     def n_runs(self) -> int:
@@ -387,6 +407,65 @@ def column_strips(cols: Band, vec: int, max_warps: int = 12, n_warps: int | None
         if best is None or cost < best[0] - 1e-9:
             best = (cost, l0, c0, nc, min(n_warps, c0.size))
     return best[1:]
+
+
+def column_panels(cols: Band, vec: int, warps: int = 6):
+    """Column panels for the two-phase ring kernel when the target row is too wide for one CTA's consumer warps
+    (or so narrow that one CTA per SM would leave the SM idle): the target columns are cut into strips of equal
+    size (<= 32, chosen with the same instruction-count model as ``column_strips``), ``warps`` consecutive strips
+    form a panel, and a CTA works on ONE panel of a (slab, run of target rows) task: its ring rows hold only the
+    panel's source columns (short rows: several CTAs fit an SM, i.e. several independent row pipelines) and every
+    consumer warp owns exactly one strip.
+
+    Returns ``(strip_l0, strip_c0_relative, strip_nc, panel_strip0, panel_c0, panel_nc)`` or None when a panel's
+    source range cannot be expressed (it would cover the whole circle)."""
+    n_out, n_src = cols.n_out, cols.n_src
+    if n_out == 0 or n_src % vec:
+        return None
+
+    def span_of(a, b):
+        """Circular source range (start, length) covering every tap of targets a .. b-1, vec-aligned."""
+        taps = [cols.idx[: cols.cnt[l], l] for l in range(a, b) if cols.cnt[l] > 0 and cols.cover[l]]
+        if not taps:
+            return 0, vec
+        u = np.unique(np.concatenate(taps)).astype(np.int64)
+        gaps = np.diff(np.append(u, u[0] + n_src))
+        g = int(np.argmax(gaps))
+        start, end = int(u[(g + 1) % u.size]), int(u[g])
+        length = (end - start) % n_src + 1
+        c0 = start - start % vec
+        length = -(-(length + start - c0) // vec) * vec
+        if length >= n_src:
+            return 0, n_src
+        return c0, length
+
+    best = None
+    for tps in range(32, 7, -1):
+        l0 = np.append(np.arange(0, n_out, tps), n_out)
+        spans = [span_of(a, b) for a, b in zip(l0[:-1], l0[1:])]
+        steps = max(-(-(nc // vec) // 32) for _, nc in spans)
+        cost = (steps * 63 + 75) / tps  # per target column
+        if best is None or cost < best[0] - 1e-9:
+            best = (cost, l0, spans)
+    _, l0, spans = best
+    n_strips = len(spans)
+    n_pan = -(-n_strips // warps)
+    per = -(-n_strips // n_pan)
+    p_strip0 = np.append(np.arange(0, n_strips, per), n_strips)
+    p_c0, p_nc, s_c0 = [], [], []
+    for a, b in zip(p_strip0[:-1], p_strip0[1:]):
+        c0, nc = span_of(int(l0[a]), int(l0[b]))
+        if nc >= n_src and n_pan > 1:
+            return None
+        p_c0.append(c0)
+        p_nc.append(nc)
+        for sidx in range(a, b):
+            rel = (spans[sidx][0] - c0) % n_src
+            if rel + spans[sidx][1] > nc and nc < n_src:  # (a full-circle panel wraps its strips like the classic layout)
+                return None
+            s_c0.append(rel)
+    return (l0.astype(np.int32), np.asarray(s_c0, np.int32), np.asarray([nc for _, nc in spans], np.int32),
+            p_strip0.astype(np.int32), np.asarray(p_c0, np.int32), np.asarray(p_nc, np.int32))
 
 
 def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: int = 2) -> RowRing | None:
@@ -459,24 +538,32 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
         if cols.n_src % vec != 0:
             return None
         ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = column_strips(cols, vec)
-        if ring.strip_c0.size > ring.n_warps:
-            # more than 12 x 32 target columns: a warp would own several strips and reload its column taps for
-            # every (target row, strip); the generic kernel is faster there (measured: 0.25 -> 0.5 deg 3x)
-            return None
-        ring.lane_cols = lane_owned_columns(cols, ring.strip_l0, ring.n_warps)
-        if not ring.lane_cols and cols.n_out <= 31 * 12:
-            # the register-resident kernel wants one strip of <= 31 targets per warp: try that decomposition
-            n_warps = int(min(12, max(1, -(-cols.n_out // 8))))
-            while -(-cols.n_out // n_warps) > 31:
-                n_warps += 1
-            l0, c0, nc, _ = column_strips(cols, vec, n_warps=n_warps)
-            if l0.size - 1 <= n_warps and lane_owned_columns(cols, l0, n_warps):
-                ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = l0, c0, nc, n_warps
-                ring.lane_cols = lane_owned_columns(cols, l0, n_warps)
-        if not ring.lane_cols and ring.n_warps < 8:
-            # few, short strips: the two-phase ring kernel leaves most of the SM idle (every warp visits every
-            # target row); the generic kernel's many small CTAs do better (measured: 1 -> 2.5 deg 1.9 vs 1.6 TB/s)
-            return None
+        ring.single_panel(cols.n_src)
+        too_wide = ring.strip_c0.size > ring.n_warps
+        if not too_wide:
+            ring.lane_cols = lane_owned_columns(cols, ring.strip_l0, ring.n_warps)
+            if not ring.lane_cols and cols.n_out <= 31 * 12:
+                # the register-resident kernel wants one strip of <= 31 targets per warp: try that decomposition
+                n_warps = int(min(12, max(1, -(-cols.n_out // 8))))
+                while -(-cols.n_out // n_warps) > 31:
+                    n_warps += 1
+                l0, c0, nc, _ = column_strips(cols, vec, n_warps=n_warps)
+                if l0.size - 1 <= n_warps and lane_owned_columns(cols, l0, n_warps):
+                    ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = l0, c0, nc, n_warps
+                    ring.lane_cols = lane_owned_columns(cols, l0, n_warps)
+                    ring.single_panel(cols.n_src)
+        if too_wide or (not ring.lane_cols and (ring.n_warps < 8 or rows.k_max <= 4)):
+            # more than 12 x 32 target columns (a warp would own several strips and reload its column taps for
+            # every target row), few short strips (one CTA per SM leaves it idle), or few row taps (coarsening
+            # ratios of 2 - 2.5: two new source rows per target row leave no time for one CTA's per-row dependency
+            # chain): column panels -- every CTA works on one panel of 6 strips, short ring rows, several CTAs
+            # (independent row pipelines) per SM
+            pan = column_panels(cols, vec)
+            if pan is None:
+                return None
+            (ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.panel_strip0, ring.panel_c0, ring.panel_nc) = pan
+            ring.n_warps = int(np.diff(ring.panel_strip0).max())
+            ring.lane_cols = 0
     return ring
 
 
