@@ -108,7 +108,7 @@ typedef struct rg_band {
  *                             padded): the rows band's weights, output-major
  *   max_live                  max over o of rows simultaneously alive (ring must hold them)
  *
- * Column decomposition: the target columns are cut into `n_strips` strips of <= 32 outputs;
+ * Column decomposition: the target columns are cut into `n_strips` strips of <= 32 (panel layouts: 64) outputs;
  * consumer warp w of `n_warps` handles strips w, w + n_warps, ...  For strip s
  *   strip_l0[s] .. strip_l0[s+1]-1   its target columns
  *   strip_c0[s], strip_nc[s]         the source columns (a range modulo n_src that may wrap
@@ -152,6 +152,8 @@ typedef struct rg_row_ring {
   const int32_t* panel_nc;     /* device, [n_panels]     */
   int32_t n_panels;            /* >= 1 */
   int32_t panel_cols_max;      /* max over p of panel_nc[p] */
+  int32_t strip_targets_max;   /* max over s of strip_l0[s+1] - strip_l0[s]: <= 32, or <= 64 in panel layouts
+                                  of 6 consumer warps (the kernel then walks a strip's targets in two passes) */
 } rg_row_ring_t;
 
 /*

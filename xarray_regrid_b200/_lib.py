@@ -57,6 +57,7 @@ class rg_row_ring_t(C.Structure):  # noqa: N801 - mirrors the C name
         ("panel_nc", C.c_void_p),
         ("n_panels", C.c_int32),
         ("panel_cols_max", C.c_int32),
+        ("strip_targets_max", C.c_int32),
     ]
 
 

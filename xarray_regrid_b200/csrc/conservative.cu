@@ -237,6 +237,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       (!pole || reinterpret_cast<uintptr_t>(pole) % 16 == 0) &&
       rows.k_max <= kRingMaxTaps && cols.k_max <= 8 && ring_c->n_runs > 0 && ring_c->n_strips > 0 &&
       ring_c->n_warps >= 1 && ring_c->n_warps <= kRingMaxWarps && ring_c->max_live <= kRingMaxLive &&
+      (ring_c->strip_targets_max <= 32 || (ring_c->strip_targets_max <= 64 && ring_c->n_warps <= 6 && cols.k_max >= 3)) &&
       ring_c->sched_row && ring_c->krec && ring_c->wrec && ring_c->run_first && ring_c->run_sched &&
       ring_c->strip_l0 && ring_c->strip_c0 && ring_c->strip_nc) {
     const int kw = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : cols.k_max <= 3 ? 3 : cols.k_max <= 5 ? 5 : 8;
@@ -249,14 +250,18 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     const bool lanes = ring_c->lane_cols == 4 && cols.k_max <= 5 && ring_c->n_strips <= ring_c->n_warps &&
                        ring_c->n_warps + 2 <= 14 && W % 2 == 0 && ring_c->n_sched < 65536 && n_panels == 1 && wp == W;
     // panel layouts of the two-phase kernel: 6 consumer warps, several CTAs per SM
-    const bool panel_cta = !lanes && have_panels && ring_c->n_warps <= 6;
-    const int min_ctas = lanes ? (sizeof(T) == 4 ? 2 : 1) : panel_cta ? (rows.k_max <= 4 ? 3 : 2) : 1;
+    const bool panel_cta = !lanes && have_panels && ring_c->n_warps <= 6 && kw >= 3;
+    const bool panel_tg2 = panel_cta && ring_c->strip_targets_max > 32;
+    const int min_ctas = lanes ? (sizeof(T) == 4 ? 2 : 1)
+                         : panel_cta ? ((rows.k_max <= 4 && !(panel_tg2 && kw >= 5)) ? 3 : 2) : 1;
     const RingLayout probe =
         lanes ? ring_layout<T>(W, 31, false, 0, 0, 0)
               : ring_layout<T>(wp, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, 0);
     // all variants stage the per-row records and weights (16 + 8 * sizeof(T) bytes per target row) and the row
     // load order (4 bytes per scheduled row) in shared memory
-    const size_t row_tables = static_cast<size_t>(rows.n_out) * (16 + kRingMaxTaps * sizeof(T)) +
+    // (the two-phase kernel keeps only the weights its instance can use: 4 per row for bands of <= 4 row taps)
+    const int w_per_row = (panel_cta && rows.k_max <= 4) ? 4 : kRingMaxTaps;  // = RMAX of the instance picked below
+    const size_t row_tables = static_cast<size_t>(rows.n_out) * (16 + (lanes ? kRingMaxTaps : w_per_row) * sizeof(T)) +
                               static_cast<size_t>(ring_c->n_sched) * sizeof(int32_t);
     // Several CTAs per SM = several independent row pipelines.  fp32 rows carry half the bytes of fp64 ones and
     // low coarsening ratios bring only two new source rows per target row: either way a target row leaves too
@@ -309,24 +314,30 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       const int warps = ring.n_warps + 2;  // + producer + sync
       const bool small = warps <= 14;
       RingKernel kern = nullptr;
+      // strips of more than 32 targets (panel layouts only) need the two-pass longitude phase (TG = 2)
+      const bool tg2 = panel_cta && ring_c->strip_targets_max > 32;
+#define RG_PANEL(KW, RMAXV, MINBV, TGV)                                                               \
+  (skipna ? conservative_ring_kernel<T, true, KW, 8, RMAXV, MINBV, TGV>                               \
+          : conservative_ring_kernel<T, false, KW, 8, RMAXV, MINBV, TGV>)
 #define RG_PICK(KW)                                                                                   \
   case KW:                                                                                            \
-    if (panel_cta && rows.k_max <= 4)                                                                 \
-      kern = skipna ? conservative_ring_kernel<T, true, KW, 8, 4, 3>                                  \
-                    : conservative_ring_kernel<T, false, KW, 8, 4, 3>;                                \
+    if (panel_cta && rows.k_max <= 4 && KW <= 3)                                                      \
+      kern = tg2 ? RG_PANEL(KW, 4, 3, 2) : RG_PANEL(KW, 4, 3, 1);                                     \
+    else if (panel_cta && rows.k_max <= 4)                                                            \
+      kern = tg2 ? RG_PANEL(KW, 4, 2, 2) : RG_PANEL(KW, 4, 3, 1);                                     \
     else if (panel_cta)                                                                               \
-      kern = skipna ? conservative_ring_kernel<T, true, KW, 8, 8, 2>                                  \
-                    : conservative_ring_kernel<T, false, KW, 8, 8, 2>;                                \
+      kern = tg2 ? RG_PANEL(KW, 8, 2, 2) : RG_PANEL(KW, 8, 2, 1);                                     \
     else                                                                                              \
-      kern = skipna ? (small ? conservative_ring_kernel<T, true, KW, 14, 8, 1>                        \
-                             : conservative_ring_kernel<T, true, KW, 26, 8, 1>)                       \
-                    : (small ? conservative_ring_kernel<T, false, KW, 14, 8, 1>                       \
-                             : conservative_ring_kernel<T, false, KW, 26, 8, 1>);                     \
+      kern = skipna ? (small ? conservative_ring_kernel<T, true, KW, 14, 8, 1, 1>                     \
+                             : conservative_ring_kernel<T, true, KW, 26, 8, 1, 1>)                    \
+                    : (small ? conservative_ring_kernel<T, false, KW, 14, 8, 1, 1>                    \
+                             : conservative_ring_kernel<T, false, KW, 26, 8, 1, 1>);                  \
     break;
       switch (kw) {
         RG_PICK(1) RG_PICK(2) RG_PICK(3) RG_PICK(5) RG_PICK(8)
         default: break;
       }
+#undef RG_PANEL
 #undef RG_PICK
       const long long tasks = static_cast<long long>(batch) * ring.n_runs * n_panels;
       long long grid = static_cast<long long>(dev.sm_count) * ctas;

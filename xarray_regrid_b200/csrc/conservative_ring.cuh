@@ -191,7 +191,7 @@ __device__ __forceinline__ void accum_clean(float& acc, float w, float x) {
 // Latitude contraction of the CNT taps of one output for one strip of source columns
 // [col0, col0 + ncols) (mod W), 16 bytes per lane per step.  CNT is a compile-time constant: the
 // CNT shared-memory loads issue back to back and the tap loop is branch-free.
-template <typename T, bool SKIPNA, int CNT>
+template <typename T, bool SKIPNA, int CNT, int RMAX>
 __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row_stride, int ring_slots,
                                             int newest, uint32_t back, const T* __restrict__ wk,
                                             TV<T, SKIPNA>* s_tv, int W, int col0, int ncols, int pad_shift,
@@ -200,7 +200,7 @@ __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row
   constexpr int N = CNT > 0 ? CNT : 1;
   const unsigned char* rowp[N];
   T w[N];
-  // weights of this output: one or more 16-byte loads from the output-major record
+  // weights of this output: one or more 16-byte loads from the staged output-major record
   {
     Pack<T, VEC> wv[(N + VEC - 1) / VEC];
 #pragma unroll
@@ -286,6 +286,7 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
       const T* src = row < ring.n_src_rows
                          ? xb + static_cast<long long>(row) * xrs
                          : pb + static_cast<long long>(row - ring.n_src_rows) * W;
+      uint32_t nap = 64;
       while (static_cast<int>(g - freed) >= ring_slots) {  // ring full: wait for the slowest warp
         // relaxed loads pipeline (acquire loads would serialise: 12-24 round trips per poll); one fence
         // below turns the poll into an acquire before the slot is overwritten
@@ -295,8 +296,14 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
           if (static_cast<int>(d - m) < 0) m = d;
         }
         freed = m;
-        if (static_cast<int>(g - freed) >= ring_slots) __nanosleep(32);
-        else fence_acq_rel_cta();
+        if (static_cast<int>(g - freed) >= ring_slots) {
+          // a full ring means the consumers are a whole ring behind: back off (the poll loop of three CTAs'
+          // producers took 13 % of an SM's issue slots with a fixed 32 ns nap)
+          __nanosleep(nap);
+          if (nap < 512) nap *= 2;
+        } else {
+          fence_acq_rel_cta();
+        }
       }
       const uint32_t dst = ring0 + static_cast<uint32_t>(slot) * row_stride;
       mbar_arrive_expect_tx(full0 + 8u * slot, bytes1 + bytes2);
@@ -326,7 +333,11 @@ __device__ __forceinline__ void ring_sync(const RingDev& ring, long long tasks, 
 
 // MAXWARPS / RMAX / MINB: launch shape.  (14 or 26, 8, 1) is the classic one-CTA-per-SM layout; (8, 4, 3) and
 // (8, 8, 2) are the column-panel layouts (6 consumer warps, bands of <= 4 / <= 8 row taps, 3 / 2 CTAs per SM).
-template <typename T, bool SKIPNA, int KW, int MAXWARPS, int RMAX, int MINB>
+// TG: groups of 32 target columns per strip (1 classic; 2 in the panel layouts: a strip of up to 64 targets walks
+// its source columns in two lane steps and its targets in two passes, halving the per-row fixed cost per target).
+// (Reading the per-row tables from global memory one row ahead instead of staging them was measured and dropped:
+// 3.6 -> 2.8 TB/s on 0.5 -> 1 degree.)
+template <typename T, bool SKIPNA, int KW, int MAXWARPS, int RMAX, int MINB, int TG>
 __global__ void __launch_bounds__(MAXWARPS * 32, MINB)
 conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
                          long long xrs, long long ybs, Band<T> cols, RingDev ring, T thr, int ring_slots,
@@ -348,11 +359,14 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
   }
   if (tid < 32) s_flags[tid] = 0;
   // per target row tables and the row load order, staged once: no global load on the per-row paths
+  // (only the RMAX weights a row of this instance can use are kept: 32 instead of 64 bytes per fp64 row)
   int4* s_krec = reinterpret_cast<int4*>(smem + L.total);
   T* s_wrec = reinterpret_cast<T*>(smem + L.total + static_cast<size_t>(n_rows_out) * 16);
-  int32_t* s_sched = reinterpret_cast<int32_t*>(s_wrec + static_cast<size_t>(n_rows_out) * kRingMaxTaps);
+  int32_t* s_sched = reinterpret_cast<int32_t*>(s_wrec + static_cast<size_t>(n_rows_out) * RMAX);
+  constexpr int wstride = RMAX;  // weights per row in the staged table
   for (int i = tid; i < n_rows_out; i += blockDim.x) s_krec[i] = ring.krec[i];
-  for (int i = tid; i < n_rows_out * kRingMaxTaps; i += blockDim.x) s_wrec[i] = static_cast<const T*>(ring.wrec)[i];
+  for (int i = tid; i < n_rows_out * RMAX; i += blockDim.x)
+    s_wrec[i] = static_cast<const T*>(ring.wrec)[(i / RMAX) * kRingMaxTaps + (i % RMAX)];
   for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
   __syncthreads();
 
@@ -376,7 +390,6 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
   const T nan = quiet_nan<T>();
   using Entry = TV<T, SKIPNA>;
   Entry* s_tv = reinterpret_cast<Entry*>(smem + L.off_strip + static_cast<size_t>(warp) * L.strip_bytes);
-  const T* wrec = s_wrec;
   uint32_t gbase = 0;    // ring position of the current run's first row
   uint32_t newest_g = 0; // ring position + 1 of the newest row needed so far
   int newest = ring_slots - 1;
@@ -385,28 +398,33 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
   // changes: a new panel, or a warp that owns several strips of the classic layout).  Indices are mapped to
   // padded slots of the strip buffer; taps beyond the output's own count get weight 0 on its first index, so
   // the longitude pass is branch-free.
-  int cur = -1, l0 = 0, nl = 0, col0 = 0, ncols = 0, ccnt = -1;
-  T tw[KW];
-  int ci[KW];
+  int cur = -1, l0 = 0, nl = 0, col0 = 0, ncols = 0;
+  int ccnt[TG];
+  T tw[TG][KW];
+  int ci[TG][KW];
   auto load_strip = [&](int st, int pc0) {
     cur = st;
     l0 = ring.strip_l0[st];
-    nl = ring.strip_l0[st + 1] - l0;
+    nl = ring.strip_l0[st + 1] - l0;  // host contract: <= 32 * TG
     col0 = ring.strip_c0[st];  // relative to the panel's first column
     ncols = ring.strip_nc[st];
     int abs0 = pc0 + col0;     // the strip's first source column in the full row
     if (abs0 >= W) abs0 -= W;
-    const int l = l0 + (lane < nl ? lane : 0);
-    const int n = cols.cnt[l];
-    ccnt = (lane < nl && cols.cover[l]) ? n : -1;
 #pragma unroll
-    for (int i = 0; i < KW; ++i) {
-      const bool live = i < n && i < cols.k_max;
-      int j = live ? cols.idx[i * Wo + l] : (n > 0 ? cols.idx[l] : abs0);
-      j -= abs0;
-      if (j < 0) j += W;
-      ci[i] = j + (pad_shift < 31 ? (j >> pad_shift) : 0);
-      tw[i] = live ? cols.w[i * Wo + l] : T(0);
+    for (int g = 0; g < TG; ++g) {
+      const int m = lane + 32 * g;
+      const int l = l0 + (m < nl ? m : 0);
+      const int n = cols.cnt[l];
+      ccnt[g] = (m < nl && cols.cover[l]) ? n : -1;
+#pragma unroll
+      for (int i = 0; i < KW; ++i) {
+        const bool live = i < n && i < cols.k_max;
+        int j = live ? cols.idx[i * Wo + l] : (n > 0 ? cols.idx[l] : abs0);
+        j -= abs0;
+        if (j < 0) j += W;
+        ci[g][i] = j + (pad_shift < 31 ? (j >> pad_shift) : 0);
+        tw[g][i] = live ? cols.w[i * Wo + l] : T(0);
+      }
     }
   };
 
@@ -421,6 +439,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
     const int pw = ring.panel_nc[panel];  // strips wrap inside a full-circle panel only (pw == W)
     for (int k = k0; k < k1; ++k) {
       const int4 rec = s_krec[k];  // {need, release, kcnt (-1: latitude not covered), packed tap_back}
+      const T* wk = s_wrec + static_cast<long long>(k) * wstride;
       const uint32_t need_g = gbase + static_cast<uint32_t>(rec.x);
       const int cnt = rec.z > 0 ? rec.z : 0;
 
@@ -431,7 +450,6 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
       if (newest >= ring_slots) newest -= ring_slots;
 
       T* yrow = y + b * ybs + static_cast<long long>(k) * Wo;
-      const T* wk = wrec + static_cast<long long>(k) * kRingMaxTaps;
       if (s_first + warp >= s_end) {  // a panel with fewer strips than consumer warps: only report progress
         if (lane == 0) st_release_smem(flags0 + 4u * (1 + warp), gbase + static_cast<uint32_t>(rec.y));
         continue;
@@ -442,23 +460,23 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
         // ---- phase 1: latitude contraction out of the ring
 #define RG_P1(C)                                                                                          \
   case C:                                                                                                 \
-    ring_phase1<T, SKIPNA, C>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), wk,   \
-                              s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);                    \
+    ring_phase1<T, SKIPNA, C, RMAX>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), \
+                                    wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);          \
     break;
         if constexpr (RMAX <= 4) {
           switch (cnt) {
             RG_P1(0) RG_P1(1) RG_P1(2) RG_P1(3)
             default:
-              ring_phase1<T, SKIPNA, 4>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
-                                        wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);
+              ring_phase1<T, SKIPNA, 4, RMAX>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
+                                              wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);
               break;
           }
         } else {
           switch (cnt) {
             RG_P1(0) RG_P1(1) RG_P1(2) RG_P1(3) RG_P1(4) RG_P1(5) RG_P1(6) RG_P1(7)
             default:
-              ring_phase1<T, SKIPNA, 8>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
-                                        wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);
+              ring_phase1<T, SKIPNA, 8, RMAX>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
+                                              wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);
               break;
           }
         }
@@ -469,22 +487,25 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
         if (st + n_warps >= s_end && lane == 0)
           st_release_smem(flags0 + 4u * (1 + warp), gbase + static_cast<uint32_t>(rec.y));
         // ---- phase 2: longitude contraction, normalise, mask, store
-        if (lane < nl) {
-          T out = nan;
-          if (rec.z >= 0 && ccnt >= 0) {
-            Entry e[KW];
 #pragma unroll
-            for (int i = 0; i < KW; ++i) e[i] = s_tv[ci[i]];
-            T so = T(0), sv = T(0);
+        for (int g = 0; g < TG; ++g) {
+          if (lane + 32 * g < nl) {
+            T out = nan;
+            if (rec.z >= 0 && ccnt[g] >= 0) {
+              Entry e[KW];
 #pragma unroll
-            for (int i = 0; i < KW; ++i) {
-              so = fma(tw[i], e[i].t, so);
-              if constexpr (SKIPNA) sv = fma(tw[i], e[i].v, sv);
+              for (int i = 0; i < KW; ++i) e[i] = s_tv[ci[g][i]];
+              T so = T(0), sv = T(0);
+#pragma unroll
+              for (int i = 0; i < KW; ++i) {
+                so = fma(tw[g][i], e[i].t, so);
+                if constexpr (SKIPNA) sv = fma(tw[g][i], e[i].v, sv);
+              }
+              if constexpr (SKIPNA) out = (sv >= thr) ? normalise_div(so, sv) : nan;
+              else out = so;
             }
-            if constexpr (SKIPNA) out = (sv >= thr) ? normalise_div(so, sv) : nan;
-            else out = so;
+            st_stream(yrow + l0 + lane + 32 * g, out);
           }
-          st_stream(yrow + l0 + lane, out);
         }
       }
     }

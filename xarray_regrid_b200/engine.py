@@ -87,7 +87,7 @@ class DeviceRing:
             ring.n_runs, int(ring.sched_row.size), ring.max_live, ring.pad_shift,
             ring.n_strips, ring.strip_cols_max, ring.n_warps, ring.lane_cols,
             self.panel_strip0.data_ptr(), self.panel_c0.data_ptr(), self.panel_nc.data_ptr(),
-            ring.n_panels, ring.panel_cols_max,
+            ring.n_panels, ring.panel_cols_max, int(np.diff(ring.strip_l0).max()),
         )
 
     @property

@@ -409,13 +409,16 @@ def column_strips(cols: Band, vec: int, max_warps: int = 12, n_warps: int | None
     return best[1:]
 
 
-def column_panels(cols: Band, vec: int, warps: int = 6):
+def column_panels(cols: Band, vec: int, warps: int = 6, table_bytes: int = 0, min_slots: int = 6,
+                  cta_budget: int = 74 * 1024):
     """Column panels for the two-phase ring kernel when the target row is too wide for one CTA's consumer warps
     (or so narrow that one CTA per SM would leave the SM idle): the target columns are cut into strips of equal
     size (<= 32, chosen with the same instruction-count model as ``column_strips``), ``warps`` consecutive strips
     form a panel, and a CTA works on ONE panel of a (slab, run of target rows) task: its ring rows hold only the
     panel's source columns (short rows: several CTAs fit an SM, i.e. several independent row pipelines) and every
-    consumer warp owns exactly one strip.
+    consumer warp owns exactly one strip.  The strip size is the cheapest (per target) one whose CTA -- a ring of
+    ``min_slots`` panel rows, the warps' strip buffers and ``table_bytes`` of per-row tables -- still fits
+    ``cta_budget`` bytes of shared memory, i.e. three CTAs per SM.
 
     Returns ``(strip_l0, strip_c0_relative, strip_nc, panel_strip0, panel_c0, panel_nc)`` or None when a panel's
     source range cannot be expressed (it would cover the whole circle)."""
@@ -439,33 +442,51 @@ def column_panels(cols: Band, vec: int, warps: int = 6):
             return 0, n_src
         return c0, length
 
-    best = None
-    for tps in range(32, 7, -1):
+    esz = 16 // vec
+    ratio = n_src / n_out
+    r = int(round(ratio))
+    padded = r >= 2 and abs(ratio - r) < 0.26 and (r & (r - 1)) == 0  # pad_shift of row_ring_schedule
+
+    def layout(tps):
         l0 = np.append(np.arange(0, n_out, tps), n_out)
         spans = [span_of(a, b) for a, b in zip(l0[:-1], l0[1:])]
-        steps = max(-(-(nc // vec) // 32) for _, nc in spans)
-        cost = (steps * 63 + 75) / tps  # per target column
-        if best is None or cost < best[0] - 1e-9:
-            best = (cost, l0, spans)
-    _, l0, spans = best
-    n_strips = len(spans)
-    n_pan = -(-n_strips // warps)
-    per = -(-n_strips // n_pan)
-    p_strip0 = np.append(np.arange(0, n_strips, per), n_strips)
-    p_c0, p_nc, s_c0 = [], [], []
-    for a, b in zip(p_strip0[:-1], p_strip0[1:]):
-        c0, nc = span_of(int(l0[a]), int(l0[b]))
-        if nc >= n_src and n_pan > 1:
-            return None
-        p_c0.append(c0)
-        p_nc.append(nc)
-        for sidx in range(a, b):
-            rel = (spans[sidx][0] - c0) % n_src
-            if rel + spans[sidx][1] > nc and nc < n_src:  # (a full-circle panel wraps its strips like the classic layout)
+        n_strips = len(spans)
+        n_pan = -(-n_strips // warps)
+        per = -(-n_strips // n_pan)
+        p_strip0 = np.append(np.arange(0, n_strips, per), n_strips)
+        p_c0, p_nc, s_c0 = [], [], []
+        for a, b in zip(p_strip0[:-1], p_strip0[1:]):
+            c0, nc = span_of(int(l0[a]), int(l0[b]))
+            if nc >= n_src and n_pan > 1:
                 return None
-            s_c0.append(rel)
-    return (l0.astype(np.int32), np.asarray(s_c0, np.int32), np.asarray([nc for _, nc in spans], np.int32),
-            p_strip0.astype(np.int32), np.asarray(p_c0, np.int32), np.asarray(p_nc, np.int32))
+            p_c0.append(c0)
+            p_nc.append(nc)
+            for sidx in range(a, b):
+                rel = (spans[sidx][0] - c0) % n_src
+                if rel + spans[sidx][1] > nc and nc < n_src:  # (a full-circle panel wraps its strips like the classic layout)
+                    return None
+                s_c0.append(rel)
+        return (l0.astype(np.int32), np.asarray(s_c0, np.int32), np.asarray([nc for _, nc in spans], np.int32),
+                p_strip0.astype(np.int32), np.asarray(p_c0, np.int32), np.asarray(p_nc, np.int32))
+
+    cands = []
+    for tps in sorted({-(-n_out // -(-n_out // t)) for t in range(64, 7, -1)}, reverse=True):  # equal strips
+        lay = layout(tps)
+        if lay is None:
+            continue
+        strip_nc_max, panel_nc_max = int(lay[2].max()), int(lay[5].max())
+        steps = -(-(strip_nc_max // vec) // 32)
+        cost = (110 + steps * 55 + -(-tps // 32) * 48) / tps  # per target: fixed + latitude steps + passes
+        row_stride = -(-(panel_nc_max * esz) // 128) * 128
+        strip_slots = strip_nc_max + (strip_nc_max // r if padded else 0) + 1
+        strip_bytes = -(-(strip_slots * 2 * esz) // 128) * 128
+        need = min_slots * row_stride + int(np.diff(lay[3]).max()) * strip_bytes + 512 + table_bytes
+        cands.append((need > cta_budget, len(lay[1]) < warps, cost, tps, lay))
+    if not cands:
+        return None
+    # fitting three CTAs per SM first, a strip for every consumer warp next, then the cheapest per target
+    cands.sort(key=lambda c: (c[0], c[1], c[2]))
+    return cands[0][4]
 
 
 def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: int = 2) -> RowRing | None:
@@ -537,6 +558,10 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
     if cols is not None:
         if cols.n_src % vec != 0:
             return None
+        if k_max >= 6 and cols.k_max > 5:
+            # many row taps and no register-resident columns: the generic kernel's plain streaming loads win
+            # (measured: 0.25 -> 1.5 deg, 7 x 7 taps: 5.2 vs 4.6 TB/s for the two-phase ring kernel)
+            return None
         ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = column_strips(cols, vec)
         ring.single_panel(cols.n_src)
         too_wide = ring.strip_c0.size > ring.n_warps
@@ -558,7 +583,10 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
             # ratios of 2 - 2.5: two new source rows per target row leave no time for one CTA's per-row dependency
             # chain): column panels -- every CTA works on one panel of 6 strips, short ring rows, several CTAs
             # (independent row pipelines) per SM
-            pan = column_panels(cols, vec)
+            esz = 16 // vec
+            w_row = 4 if rows.k_max <= 4 else 8
+            pan = column_panels(cols, vec, table_bytes=n_out * (16 + w_row * esz) + 4 * len(sched),
+                                min_slots=int(max_live) + 3)
             if pan is None:
                 return None
             (ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.panel_strip0, ring.panel_c0, ring.panel_nc) = pan
