@@ -236,6 +236,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   if (ring_c && aligned && (static_cast<size_t>(W) * sizeof(T)) % 16 == 0 &&
       (!pole || reinterpret_cast<uintptr_t>(pole) % 16 == 0) &&
       rows.k_max <= kRingMaxTaps && cols.k_max <= 8 && ring_c->n_runs > 0 && ring_c->n_strips > 0 &&
+      ring_c->n_sched < 65536 &&  // the staged per-row record packs need / release into 16 bits each
       ring_c->n_warps >= 1 && ring_c->n_warps <= kRingMaxWarps && ring_c->max_live <= kRingMaxLive &&
       (ring_c->strip_targets_max <= 32 || (ring_c->strip_targets_max <= 64 && ring_c->n_warps <= 6 && cols.k_max >= 3)) &&
       ring_c->sched_row && ring_c->krec && ring_c->wrec && ring_c->run_first && ring_c->run_sched &&

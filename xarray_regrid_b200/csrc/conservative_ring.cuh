@@ -193,7 +193,7 @@ __device__ __forceinline__ void accum_clean(float& acc, float w, float x) {
 // CNT shared-memory loads issue back to back and the tap loop is branch-free.
 template <typename T, bool SKIPNA, int CNT, int RMAX>
 __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row_stride, int ring_slots,
-                                            int newest, uint32_t back, const T* __restrict__ wk,
+                                            uint32_t slots03, uint32_t slots47, const T* __restrict__ wk,
                                             TV<T, SKIPNA>* s_tv, int W, int col0, int ncols, int pad_shift,
                                             int lane, int zero_fill) {
   constexpr int VEC = 16 / sizeof(T);
@@ -210,9 +210,10 @@ __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row
   }
 #pragma unroll
   for (int i = 0; i < CNT; ++i) {
-    int slot = newest - static_cast<int>((back >> (4 * i)) & 15u);  // rows back from the newest landed row
-    if (slot < 0) slot += ring_slots;
-    rowp[i] = s_ring + slot * row_stride;
+    // ring slot of tap i: byte i of the staged per-row table + the task's rotation (see ring_row_record)
+    uint32_t slot = __byte_perm(i < 4 ? slots03 : slots47, 0u, 0x4440u + static_cast<uint32_t>(i & 3));
+    slot = min(slot, slot - static_cast<uint32_t>(ring_slots));  // unsigned: wraps to slot when slot < ring_slots
+    rowp[i] = s_ring + slot * static_cast<uint32_t>(row_stride);
   }
   for (int q = lane * VEC; q < ncols; q += 32 * VEC) {
     int j = col0 + q;
@@ -254,6 +255,22 @@ __device__ __forceinline__ void ring_phase1(const unsigned char* s_ring, int row
       }
     }
   }
+}
+
+// The host's per-row record {need, release, kcnt, 8 x 4-bit rows-back} as the kernels keep it in shared memory:
+// {need | release << 16, kcnt, 8 x 8-bit ring slot of the tap relative to the run's first row}.  The per-row path
+// only adds the task's ring rotation (gbase mod ring_slots) to the packed bytes: one PRMT + one VIADDMNMX per tap
+// instead of nine integer instructions.
+__device__ __forceinline__ int4 ring_row_record(const int4 r, int ring_slots) {
+  const int cnt = r.z > 0 ? r.z : 0;
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int tp = 0; tp < kRingMaxTaps; ++tp) {
+    const int pos = r.x - 1 - static_cast<int>((static_cast<uint32_t>(r.w) >> (4 * tp)) & 15u);
+    const uint32_t sl = (tp < cnt && pos >= 0) ? static_cast<uint32_t>(pos % ring_slots) : 0u;
+    if (tp < 4) lo |= sl << (8 * tp); else hi |= sl << (8 * (tp - 4));
+  }
+  return make_int4(r.x | (r.y << 16), r.z, static_cast<int>(lo), static_cast<int>(hi));
 }
 
 // ---------------------------------------------------------------- producer / sync roles
@@ -364,7 +381,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
   T* s_wrec = reinterpret_cast<T*>(smem + L.total + static_cast<size_t>(n_rows_out) * 16);
   int32_t* s_sched = reinterpret_cast<int32_t*>(s_wrec + static_cast<size_t>(n_rows_out) * RMAX);
   constexpr int wstride = RMAX;  // weights per row in the staged table
-  for (int i = tid; i < n_rows_out; i += blockDim.x) s_krec[i] = ring.krec[i];
+  for (int i = tid; i < n_rows_out; i += blockDim.x) s_krec[i] = ring_row_record(ring.krec[i], ring_slots);
   for (int i = tid; i < n_rows_out * RMAX; i += blockDim.x)
     s_wrec[i] = static_cast<const T*>(ring.wrec)[(i / RMAX) * kRingMaxTaps + (i % RMAX)];
   for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
@@ -390,9 +407,8 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
   const T nan = quiet_nan<T>();
   using Entry = TV<T, SKIPNA>;
   Entry* s_tv = reinterpret_cast<Entry*>(smem + L.off_strip + static_cast<size_t>(warp) * L.strip_bytes);
-  uint32_t gbase = 0;    // ring position of the current run's first row
-  uint32_t newest_g = 0; // ring position + 1 of the newest row needed so far
-  int newest = ring_slots - 1;
+  uint32_t gbase = 0;  // ring position of the current run's first row
+  uint32_t rot = 0;    // gbase % ring_slots
 
   // The longitude taps of the output this lane produces stay in registers (reloaded only when the warp's strip
   // changes: a new panel, or a warp that owns several strips of the classic layout).  Indices are mapped to
@@ -437,21 +453,21 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
     const int s_first = ring.panel_strip0[panel], s_end = ring.panel_strip0[panel + 1];
     const int pc0 = ring.panel_c0[panel];
     const int pw = ring.panel_nc[panel];  // strips wrap inside a full-circle panel only (pw == W)
+    const uint32_t rot4 = rot * 0x01010101u;
     for (int k = k0; k < k1; ++k) {
-      const int4 rec = s_krec[k];  // {need, release, kcnt (-1: latitude not covered), packed tap_back}
+      const int4 rec = s_krec[k];  // {need | release << 16, kcnt (-1: latitude not covered), slots 0-3, slots 4-7}
       const T* wk = s_wrec + static_cast<long long>(k) * wstride;
-      const uint32_t need_g = gbase + static_cast<uint32_t>(rec.x);
-      const int cnt = rec.z > 0 ? rec.z : 0;
+      const uint32_t need_g = gbase + (static_cast<uint32_t>(rec.x) & 0xffffu);
+      const uint32_t rel_g = gbase + (static_cast<uint32_t>(rec.x) >> 16);
+      const int cnt = rec.y > 0 ? rec.y : 0;
+      const uint32_t s03 = static_cast<uint32_t>(rec.z) + rot4, s47 = static_cast<uint32_t>(rec.w) + rot4;
 
       // ---- wait until every row this output needs has landed in the ring
       while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(100);
-      newest += static_cast<int>(need_g - newest_g);
-      newest_g = need_g;
-      if (newest >= ring_slots) newest -= ring_slots;
 
       T* yrow = y + b * ybs + static_cast<long long>(k) * Wo;
       if (s_first + warp >= s_end) {  // a panel with fewer strips than consumer warps: only report progress
-        if (lane == 0) st_release_smem(flags0 + 4u * (1 + warp), gbase + static_cast<uint32_t>(rec.y));
+        if (lane == 0) st_release_smem(flags0 + 4u * (1 + warp), rel_g);
         continue;
       }
       for (int st = s_first + warp; st < s_end; st += n_warps) {
@@ -460,14 +476,14 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
         // ---- phase 1: latitude contraction out of the ring
 #define RG_P1(C)                                                                                          \
   case C:                                                                                                 \
-    ring_phase1<T, SKIPNA, C, RMAX>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w), \
+    ring_phase1<T, SKIPNA, C, RMAX>(smem, L.row_stride, ring_slots, s03, s47,                             \
                                     wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);          \
     break;
         if constexpr (RMAX <= 4) {
           switch (cnt) {
             RG_P1(0) RG_P1(1) RG_P1(2) RG_P1(3)
             default:
-              ring_phase1<T, SKIPNA, 4, RMAX>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
+              ring_phase1<T, SKIPNA, 4, RMAX>(smem, L.row_stride, ring_slots, s03, s47,
                                               wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);
               break;
           }
@@ -475,7 +491,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
           switch (cnt) {
             RG_P1(0) RG_P1(1) RG_P1(2) RG_P1(3) RG_P1(4) RG_P1(5) RG_P1(6) RG_P1(7)
             default:
-              ring_phase1<T, SKIPNA, 8, RMAX>(smem, L.row_stride, ring_slots, newest, static_cast<uint32_t>(rec.w),
+              ring_phase1<T, SKIPNA, 8, RMAX>(smem, L.row_stride, ring_slots, s03, s47,
                                               wk, s_tv, pw, col0, ncols, pad_shift, lane, ring.zero_fill);
               break;
           }
@@ -484,14 +500,13 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
         __syncwarp();
         // rows that are dead after this output are no longer read once the LAST strip's latitude
         // pass is done: publish this warp's progress so the producer can recycle them early
-        if (st + n_warps >= s_end && lane == 0)
-          st_release_smem(flags0 + 4u * (1 + warp), gbase + static_cast<uint32_t>(rec.y));
+        if (st + n_warps >= s_end && lane == 0) st_release_smem(flags0 + 4u * (1 + warp), rel_g);
         // ---- phase 2: longitude contraction, normalise, mask, store
 #pragma unroll
         for (int g = 0; g < TG; ++g) {
           if (lane + 32 * g < nl) {
             T out = nan;
-            if (rec.z >= 0 && ccnt[g] >= 0) {
+            if (rec.y >= 0 && ccnt[g] >= 0) {
               Entry e[KW];
 #pragma unroll
               for (int i = 0; i < KW; ++i) e[i] = s_tv[ci[g][i]];
@@ -509,7 +524,9 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
         }
       }
     }
-    gbase += static_cast<uint32_t>(ring.run_sched[run + 1] - ring.run_sched[run]);
+    const uint32_t run_len = static_cast<uint32_t>(ring.run_sched[run + 1] - ring.run_sched[run]);
+    gbase += run_len;
+    rot = (rot + run_len) % static_cast<uint32_t>(ring_slots);
   }
 }
 
@@ -638,20 +655,7 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
     fence_mbar_init();
   }
   if (tid < 32) s_flags[tid] = 0;
-  // the host record {need, release, kcnt, 8 x 4-bit rows-back} becomes {need | release << 16, kcnt,
-  // 8 x 8-bit ring slot of the tap relative to the run's first row}: the per-row path only adds the rotation
-  for (int i = tid; i < n_rows_out; i += blockDim.x) {
-    const int4 r = ring.krec[i];
-    const int cnt = r.z > 0 ? r.z : 0;
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int tp = 0; tp < kRingMaxTaps; ++tp) {
-      const int pos = r.x - 1 - static_cast<int>((static_cast<uint32_t>(r.w) >> (4 * tp)) & 15u);
-      const uint32_t sl = (tp < cnt && pos >= 0) ? static_cast<uint32_t>(pos % ring_slots) : 0u;
-      if (tp < 4) lo |= sl << (8 * tp); else hi |= sl << (8 * (tp - 4));
-    }
-    s_krec[i] = make_int4(r.x | (r.y << 16), r.z, static_cast<int>(lo), static_cast<int>(hi));
-  }
+  for (int i = tid; i < n_rows_out; i += blockDim.x) s_krec[i] = ring_row_record(ring.krec[i], ring_slots);
   for (int i = tid; i < n_rows_out * kRingMaxTaps; i += blockDim.x) s_wrec[i] = static_cast<const T*>(ring.wrec)[i];
   int32_t* s_sched = reinterpret_cast<int32_t*>(s_wrec + static_cast<size_t>(n_rows_out) * kRingMaxTaps);
   for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
