@@ -292,3 +292,66 @@ def test_threshold_ties_are_the_only_nan_placement_differences(engine):
     np.testing.assert_array_equal(np.isnan(y)[~ties], np.isnan(want)[~ties])
     both = ~np.isnan(y) & ~np.isnan(want)
     np.testing.assert_allclose(y[both], want[both], rtol=1e-12)
+
+
+# ------------------------------------------------------------------- column-panel layouts of the two-phase kernel
+PANEL_CASES = {
+    # name: (src lat, src lon, tgt lat, tgt lon)
+    "ratio2_centred": (np.arange(-90.0, 90.25, 0.5), np.arange(0.0, 360.0, 0.5),
+                       np.arange(-90.0, 90.5, 1.0), np.arange(0.0, 360.0, 1.0)),
+    "ratio2_edge_aligned_poles": (np.arange(-89.75, 90, 0.5), np.arange(0.25, 360, 0.5),
+                                  np.arange(-90.0, 90.5, 1.0), np.arange(0.0, 360.0, 1.0)),
+    "ratio2p5": (np.arange(-90.0, 90.5, 1.0), np.arange(0.0, 360.0, 1.0),
+                 np.arange(-90.0, 90.1, 2.5), np.arange(0.0, 360.0, 2.5)),
+    "ratio2_wide_two_panels": (np.arange(-45.0, 45.1, 0.25), np.arange(0.0, 360.0, 0.25),
+                               np.arange(-45.0, 45.1, 0.5), np.arange(0.0, 360.0, 0.5)),
+    "ragged_last_panel": (np.arange(-30.0, 30.1, 0.5), np.arange(0.0, 190.0, 0.5),   # regional: 7 strips -> 4 + 3
+                          np.arange(-30.0, 30.1, 1.0), np.arange(0.0, 189.5, 1.0)),
+    "descending_lat_shifted_lon": (np.arange(60.0, -60.1, -0.5), np.arange(-180.0, 180.0, 0.5),
+                                   np.arange(-60.0, 60.1, 1.0), np.arange(0.0, 360.0, 1.0)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(PANEL_CASES))
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_panel_layouts_match_oracle_and_generic_kernel(engine, case, dtype):
+    """Coarsening ratios of 2 - 2.5 run the two-phase ring kernel in its column-panel layout (several CTAs per
+    SM, strips of up to 64 targets, panels that wrap the date line, panels with fewer strips than consumer
+    warps, synthetic pole rows with weight).  Every NaN mode against the oracle and against the generic kernel."""
+    from xarray_regrid_b200 import tables
+
+    lat, lon, tlat, tlon = PANEL_CASES[case]
+    rng = np.random.default_rng(77)
+    x = (0.5 + rng.random((5, lat.size, lon.size))).astype(dtype)
+    x[rng.random(x.shape) < 0.06] = np.nan
+    x[1, 10:14, :] = np.nan        # whole target rows missing
+    x[2, :, 37:45] = np.nan        # whole target columns missing
+    x[3] = 2.5                     # NaN-free slab
+    spherical = case != "ratio2_edge_aligned_poles"  # keep a weight on the synthetic pole rows in that case
+    plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"),
+                                   spherical_rows=spherical)
+    xt = torch.from_numpy(x).cuda()
+    ring = plan._ring(5, lat.size, lon.size, xt.dtype)
+    assert ring is not None and ring.host.lane_cols == 0 and ring.host.n_warps <= 6, "panel layout expected"
+    assert int(np.diff(ring.host.strip_l0).max()) <= 64
+    if case == "ragged_last_panel" and dtype == np.float64:  # (the fp32 strip decomposition differs)
+        assert np.diff(ring.host.panel_strip0).min() < ring.host.n_warps
+    if case == "ratio2_edge_aligned_poles":
+        assert plan.pole_rows
+    rtol = 1e-12 if dtype == np.float64 else 2e-5
+    for skipna, thr in [(True, 0.3), (True, 1.0), (False, 1.0)]:
+        want, valid = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr,
+                                       latitude_weighting=spherical, return_valid=True)
+        ties = np.abs(valid - oc.valid_threshold(thr)) <= (1e-13 if dtype == np.float64 else 1e-6)
+        got = {}
+        for use_ring in (True, False):
+            plan.use_ring = use_ring
+            got[use_ring] = plan(xt, skipna=skipna, nan_threshold=thr).cpu().numpy()
+            y = got[use_ring]
+            np.testing.assert_array_equal(np.isnan(y)[~ties], np.isnan(want)[~ties])
+            both = ~np.isnan(y) & ~np.isnan(want)
+            np.testing.assert_allclose(y[both], want[both], rtol=rtol, atol=rtol)
+        plan.use_ring = True
+    # the host pipeline drives the same kernels chunk by chunk
+    y_host = plan.apply_host(torch.from_numpy(x).pin_memory(), skipna=True, nan_threshold=0.3, chunk_batch=2)
+    np.testing.assert_array_equal(y_host.numpy(), plan(xt, skipna=True, nan_threshold=0.3).cpu().numpy())
