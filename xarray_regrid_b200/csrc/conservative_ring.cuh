@@ -467,7 +467,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
 
       T* yrow = y + b * ybs + static_cast<long long>(k) * Wo;
       if (s_first + warp >= s_end) {  // a panel with fewer strips than consumer warps: only report progress
-        if (lane == 0) st_release_smem(flags0 + 4u * (1 + warp), rel_g);
+        if (lane == 0) st_relaxed_smem(flags0 + 4u * (1 + warp), rel_g);
         continue;
       }
       for (int st = s_first + warp; st < s_end; st += n_warps) {
@@ -500,7 +500,7 @@ conservative_ring_kernel(const T* __restrict__ x, T* __restrict__ y, long long b
         __syncwarp();
         // rows that are dead after this output are no longer read once the LAST strip's latitude
         // pass is done: publish this warp's progress so the producer can recycle them early
-        if (st + n_warps >= s_end && lane == 0) st_release_smem(flags0 + 4u * (1 + warp), rel_g);
+        if (st + n_warps >= s_end && lane == 0) st_relaxed_smem(flags0 + 4u * (1 + warp), rel_g);
         // ---- phase 2: longitude contraction, normalise, mask, store
 #pragma unroll
         for (int g = 0; g < TG; ++g) {
