@@ -360,7 +360,7 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   if (band_rows < kUpRowsPerSync || band_rows % kUpRowsPerSync != 0) return RG_ERR_UNSUPPORTED;
   if (band_rows > kUpBandRows) band_rows = kUpBandRows;
   // heavy taps (4 fp64 taps per column) use 512-thread CTAs so that the per-thread tap registers halve
-  const int nt = (cols.k_max > 2 && sizeof(T) == 8) ? 512 : 256;
+  const int nt = (cols.k_max >= 2 && sizeof(T) == 8) ? 512 : 256;
   if (Wo < 2 * W || Wo > nt * 4 * 4) return RG_ERR_UNSUPPORTED;  // upsampling, <= 4 groups / thread
   if ((reinterpret_cast<uintptr_t>(y) % 16) != 0 || (ybs * sizeof(T)) % 16 != 0 || (Wo * sizeof(T)) % 16 != 0)
     return RG_ERR_UNSUPPORTED;
