@@ -729,22 +729,27 @@ def run_engine_arm(args) -> None:
     if rank == 0 and world == 1 and not args.no_e2e:
         from xarray_regrid_b200.labelled import DataArray, Dataset
 
-        n_acc = min(256, my_steps)
+        n_acc = min(512, my_steps)
         xa = x[:n_acc].cpu().numpy()
         da = DataArray(xa, ("time", "latitude", "longitude"),
                        {"time": __import__("numpy").arange(n_acc), "latitude": lat, "longitude": lon})
         tgt = Dataset({}, {"latitude": tlat, "longitude": tlon})
         out = da.regrid.conservative(tgt, skipna=True, nan_threshold=NAN_THRESHOLD)  # warm-up (plan, staging)
+        out = None
+        # (the previous result is dropped before every call in both arms: its page-locked block is then reused
+        # instead of a second one being page-locked inside the timed region)
         t0 = time.perf_counter()
-        for _ in range(2):
+        for _ in range(3):
+            out = None
             out = da.regrid.conservative(tgt, skipna=True, nan_threshold=NAN_THRESHOLD)
-        dt_a = (time.perf_counter() - t0) / 2
+        dt_a = (time.perf_counter() - t0) / 3
         xp = torch.from_numpy(xa).pin_memory()
-        plan.apply_host(xp, skipna=True, nan_threshold=NAN_THRESHOLD)
+        ref = plan.apply_host(xp, skipna=True, nan_threshold=NAN_THRESHOLD)
         t0 = time.perf_counter()
-        for _ in range(2):
+        for _ in range(3):
+            ref = None
             ref = plan.apply_host(xp, skipna=True, nan_threshold=NAN_THRESHOLD)
-        dt_p = (time.perf_counter() - t0) / 2
+        dt_p = (time.perf_counter() - t0) / 3
         accessor = {
             "value": n_acc * BYTES_PER_TIMESTEP / dt_a / 1e9, "unit": "GB/s", "timesteps": n_acc,
             "apply_host_pinned_value": n_acc * BYTES_PER_TIMESTEP / dt_p / 1e9,

@@ -117,8 +117,10 @@ class HostPipeline:
         self.handle = handle
         import os
 
-        self.copy_threads = int(copy_threads or max(1, min(16, (os.cpu_count() or 2) // 2)))
-        self.stage_bytes = 4 * (32 << 20)  # staging ring per direction: 4 pieces of 32 MiB
+        # staging memcpy threads: most of the host's cores (the copies are what bounds the pageable path)
+        self.copy_threads = int(copy_threads or max(1, min(24, (os.cpu_count() or 2) - 2)))
+        self.stage_bytes = 4 * (32 << 20)  # staging ring per direction: 4 pieces of 32 MiB (measured best: 8 MiB
+        # pieces leave the per-piece event / launch latency exposed, 128 MiB ones overlap less)
         self._dev: dict = {}     # name -> per-slot device buffers (uint8)
         self._pinned: dict = {}  # direction -> page-locked staging ring (uint8)
         self.compute_stream = torch.cuda.ExternalStream(lib.rg_pipeline_stream(handle, 1), device=self.device)
@@ -240,6 +242,12 @@ class HostPipeline:
                 self.drain()
         return out_host
 
+
+# Results of the host paths are allocated page-locked even when the input is pageable (numpy): the D2H copies
+# then need no staging, and a fresh pageable result would pay a first-touch page fault per 4 KB while it is
+# filled (measured: 77 ms for a 267 MB result, more than the regrid itself).  torch's host allocator caches the
+# blocks, so only the first result of a size pays for the page-locking.
+PINNED_RESULTS = True
 
 _PIPELINES: dict = {}
 
@@ -492,7 +500,7 @@ class ConservativePlan(BandOp):
                     f"data is [{H}, {W}] but the plan was built for [{rows.host.n_src}, {cols.host.n_src}]")
             Ho, Wo = rows.host.n_out, cols.host.n_out
             if out_host is None:
-                out_host = torch.empty((B, Ho, Wo), dtype=dtype, pin_memory=x3.is_pinned())
+                out_host = torch.empty((B, Ho, Wo), dtype=dtype, pin_memory=x3.is_pinned() or PINNED_RESULTS)
             else:
                 out_host = _check_out_host(out_host, (B, Ho, Wo), dtype)
             if B == 0:
@@ -776,7 +784,7 @@ class InterpPlan:
         B, H, W = x3.shape
         Ho, Wo = self.out_hw(H, W)
         if out_host is None:
-            out_host = torch.empty((B, Ho, Wo), dtype=res_dtype, pin_memory=x3.is_pinned())
+            out_host = torch.empty((B, Ho, Wo), dtype=res_dtype, pin_memory=x3.is_pinned() or PINNED_RESULTS)
         else:
             out_host = _check_out_host(out_host, (B, Ho, Wo), res_dtype)
         if B == 0:
@@ -1001,7 +1009,7 @@ class ReducePlan:
         B, H, W = x3.shape
         Ho, Wo = self.out_hw(H, W)
         if out_host is None:
-            out_host = torch.empty((B, Ho, Wo), dtype=res_dtype, pin_memory=x3.is_pinned())
+            out_host = torch.empty((B, Ho, Wo), dtype=res_dtype, pin_memory=x3.is_pinned() or PINNED_RESULTS)
         else:
             out_host = _check_out_host(out_host, (B, Ho, Wo), res_dtype)
         if B:
