@@ -55,3 +55,32 @@ def test_host_copy_is_a_plain_memcpy():
         dst = np.zeros(n + 8, dtype=np.uint8)
         assert _lib.lib.rg_host_copy(dst.ctypes.data, src.ctypes.data, n, threads) == 0
         assert np.array_equal(dst[:n], src) and not dst[n:].any()
+
+
+def test_host_copy_pool_survives_fork():
+    """The staging memcpy keeps worker threads alive between calls; a fork()ed child (multiprocessing workers)
+    inherits the pool object but none of its threads and must start its own instead of waiting for them."""
+    import os
+    import warnings
+
+    import numpy as np
+
+    from xarray_regrid_b200 import _lib
+
+    src = np.random.default_rng(1).integers(0, 256, 48 << 20, dtype=np.uint8)
+    dst = np.zeros_like(src)
+    assert _lib.lib.rg_host_copy(dst.ctypes.data, src.ctypes.data, src.size, 6) == 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        pid = os.fork()
+    if pid == 0:
+        ok = 1
+        try:
+            d2 = np.zeros_like(src)
+            _lib.lib.rg_host_copy(d2.ctypes.data, src.ctypes.data, src.size, 6)
+            ok = 0 if np.array_equal(d2, src) else 1
+        finally:
+            os._exit(ok)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+    assert np.array_equal(dst, src)

@@ -4,6 +4,8 @@
 #include <thread>
 #include <vector>
 
+#include <pthread.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
@@ -92,9 +94,30 @@ class CopyPool {
   bool stop_ = false;
 };
 
+// The pool is intentionally leaked (its threads must not be joined at exit), and a fork()ed child -- which
+// inherits the object but none of its threads -- starts a fresh one.
+static std::atomic<CopyPool*> g_copy_pool{nullptr};
+static std::mutex g_copy_pool_mutex;
+
 inline CopyPool& copy_pool() {
-  static CopyPool* pool = new CopyPool();  // intentionally leaked: worker threads must not be joined at exit
-  return *pool;
+  CopyPool* p = g_copy_pool.load(std::memory_order_acquire);
+  if (!p) {
+    std::lock_guard<std::mutex> lk(g_copy_pool_mutex);
+    p = g_copy_pool.load(std::memory_order_acquire);
+    if (!p) {
+      static bool hooked = false;
+      if (!hooked) {
+        pthread_atfork(nullptr, nullptr, [] {
+          g_copy_pool.store(nullptr, std::memory_order_release);
+          new (&g_copy_pool_mutex) std::mutex();  // the parent may have held it at fork time
+        });
+        hooked = true;
+      }
+      p = new CopyPool();
+      g_copy_pool.store(p, std::memory_order_release);
+    }
+  }
+  return *p;
 }
 
 }  // namespace rg
