@@ -389,3 +389,66 @@ def test_c2_full_stack_8760_steps(engine):
     # NaN fraction of the result is plausible for a 10 % masked input with a 0.5 threshold
     frac = float(torch.isnan(y).float().mean())
     assert 0.02 < frac < 0.2
+
+
+# --------------------------------------------------------------- more than two regridded coordinates at once
+def test_conservative_over_three_coordinates_joint_valid_mass():
+    """The reference contracts ALL shared coordinates in one `xr.dot` (methods/conservative.py:188-198), so the
+    valid mass is joint over (level, latitude, longitude).  The engine folds level x latitude into the kernels'
+    rows axis (tables.kron_band)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xarray_regrid_b200.labelled import DataArray, Dataset
+
+    rng = np.random.default_rng(12)
+    lev, tlev = np.arange(0.0, 10.0), np.array([0.5, 2.5, 4.5, 6.5, 8.5])
+    lat, tlat = np.arange(-30.0, 30.1, 1.0), np.arange(-28.0, 28.1, 4.0)
+    lon, tlon = np.arange(0.0, 360.0, 2.0), np.arange(0.0, 360.0, 8.0)
+    x = 0.5 + rng.random((3, lev.size, lat.size, lon.size))
+    x[rng.random(x.shape) < 0.15] = np.nan
+    x[1, 2:4, 10:20, 30:60] = np.nan
+    da = DataArray(x, ("time", "level", "latitude", "longitude"),
+                   {"time": np.arange(3), "level": lev, "latitude": lat, "longitude": lon})
+    tgt = Dataset({}, {"level": tlev, "latitude": tlat, "longitude": tlon})
+    xf, latf, lonf = of.format_for_regrid(x, lat, lon, tlat, tlon)
+    for skipna, thr in [(True, 0.4), (True, 1.0), (False, 1.0)]:
+        out = da.regrid.conservative(tgt, skipna=skipna, nan_threshold=thr)
+        assert out.dims == da.dims and out.shape == (3, tlev.size, tlat.size, tlon.size)
+        want, valid = oc.regrid(xf, [lev, latf, lonf], [tlev, tlat, tlon], [-3, -2, -1], latitude_index=1,
+                                skipna=skipna, nan_threshold=thr, return_valid=True)
+        ties = np.abs(valid - oc.valid_threshold(thr)) <= 1e-13
+        np.testing.assert_array_equal(np.isnan(out.data)[~ties], np.isnan(want)[~ties])
+        both = ~np.isnan(out.data) & ~np.isnan(want)
+        np.testing.assert_allclose(out.data[both], want[both], rtol=1e-12)
+    # dims in another order, CUDA input
+    xt = torch.from_numpy(np.ascontiguousarray(x.transpose(2, 0, 3, 1))).cuda()
+    da2 = DataArray(xt, ("latitude", "time", "longitude", "level"), dict(da.coords))
+    out2 = da2.regrid.conservative(tgt, skipna=True, nan_threshold=0.4)
+    ref = da.regrid.conservative(tgt, skipna=True, nan_threshold=0.4).data
+    got2 = out2.data.cpu().numpy()  # (the folding order follows the dim order: same taps, another summation order)
+    np.testing.assert_array_equal(np.isnan(got2), np.isnan(ref.transpose(2, 0, 3, 1)))
+    np.testing.assert_allclose(got2, ref.transpose(2, 0, 3, 1), rtol=1e-13)
+
+
+@pytest.mark.parametrize("method", ["linear", "nearest", "cubic"])
+def test_interp_over_three_coordinates(method):
+    """xr.interp interpolates coordinate after coordinate: three shared coordinates = the fused (lat, lon) pass,
+    then the third axis."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xarray_regrid_b200.labelled import DataArray, Dataset
+
+    rng = np.random.default_rng(13)
+    lev, tlev = np.arange(0.0, 12.0), np.linspace(0.5, 10.5, 9)
+    lat, tlat = np.arange(-30.0, 30.1, 2.0), np.arange(-29.0, 29.1, 0.5)
+    lon, tlon = np.arange(0.0, 360.0, 4.0), np.arange(0.0, 358.0, 1.5)
+    x = rng.random((2, lev.size, lat.size, lon.size))
+    da = DataArray(x, ("time", "level", "latitude", "longitude"),
+                   {"time": np.arange(2), "level": lev, "latitude": lat, "longitude": lon})
+    tgt = Dataset({}, {"level": tlev, "latitude": tlat, "longitude": tlon})
+    out = getattr(da.regrid, method)(tgt)
+    xf, latf, lonf = of.format_for_regrid(x, lat, lon, tlat, tlon)
+    want = oi.regrid(xf, [latf, lonf, lev], [tlat, tlon, tlev], [-2, -1, -3], method)
+    assert out.shape == want.shape
+    np.testing.assert_array_equal(np.isnan(out.data), np.isnan(want))
+    np.testing.assert_allclose(out.data, want, rtol=0 if method == "nearest" else 1e-10, atol=1e-12)

@@ -347,3 +347,20 @@ def test_pole_rows_come_from_the_sorted_edge_rows(order, lon_mean):
         data, flat = of.format_lat(*of.ensure_monotonic(x, lat, 0), 0, 1)
     want = oi.regrid(data, [flat], [tlat], [0], "linear")
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def test_kron_band_is_the_kronecker_product_of_the_dense_weights():
+    """tables.kron_band folds two regridded axes into one (flattened) axis: its dense matrix is the Kronecker
+    product of the two axes' weight matrices, its coverage the AND of theirs."""
+    z, tz = np.arange(0.0, 12.0), np.array([8.5, 0.5, 2.5, 12.5])  # unsorted target, one target outside
+    lat, tlat = np.arange(-10.0, 10.1, 1.0), np.arange(-9.0, 9.1, 3.0)
+    bo = tables.conservative_band(tables.plain_axis(z), tz)
+    bi = tables.conservative_band(tables.format_lat_axis(lat), tlat, spherical=True)
+    k = tables.kron_band(bo, bi)
+    want = np.einsum("ik,jl->ijkl", bo.dense(), bi.dense()).reshape(z.size * lat.size, tz.size * tlat.size)
+    np.testing.assert_array_equal(k.dense(), want)
+    np.testing.assert_array_equal(k.cover.reshape(tz.size, tlat.size), bo.cover[:, None] & bi.cover[None, :])
+    assert k.n_src == z.size * lat.size and k.k_max == bo.k_max * bi.k_max
+    with pytest.raises(NotImplementedError):  # pole rows keep a weight without the spherical correction
+        tables.kron_band(bo, tables.conservative_band(tables.format_lat_axis(np.arange(-89.5, 90, 1.0)),
+                                                      np.arange(-90.0, 91, 5.0)))

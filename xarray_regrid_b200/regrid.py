@@ -89,7 +89,7 @@ def _layout(da: DataArray, names, prefer_rows=None):
     if not names:
         return None
     if len(names) > 2:
-        raise NotImplementedError("regridding over more than two dimensions at once is not supported")
+        raise NotImplementedError("this method regrids at most two dimensions at once")
     rows = next((n for n in names if _kind(n) == "lat"), None)
     cols = next((n for n in names if _kind(n) == "lon"), None)
     rest = sorted((n for n in names if n not in (rows, cols)),
@@ -100,6 +100,17 @@ def _layout(da: DataArray, names, prefer_rows=None):
         elif cols is None:
             cols = n
     return rows, cols
+
+
+def _interp_groups(da: DataArray, names):
+    """Regridded coordinate names of ``da`` in groups of at most two: lat + lon together, the rest alone."""
+    names = [n for n in names if n in da.dims]
+    if len(names) <= 2:
+        return [names]
+    pair = [n for n in names if _kind(n) in ("lat", "lon")][:2]
+    rest = [n for n in names if n not in pair]
+    groups = [pair] if pair else []
+    return groups + [[n] for n in rest]
 
 
 def _to_device(data):
@@ -178,6 +189,53 @@ def _apply(da: DataArray, target: Dataset, names, run, coord_attrs_from: str, pr
     return DataArray(_from_device(y.contiguous(), how), da.dims, coords, dict(da.attrs), cattrs, da.name)
 
 
+def _conservative_nd(da: DataArray, target: Dataset, names, latitude_coord, skipna, nan_threshold) -> DataArray:
+    """Conservative regridding over MORE than two coordinates at once, with the reference's joint valid mass
+    (``xr.dot`` contracts all regridded dims together, methods/conservative.py:188-198): every coordinate but the
+    last is folded into the kernels' rows axis through a Kronecker band (``tables.kron_band``), then the usual
+    fused kernels run on ``[batch, rows..., cols]`` viewed as ``[batch, prod(rows), cols]``."""
+    cols = next((n for n in names if _kind(n) == "lon"), None) or max(names, key=da.dims.index)
+    folded = sorted((n for n in names if n != cols), key=da.dims.index)
+    batch = [d for d in da.dims if d not in names]
+    order = batch + folded + [cols]
+    x, how = _to_device(da.data)
+    x = x.permute([da.dims.index(d) for d in order]).contiguous()
+    has_lon = cols is not None and _kind(cols) == "lon"
+
+    def axis_band(n):
+        spec = engine.AxisSpec(np.asarray(da.coords[n]), np.asarray(target.coords[n]), _kind(n))
+        if _kind(n) == "lon":
+            ax = tables.format_lon_axis(spec.src, spec.tgt)
+        elif _kind(n) == "lat":
+            ax = tables.format_lat_axis(spec.src, lon_mean=has_lon)
+        else:
+            ax = tables.plain_axis(spec.src)
+        return tables.conservative_band(ax, spec.tgt, spherical=(n == latitude_coord))
+
+    key = _key("conservative-nd", tuple(names), latitude_coord,
+               *[np.asarray(da.coords[n]) for n in folded + [cols]],
+               *[np.asarray(target.coords[n]) for n in folded + [cols]], str(x.device))
+
+    def build():
+        rows_band = axis_band(folded[0])
+        for n in folded[1:]:
+            rows_band = tables.kron_band(rows_band, axis_band(n))
+        return engine.BandOp(rows_band, axis_band(cols), x.device)
+
+    op = _cached(key, build)
+    lead = x.shape[:len(batch)]
+    n_rows = int(np.prod([x.shape[len(batch) + i] for i in range(len(folded))]))
+    dtype = engine._result_dtype(x)
+    x3 = x.reshape((-1, n_rows, x.shape[-1])).to(dtype)
+    y = op.run(x3, engine.NAN_SKIP if skipna else engine.NAN_ZERO, tables.valid_threshold(nan_threshold))
+    out_shape = tuple(lead) + tuple(len(target.coords[n]) for n in folded) + (len(target.coords[cols]),)
+    y = y.reshape(out_shape).permute([order.index(d) for d in da.dims])
+    coords = dict(da.coords)
+    for n in names:
+        coords[n] = np.asarray(target.coords[n])
+    return DataArray(_from_device(y.contiguous(), how), da.dims, coords, dict(da.attrs), dict(da.coord_attrs), da.name)
+
+
 def _map(obj, fn):
     """Apply ``fn`` to a DataArray or to every data variable of a Dataset (utils.py:201-224)."""
     if isinstance(obj, DataArray):
@@ -215,7 +273,12 @@ class Regridder:
                 plan = _cached(key, lambda: engine.InterpPlan(rs, cs, method, device=dev))
                 return plan.apply_host(x) if host else plan(x)
 
-            return _apply(da, target, names, run, "data")
+            # xr.interp interpolates one coordinate after the other (interp.py:39-46), so more than two shared
+            # coordinates are a chain: the (lat, lon) pair in one fused pass, the others one by one
+            out = da
+            for group in _interp_groups(da, names):
+                out = _apply(out, target, group, run, "data")
+            return out
 
         return _map(self._obj, one)
 
@@ -263,6 +326,9 @@ class Regridder:
                     return plan.apply_host(x, skipna=skipna, nan_threshold=nan_threshold)
                 return plan(x, skipna=skipna, nan_threshold=nan_threshold)
 
+            if len([n for n in names if n in da.dims]) > 2:
+                return _conservative_nd(da, target, [n for n in names if n in da.dims], latitude_coord, skipna,
+                                        nan_threshold)
             return _apply(da, target, names, run, "data", prefer_rows=latitude_coord)
 
         return _map(self._obj, one)

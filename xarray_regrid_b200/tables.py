@@ -278,6 +278,38 @@ def conservative_band(axis: FormattedAxis, tgt, spherical: bool = False) -> Band
                 {"formatted_size": int(src.size), "pole_rows": axis.has_pole_rows, "pole_src": axis.pole_src})
 
 
+def kron_band(outer: Band, inner: Band) -> Band:
+    """Band of the FLATTENED axis ``outer x inner`` (C order: index = i_outer * n_inner + i_inner) whose weights
+    are the products of the two bands' weights: contracting it is contracting both axes at once.
+
+    This is how more than two coordinates are regridded conservatively in one pass with the reference's JOINT
+    valid mass (``xr.dot`` over all regridded dims, methods/conservative.py:188-198): every axis but the last is
+    folded into the kernels' rows axis.  Taps multiply (k_outer * k_inner per output); synthetic pole rows have no
+    place in a flattened axis (under the spherical correction they carry zero weight and are dropped anyway)."""
+    if (outer.idx >= outer.n_src).any() or (inner.idx >= inner.n_src).any():
+        raise NotImplementedError("synthetic pole rows cannot be folded into a flattened axis")
+    ko, ki = outer.k_max, inner.k_max
+    no, ni = outer.n_out, inner.n_out
+    live_o = np.arange(ko)[:, None] < outer.cnt[None, :]
+    live_i = np.arange(ki)[:, None] < inner.cnt[None, :]
+    # [ko, ki, no, ni] -> taps of output (o, i) ordered (to, ti); dead taps are compacted away below
+    idx = outer.idx[:, None, :, None].astype(np.int64) * inner.n_src + inner.idx[None, :, None, :]
+    w = outer.w[:, None, :, None] * inner.w[None, :, None, :]
+    live = live_o[:, None, :, None] & live_i[None, :, None, :]
+    idx = np.where(live, idx, 0).reshape(ko * ki, no * ni)
+    w = np.where(live, w, 0.0).reshape(ko * ki, no * ni)
+    live = live.reshape(ko * ki, no * ni)
+    order = np.argsort(~live, axis=0, kind="stable")
+    idx = np.take_along_axis(idx, order, axis=0)
+    w = np.take_along_axis(w, order, axis=0)
+    cnt = live.sum(axis=0).astype(np.int32)
+    k = int(max(cnt.max(), 1))
+    cover = (outer.cover[:, None].astype(bool) & inner.cover[None, :].astype(bool)).reshape(-1)
+    return Band(np.ascontiguousarray(idx[:k].astype(np.int32)), np.ascontiguousarray(w[:k]), cnt,
+                cover.astype(np.uint8), outer.n_src * inner.n_src, None,
+                {"pole_rows": False, "pole_src": (0, 0), "kron": (no, ni)})
+
+
 def identity_band(n: int) -> Band:
     """Pass-through axis (used when only one spatial coordinate is regridded)."""
     return Band(
