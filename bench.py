@@ -83,7 +83,7 @@ class ClockSampler:
     FIELDS = (
         "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks.mem,temperature.gpu"
     )
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
@@ -122,7 +122,17 @@ class ClockSampler:
                 continue
             try:
                 ts = dt.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                self.rows.append((ts, float(parts[1]), float(parts[2]), parts[5:9]))
+                extra = []
+                for v in parts[9:11]:
+                    try:
+                        extra.append(float(v))
+                    except ValueError:
+                        extra.append(None)
+                try:
+                    extra.append(float(parts[3]))
+                except ValueError:
+                    extra.append(None)
+                self.rows.append((ts, float(parts[1]), float(parts[2]), parts[5:9], extra))
             except ValueError:
                 continue
         try:
@@ -135,16 +145,26 @@ class ClockSampler:
         self._finish()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm, mx, reasons = [], [], set()
-        for ts, clk, cmax, flags in self.rows:
+        mem, temp, power = [], [], []
+        for ts, clk, cmax, flags, extra in self.rows:
             if ts < t0 - 0.05 or ts > t1 + 0.05:
                 continue
             sm.append(clk)
             mx.append(cmax)
+            for lst, v in zip((mem, temp, power), extra):
+                if v is not None:
+                    lst.append(v)
             for name, val in zip(self.NAMES, flags):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        if mem:
+            out["mem_mhz"] = statistics.median(mem)
+        if temp:
+            out["temp_c"] = max(temp)
+        if power:
+            out["power_w"] = statistics.median(power)
         out["reasons"] = sorted(reasons)
         return out
 
@@ -668,7 +688,19 @@ def run_engine_arm(args) -> None:
             best = min(best, c0.elapsed_time(c1))
         roofline["copy_gbs_this_gpu_now"] = 2 * a_.numel() * 2 / (best * 1e-3) / 1e9
         roofline["frac_of_copy_this_gpu_now"] = achieved / roofline["copy_gbs_this_gpu_now"]
-        del a_, b_
+        # ... and a pure READ (torch sum over the same 2 GiB): the regrid is 94 % reads, and the read rate is what
+        # differs most between the GPUs of the pool (6.1 - 7 TB/s)
+        a32 = a_.view(torch.float32)
+        best_r = float("inf")
+        for _ in range(8):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            a32.sum()
+            c1.record()
+            torch.cuda.synchronize(device)
+            best_r = min(best_r, c0.elapsed_time(c1))
+        roofline["read_gbs_this_gpu_now"] = a_.numel() * 2 / (best_r * 1e-3) / 1e9
+        del a_, b_, a32
     except Exception:  # noqa: BLE001 - out of memory next to the 72.8 GB stack: skip the extra figure
         pass
     traffic_file = ROOT / "profiles" / "traffic_conservative.json"
