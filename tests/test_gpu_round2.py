@@ -312,15 +312,24 @@ PANEL_CASES = {
 }
 
 
+PANEL_CASES["ratio2_odd_targets_regional"] = (np.arange(-30.0, 30.1, 0.5), np.arange(10.0, 130.0, 0.5),
+                                              np.arange(-30.0, 30.1, 1.0), np.arange(10.0, 128.5, 1.0))  # 240 -> 119
+PAIR_CASES = {"ratio2_centred", "ratio2_edge_aligned_poles", "ratio2_wide_two_panels", "ragged_last_panel",
+              "descending_lat_shifted_lon", "ratio2_odd_targets_regional"}  # coarsening by exactly two
+
+
 @pytest.mark.parametrize("case", sorted(PANEL_CASES))
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_panel_layouts_match_oracle_and_generic_kernel(engine, case, dtype):
-    """Coarsening ratios of 2 - 2.5 run the two-phase ring kernel in its column-panel layout (several CTAs per
-    SM, strips of up to 64 targets, panels that wrap the date line, panels with fewer strips than consumer
-    warps, synthetic pole rows with weight).  Every NaN mode against the oracle and against the generic kernel."""
-    from xarray_regrid_b200 import tables
-
+@pytest.mark.parametrize("layout", ["default", "panels"])
+def test_panel_layouts_match_oracle_and_generic_kernel(engine, case, dtype, layout):
+    """Coarsening ratios of 2 - 2.5.  ``panels``: the two-phase ring kernel in its column-panel layout (several
+    CTAs per SM, strips of up to 64 targets, panels that wrap the date line, panels with fewer strips than
+    consumer warps, synthetic pole rows with weight).  ``default``: ratio 2 runs the register-resident kernel with
+    two targets per lane (halo lanes at both ends of a warp, odd target counts, regional axes, the date line inside
+    a warp).  Every NaN mode against the oracle and against the generic kernel."""
     lat, lon, tlat, tlon = PANEL_CASES[case]
+    if layout == "default" and case not in PAIR_CASES:
+        pytest.skip("the default layout of this case is the panel one")
     rng = np.random.default_rng(77)
     x = (0.5 + rng.random((5, lat.size, lon.size))).astype(dtype)
     x[rng.random(x.shape) < 0.06] = np.nan
@@ -330,12 +339,20 @@ def test_panel_layouts_match_oracle_and_generic_kernel(engine, case, dtype):
     spherical = case != "ratio2_edge_aligned_poles"  # keep a weight on the synthetic pole rows in that case
     plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"),
                                    spherical_rows=spherical)
+    plan.use_lanes = layout == "default"
     xt = torch.from_numpy(x).cuda()
     ring = plan._ring(5, lat.size, lon.size, xt.dtype)
-    assert ring is not None and ring.host.lane_cols == 0 and ring.host.n_warps <= 6, "panel layout expected"
-    assert int(np.diff(ring.host.strip_l0).max()) <= 64
-    if case == "ragged_last_panel" and dtype == np.float64:  # (the fp32 strip decomposition differs)
-        assert np.diff(ring.host.panel_strip0).min() < ring.host.n_warps
+    assert ring is not None
+    if layout == "default":
+        assert ring.host.lane_cols == 2 and ring.host.n_warps <= 12, "two targets per lane expected"
+        assert int(np.diff(ring.host.strip_l0).max()) <= 60
+        # the interpolation (NaN-propagating) mode never takes that layout
+        assert plan._ring(5, lat.size, lon.size, xt.dtype, pairs=False).host.lane_cols == 0
+    else:
+        assert ring.host.lane_cols == 0 and ring.host.n_warps <= 6, "panel layout expected"
+        assert int(np.diff(ring.host.strip_l0).max()) <= 64
+        if case == "ragged_last_panel" and dtype == np.float64:  # (the fp32 strip decomposition differs)
+            assert np.diff(ring.host.panel_strip0).min() < ring.host.n_warps
     if case == "ratio2_edge_aligned_poles":
         assert plan.pole_rows
     rtol = 1e-12 if dtype == np.float64 else 2e-5
@@ -355,6 +372,22 @@ def test_panel_layouts_match_oracle_and_generic_kernel(engine, case, dtype):
     # the host pipeline drives the same kernels chunk by chunk
     y_host = plan.apply_host(torch.from_numpy(x).pin_memory(), skipna=True, nan_threshold=0.3, chunk_batch=2)
     np.testing.assert_array_equal(y_host.numpy(), plan(xt, skipna=True, nan_threshold=0.3).cpu().numpy())
+
+
+def test_interp_on_a_ratio2_grid_keeps_nan_propagation(engine):
+    """Linear interpolation onto a grid twice as coarse shares the bands' shape with the conservative case but must
+    not take the two-targets-per-lane kernel (its zero-weight taps would spread a NaN to the neighbouring target)."""
+    lat, lon = np.arange(-30.0, 30.1, 0.5), np.arange(0.0, 360.0, 0.5)
+    tlat, tlon = np.arange(-29.75, 30.0, 1.0), np.arange(0.25, 359.0, 1.0)
+    rng = np.random.default_rng(5)
+    x = rng.random((3, lat.size, lon.size))
+    x[rng.random(x.shape) < 0.02] = np.nan
+    plan = engine.InterpPlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"), "linear")
+    y = plan(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = oi.regrid_latlon(x, lat, lon, tlat, tlon, "linear")
+    assert np.isnan(want).any()
+    np.testing.assert_array_equal(np.isnan(y), np.isnan(want))
+    np.testing.assert_allclose(y[~np.isnan(y)], want[~np.isnan(want)], rtol=1e-12)
 
 
 def test_c2_full_stack_8760_steps(engine):

@@ -262,9 +262,23 @@ def test_lane_owned_columns_eligibility():
         assert all(b - a <= 31 for a, b in zip(ring.strip_l0[:-1], ring.strip_l0[1:]))
         first = cols.idx[0].astype(np.int64)
         assert (first % 2 == 0).all() and ((np.diff(first) - 4) % cols.n_src == 0).all()
-    # 2:1 coarsening, a regional target (uncovered edge cells) and a non-integer ratio do not qualify
-    ring, _ = ring_for(lat1, lon1, np.arange(-90, 91, 2.0), np.arange(0, 360, 2.0))
-    assert ring is None or ring.lane_cols == 0
+    # 2:1 coarsening takes the two-targets-per-lane layout: <= 30 pairs per warp, own blocks start on even columns,
+    # every tap of pair p inside [c0 + 4p - 1, c0 + 4p + 4]
+    for lon_t in (np.arange(0, 360, 2.0), np.arange(0.5, 360, 2.0), np.arange(0, 357, 2.0)):
+        ring, cols = ring_for(lat1, lon1, np.arange(-90, 91, 2.0), lon_t)
+        assert ring.lane_cols == 2 and ring.n_strips == ring.n_warps <= 12 and ring.n_panels == 1
+        assert (ring.strip_c0 % 2 == 0).all() and (np.diff(ring.strip_l0) <= 60).all()
+        assert ring.strip_l0[0] == 0 and ring.strip_l0[-1] == cols.n_out
+        for s in range(ring.n_strips):
+            for l in range(ring.strip_l0[s], ring.strip_l0[s + 1]):
+                c0 = ring.strip_c0[s] + 4 * ((l - ring.strip_l0[s]) // 2)
+                q = (cols.idx[: cols.cnt[l], l].astype(np.int64) - (c0 - 1)) % cols.n_src
+                assert (q < 6).all(), (s, l, q)
+        # ... but not for the NaN-propagating interpolation mode
+        rows = tables.conservative_band(engine._axis(engine.AxisSpec(lat1, np.arange(-90, 91, 2.0), "lat"), True),
+                                        np.arange(-90, 91, 2.0), spherical=True)
+        assert tables.row_ring_schedule(rows, 4, cols, 2, allow_pairs=False).lane_cols == 0
+    # a regional target with uncovered edge cells and a non-integer ratio do not qualify for either
     ring, _ = ring_for(lat025[200:400], lon025[100:700], lat1[40:110], lon1[20:180])
     assert ring is None or ring.lane_cols == 0
     ring, _ = ring_for(lat025, lon025, np.arange(-90, 90.1, 0.7), np.arange(0, 360, 0.7))

@@ -98,5 +98,11 @@ __device__ __forceinline__ void st_stream(double* p, double v) {
 __device__ __forceinline__ void st_stream(float* p, float v) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+__device__ __forceinline__ void st_stream2(double* p, double a, double b) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream2(float* p, float a, float b) {
+  asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 
 }  // namespace rg

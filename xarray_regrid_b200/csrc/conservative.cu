@@ -233,12 +233,19 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
 
   // ---- fast path: TMA row-ring kernels (need 16-byte aligned rows, <= 8 taps per
   //      axis, a ring that fits shared memory)
+  // lane_cols == 2: the register-resident kernel with two targets per lane (<= 30 pairs per warp, conservative
+  // NaN modes only).  That strip layout has no two-phase form: anything else goes to the generic kernel.
+  const bool lanes2 = ring_c && ring_c->lane_cols == 2 && cols.k_max <= 3 && rows.k_max <= 5 &&
+                      (skipna || zero_fill) && ring_c->strip_targets_max <= 60 && ring_c->n_panels == 1 &&
+                      ring_c->n_strips <= ring_c->n_warps && ring_c->n_warps + 2 <= 14 && W % 2 == 0;
+  if (ring_c && ring_c->lane_cols == 2 && !lanes2) ring_c = nullptr;
   if (ring_c && aligned && (static_cast<size_t>(W) * sizeof(T)) % 16 == 0 &&
       (!pole || reinterpret_cast<uintptr_t>(pole) % 16 == 0) &&
       rows.k_max <= kRingMaxTaps && cols.k_max <= 8 && ring_c->n_runs > 0 && ring_c->n_strips > 0 &&
       ring_c->n_sched < 65536 &&  // the staged per-row record packs need / release into 16 bits each
       ring_c->n_warps >= 1 && ring_c->n_warps <= kRingMaxWarps && ring_c->max_live <= kRingMaxLive &&
-      (ring_c->strip_targets_max <= 32 || (ring_c->strip_targets_max <= 64 && ring_c->n_warps <= 6 && cols.k_max >= 3)) &&
+      (ring_c->strip_targets_max <= 32 || lanes2 ||
+       (ring_c->strip_targets_max <= 64 && ring_c->n_warps <= 6 && cols.k_max >= 3)) &&
       ring_c->sched_row && ring_c->krec && ring_c->wrec && ring_c->run_first && ring_c->run_sched &&
       ring_c->strip_l0 && ring_c->strip_c0 && ring_c->strip_nc) {
     const int kw = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : cols.k_max <= 3 ? 3 : cols.k_max <= 5 ? 5 : 8;
@@ -248,12 +255,14 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     const int wp = have_panels ? ring_c->panel_cols_max : W;  // columns of a ring row
     // lane-owned columns variant (4 source columns + 1 per target, see conservative_ring.cuh): no strip buffers
     // (the staged per-row record packs need / release into 16 bits each)
-    const bool lanes = ring_c->lane_cols == 4 && cols.k_max <= 5 && ring_c->n_strips <= ring_c->n_warps &&
+    const bool lanes = ((ring_c->lane_cols == 4 && cols.k_max <= 5) || lanes2) && ring_c->n_strips <= ring_c->n_warps &&
                        ring_c->n_warps + 2 <= 14 && W % 2 == 0 && ring_c->n_sched < 65536 && n_panels == 1 && wp == W;
     // panel layouts of the two-phase kernel: 6 consumer warps, several CTAs per SM
     const bool panel_cta = !lanes && have_panels && ring_c->n_warps <= 6 && kw >= 3;
     const bool panel_tg2 = panel_cta && ring_c->strip_targets_max > 32;
-    const int min_ctas = lanes ? (sizeof(T) == 4 ? 2 : 1)
+    // (register-resident kernel: 14 warps of fp64 fill an SM's registers; rows of <= 6 consumer warps leave room
+    // for a second -- fp32: third -- CTA)
+    const int min_ctas = lanes ? ((sizeof(T) == 4 ? 2 : 1) + (ring_c->n_warps <= 6 ? 1 : 0))
                          : panel_cta ? ((rows.k_max <= 4 && !(panel_tg2 && kw >= 5)) ? 3 : 2) : 1;
     const RingLayout probe =
         lanes ? ring_layout<T>(W, 31, false, 0, 0, 0)
@@ -344,7 +353,8 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       long long grid = static_cast<long long>(dev.sm_count) * ctas;
       if (grid > tasks) grid = tasks;
       if (lanes) {
-        auto lk = rows.k_max <= 5
+        auto lk = lanes2 ? (skipna ? conservative_lanes_kernel<T, true, 14, 5, 2> : conservative_lanes_kernel<T, false, 14, 5, 2>)
+                  : rows.k_max <= 5
                       ? (skipna ? conservative_lanes_kernel<T, true, 14, 5> : conservative_lanes_kernel<T, false, 14, 5>)
                       : (skipna ? conservative_lanes_kernel<T, true, 14, 8> : conservative_lanes_kernel<T, false, 14, 8>);
         const size_t smem_l = L.total + row_tables;

@@ -633,7 +633,12 @@ __device__ __forceinline__ void lane_phase1_dispatch(int cnt, uint32_t baseA, ui
 #undef RG_L1
 }
 
-template <typename T, bool SKIPNA, int MAXWARPS, int RMAX>
+//
+// M = 2 (rg_row_ring_t.lane_cols == 2, coarsening by two, conservative NaN modes only): a lane still owns 4
+// source columns but produces the PAIR of targets whose (<= 3 contiguous) taps lie in its block and the two
+// columns next to it: the left one comes from the previous lane, the right one from the next.  Lane 0 of a warp
+// and the lane after its last pair only produce those halos; strip_c0[warp] = first own column of the first pair.
+template <typename T, bool SKIPNA, int MAXWARPS, int RMAX, int M = 1>
 __global__ void __launch_bounds__(MAXWARPS * 32, sizeof(T) == 4 ? 2 : 1)
 conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
                           long long xrs, long long ybs, Band<T> cols, RingDev ring, T thr, int ring_slots,
@@ -685,6 +690,12 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   const int l = l0 + m;
   // first source column of this lane's group of 4 (the halo lane continues one group further)
   int cfirst = (has_strip && nl > 0) ? cols.idx[l] + 4 * ((lane < nl ? lane : nl) - m) : 0;
+  const int n_pairs = (nl + 1) >> 1;  // M = 2: host contract <= 30
+  if constexpr (M == 2) {
+    const int blk = (lane <= n_pairs ? lane : n_pairs + 1) - 1;  // -1: left halo block, n_pairs: right halo block
+    cfirst = has_strip ? ring.strip_c0[warp] + 4 * blk : 0;
+    cfirst = ((cfirst % W) + W) % W;
+  }
   constexpr int SWZ = sizeof(T) == 8 ? 2 : 3;
   const int swz = (lane >> SWZ) & 1;
   int jA = cfirst + 2 * swz, jB = cfirst + 2 * (1 - swz);
@@ -700,11 +711,49 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   const T twA0 = swz ? tw[2] : tw[0], twA1 = swz ? tw[3] : tw[1];
   const T twB0 = swz ? tw[0] : tw[2], twB1 = swz ? tw[1] : tw[3];
   const T tw4 = tw[4];
+  // M = 2: weights of the lane's two targets over {left halo, own 4 columns in register order, right halo}
+  T tw2[M == 2 ? 2 : 1][6];
+  bool have2[2] = {false, false};
+  bool pair_store = false;
+  if constexpr (M == 2) {
+    const int c_left = (cfirst + W - 1) % W;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int lj = 2 * (lane - 1) + j;  // target inside the strip
+      const bool live = has_strip && lane >= 1 && lj < nl;
+      have2[j] = live && cols.cover[live ? l0 + lj : 0] != 0;
+      T nat[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) nat[q] = T(0);
+      if (have2[j]) {
+        const int cj = cols.cnt[l0 + lj];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < cj && i < cols.k_max) {
+            const int q = (cols.idx[i * Wo + l0 + lj] - c_left + W) % W;
+            const T wv = cols.w[i * Wo + l0 + lj];
+#pragma unroll
+            for (int qq = 0; qq < 6; ++qq)
+              if (qq == q) nat[qq] = wv;
+          }
+        }
+      }
+      tw2[j][0] = nat[0];
+      tw2[j][1] = swz ? nat[3] : nat[1];
+      tw2[j][2] = swz ? nat[4] : nat[2];
+      tw2[j][3] = swz ? nat[1] : nat[3];
+      tw2[j][4] = swz ? nat[2] : nat[4];
+      tw2[j][5] = nat[5];
+    }
+    // both targets of a pair in one 2-element store where every such address is aligned
+    pair_store = (Wo % 2 == 0) && (ybs % 2 == 0) && (l0 % 2 == 0) &&
+                 reinterpret_cast<uintptr_t>(y) % (2 * sizeof(T)) == 0;
+  }
   // zero-weight taps must not see the data (0 * NaN) -- only where NaNs survive the latitude pass
   const bool padded = !SKIPNA && !ring.zero_fill && ccnt >= 0 && ccnt < 5;
   const bool zero_fill = !SKIPNA && ring.zero_fill;
-  const bool writer = lane < nl;
-  T* const ylane = y + l0 + lane;
+  const bool writer = M == 2 ? (lane >= 1 && 2 * (lane - 1) < nl) : lane < nl;
+  T* const ylane = y + l0 + (M == 2 ? 2 * (lane - 1) : lane);
 
   const uint32_t wrec0 = smem_u32(s_wrec);
   const uint32_t row_stride = static_cast<uint32_t>(L.row_stride), slots = static_cast<uint32_t>(ring_slots);
@@ -751,6 +800,51 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
       __syncwarp();
       if (lane == 0) st_relaxed_smem(flags0 + 4u * (1 + warp), gbase + (static_cast<uint32_t>(rec.x) >> 16));
 
+      if constexpr (M == 2) {
+        // halos: the previous lane's last column, the next lane's first one
+        const T t_lo = swz ? t[2] : t[0], t_hi = swz ? t[1] : t[3];
+        const T tl = __shfl_up_sync(0xffffffffu, t_hi, 1), tr = __shfl_down_sync(0xffffffffu, t_lo, 1);
+        T vl = T(0), vr = T(0);
+        if constexpr (SKIPNA) {
+          const T v_lo = swz ? v[2] : v[0], v_hi = swz ? v[1] : v[3];
+          vl = __shfl_up_sync(0xffffffffu, v_hi, 1);
+          vr = __shfl_down_sync(0xffffffffu, v_lo, 1);
+        }
+        if (writer) {
+          T out[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            out[j] = nan;
+            if (rec.y >= 0 && have2[j]) {
+              T so = tw2[j][0] * tl;
+              so = fma(tw2[j][1], t[0], so);
+              so = fma(tw2[j][2], t[1], so);
+              so = fma(tw2[j][3], t[2], so);
+              so = fma(tw2[j][4], t[3], so);
+              so = fma(tw2[j][5], tr, so);
+              if constexpr (SKIPNA) {
+                T sv = tw2[j][0] * vl;
+                sv = fma(tw2[j][1], v[0], sv);
+                sv = fma(tw2[j][2], v[1], sv);
+                sv = fma(tw2[j][3], v[2], sv);
+                sv = fma(tw2[j][4], v[3], sv);
+                sv = fma(tw2[j][5], vr, sv);
+                out[j] = (sv >= thr) ? normalise_div(so, sv) : nan;
+              } else {
+                out[j] = so;
+              }
+            }
+          }
+          const bool both = 2 * (lane - 1) + 1 < nl;
+          if (both && pair_store) {
+            st_stream2(yrow, out[0], out[1]);
+          } else {
+            st_stream(yrow, out[0]);
+            if (both) st_stream(yrow + 1, out[1]);
+          }
+        }
+        continue;
+      }
       // the 5th tap is the first column of the next lane's group
       const T t_first = swz ? t[2] : t[0];
       const T tn = __shfl_down_sync(0xffffffffu, t_first, 1);

@@ -352,17 +352,18 @@ class BandOp:
         cols = self.cols_band if self.cols_band is not None else tables.identity_band(n_cols)
         return rows, cols
 
-    def _ring(self, batch: int, n_rows: int, n_cols: int, dtype: torch.dtype):
-        """Row-ring schedule sized so that (slabs x runs) fills the SMs about twice over."""
+    def _ring(self, batch: int, n_rows: int, n_cols: int, dtype: torch.dtype, pairs: bool = True):
+        """Row-ring schedule sized so that (slabs x runs) fills the SMs about twice over.  ``pairs``: allow the
+        two-targets-per-lane layout of the register-resident kernel (conservative NaN modes only)."""
         if not self.use_ring:
             return None
         rows, cols = self._host_bands(n_rows, n_cols)
         sms = max(sm_count(), 1)
         n_runs = int(min(rows.n_out, max(1, -(-2 * sms // max(batch, 1)))))
         vec = 2 if dtype == torch.float64 else 4
-        key = (n_runs, n_rows, n_cols, vec, self.use_lanes)
+        key = (n_runs, n_rows, n_cols, vec, self.use_lanes, pairs)
         if key not in self._rings:
-            host = tables.row_ring_schedule(rows, n_runs, cols, vec)
+            host = tables.row_ring_schedule(rows, n_runs, cols, vec, allow_pairs=pairs and self.use_lanes)
             if host is not None and not self.use_lanes:
                 host.lane_cols = 0
             self._rings[key] = None if host is None else DeviceRing(host, rows, dtype, self.device)
@@ -408,7 +409,7 @@ class BandOp:
             fn = lib.rg_row_nanmean_f64 if dtype == torch.float64 else lib.rg_row_nanmean_f32
             check(fn(x3.data_ptr(), pole.data_ptr(), B, H, W, x3.stride(0), x3.stride(1),
                      int(self.pole_src[0]), int(self.pole_src[1]), stream), "rg_row_nanmean")
-        ring = self._ring(B, H, W, dtype)
+        ring = self._ring(B, H, W, dtype, pairs=nan_mode != NAN_PROPAGATE)
         xbs = x3.stride(0) if B > 1 else H * x3.stride(1)
         pole_ptr = None if pole is None else pole.data_ptr()
         ring_ref = None if ring is None else ring.ref

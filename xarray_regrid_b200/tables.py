@@ -521,7 +521,8 @@ def column_panels(cols: Band, vec: int, warps: int = 6, table_bytes: int = 0, mi
     return cands[0][4]
 
 
-def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: int = 2) -> RowRing | None:
+def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: int = 2,
+                      allow_pairs: bool = True) -> RowRing | None:
     """Schedule for streaming the source rows of ``rows`` through a shared-memory ring.
 
     Outputs are visited in order and split into ``n_runs`` contiguous runs.  Inside a run a
@@ -609,7 +610,15 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
                     ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = l0, c0, nc, n_warps
                     ring.lane_cols = lane_owned_columns(cols, l0, n_warps)
                     ring.single_panel(cols.n_src)
-        if too_wide or (not ring.lane_cols and (ring.n_warps < 8 or rows.k_max <= 4)):
+        pairs = lane_pairs_layout(cols) if (allow_pairs and not ring.lane_cols and rows.k_max <= 5) else None
+        if pairs is not None:
+            # coarsening by two: the register-resident kernel with two targets per lane (conservative modes only:
+            # its zero-weight taps would let a NaN through in the NaN-propagating interpolation mode)
+            ring.strip_l0, ring.strip_c0, ring.n_warps = pairs
+            ring.strip_nc = np.full(ring.strip_c0.size, 4 * 32, np.int32)
+            ring.single_panel(cols.n_src)
+            ring.lane_cols = 2
+        elif too_wide or (not ring.lane_cols and (ring.n_warps < 8 or rows.k_max <= 4)):
             # more than 12 x 32 target columns (a warp would own several strips and reload its column taps for
             # every target row), few short strips (one CTA per SM leaves it idle), or few row taps (coarsening
             # ratios of 2 - 2.5: two new source rows per target row leave no time for one CTA's per-row dependency
@@ -650,6 +659,49 @@ def lane_owned_columns(cols: Band, strip_l0: np.ndarray, n_warps: int, step: int
         if ((first[a + 1:b] - first[a:b - 1] - step) % n_src).any():
             return 0
     return step
+
+
+def lane_pairs_layout(cols: Band, max_warps: int = 12, pairs_per_warp: int = 30):
+    """Strip layout of the register-resident kernel's TWO-TARGETS-PER-LANE variant (``lane_cols == 2``), or None.
+
+    Coarsening by two: every target covered with 1..3 contiguous taps (modulo n_src) and consecutive targets
+    exactly two source columns apart.  A lane then owns a block of 4 source columns and produces the PAIR of
+    targets whose taps lie in the block and its two neighbouring columns (left halo from the previous lane, right
+    halo from the next one).  Returns ``(strip_l0, strip_c0, n_warps)``: ``strip_c0[s]`` is the first own column
+    (even) of the first pair of strip ``s``; a strip holds at most ``pairs_per_warp`` pairs (lane 0 and the lane
+    after the last pair only produce the halos)."""
+    n_src, n_out = cols.n_src, cols.n_out
+    if n_out < 2 or n_src % 2 or cols.k_max > 3:
+        return None
+    if not (cols.cover > 0).all() or (cols.cnt < 1).any() or (cols.cnt > 3).any():
+        return None
+    first = cols.idx[0].astype(np.int64)
+    for i in range(1, cols.k_max):
+        live = cols.cnt > i
+        if ((cols.idx[i].astype(np.int64) - first - i) % n_src)[live].any():
+            return None
+    # unwrapped first taps (forward steps of a few columns, the date line crossed at most once)
+    step = (first[1:] - first[:-1]) % n_src
+    if (step > 4).any():
+        return None
+    first_u = first[0] + np.concatenate([[0], np.cumsum(step)])
+    if first_u[-1] + int(cols.cnt[-1]) - first_u[0] > n_src + 2:
+        return None
+    # every tap of pair p must lie in [c00 + 4p - 1, c00 + 4p + 4] for one even c00
+    rel = first_u - 4 * (np.arange(n_out) // 2)
+    lo, hi = int(rel.min()), int((rel + cols.cnt - 1).max())
+    c00 = hi - 4 + ((hi - 4) % 2)
+    if c00 > lo + 1:
+        return None
+    n_pairs = -(-n_out // 2)
+    n_warps = -(-n_pairs // pairs_per_warp)
+    if n_warps > max_warps:
+        return None
+    per = -(-n_pairs // n_warps)
+    p0 = np.append(np.arange(0, n_pairs, per), n_pairs)
+    strip_l0 = np.minimum(2 * p0, n_out).astype(np.int32)
+    strip_c0 = ((c00 + 4 * p0[:-1]) % n_src).astype(np.int32)
+    return strip_l0, strip_c0, int(p0.size - 1)
 
 
 def band_window_rows(band: "Band", cap: int = 16, max_rows: int = 32, step: int = 4) -> int:
