@@ -38,8 +38,9 @@ extern "C" {
 #define RG_ERR_UNSUPPORTED (-4)
 #define RG_ERR_ALIGN (-5)
 
-#define RG_ABI_VERSION 3 /* 3: rg_pipeline_*, rg_host_copy, pole source rows in rg_row_nanmean_* / rg_conservative_host_*,
-                            rg_conservative_*(skipna = 0) counts NaN as 0 like the reference's fillna(0) */
+#define RG_ABI_VERSION 4 /* 3: rg_pipeline_*, rg_host_copy, pole source rows in rg_row_nanmean_* / rg_conservative_host_*,
+                            rg_conservative_*(skipna = 0) counts NaN as 0 like the reference's fillna(0)
+                            4: rg_row_ring_t block layout (lane_cols == 2: strip_b0, block_l0, halo_l, halo_r) */
 
 /* ABI version of the loaded library (== RG_ABI_VERSION of the header it was built from). */
 int rg_abi_version(void);
@@ -146,7 +147,15 @@ typedef struct rg_row_ring {
   int32_t lane_cols; /* 4: every target column takes taps idx0 .. idx0 + cnt - 1 (cnt <= 5, mod n_src), idx0 is
                         even and grows by exactly 4 from one target to the next inside a strip, every strip has
                         <= 31 targets, all covered, and n_strips <= n_warps: the kernel then keeps both
-                        contractions in registers (one lane per target column).  0: no such structure. */
+                        contractions in registers (one lane per target column).
+                        2: block layout (coarsening by 2 - 3, rg_conservative_* only): a lane owns the 4 source
+                        columns strip_c0[s] + 4 j .. + 3 (strip_c0 ABSOLUTE and even; a multiple of 4 for fp32
+                        when n_panels > 1) of block strip_b0[s] + j and produces the targets block_l0[b] ..
+                        block_l0[b + 1] - 1 (at most two) whose contiguous taps all lie within halo_l columns
+                        before / halo_r columns after the block; <= 30 blocks per strip, all targets covered.
+                        Panels: panel_c0[p] = first own column of the panel - 4, panel_nc[p] = 4 * (blocks + 2),
+                        or one panel {0, n_src}; strips per panel <= n_warps <= 12.
+                        0: no such structure. */
   const int32_t* panel_strip0; /* device, [n_panels + 1] */
   const int32_t* panel_c0;     /* device, [n_panels]     */
   const int32_t* panel_nc;     /* device, [n_panels]     */
@@ -154,6 +163,10 @@ typedef struct rg_row_ring {
   int32_t panel_cols_max;      /* max over p of panel_nc[p] */
   int32_t strip_targets_max;   /* max over s of strip_l0[s+1] - strip_l0[s]: <= 32, or <= 64 in panel layouts
                                   of 6 consumer warps (the kernel then walks a strip's targets in two passes) */
+  const int32_t* strip_b0;     /* device, [n_strips + 1] or NULL: first block of every strip (lane_cols == 2) */
+  const int32_t* block_l0;     /* device, [n_blocks + 1] or NULL: first target of every block (lane_cols == 2) */
+  int32_t halo_l;              /* 1..2 (lane_cols == 2) */
+  int32_t halo_r;              /* 1..2 (lane_cols == 2) */
 } rg_row_ring_t;
 
 /*

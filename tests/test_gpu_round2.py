@@ -314,8 +314,13 @@ PANEL_CASES = {
 
 PANEL_CASES["ratio2_odd_targets_regional"] = (np.arange(-30.0, 30.1, 0.5), np.arange(10.0, 130.0, 0.5),
                                               np.arange(-30.0, 30.1, 1.0), np.arange(10.0, 128.5, 1.0))  # 240 -> 119
-PAIR_CASES = {"ratio2_centred", "ratio2_edge_aligned_poles", "ratio2_wide_two_panels", "ragged_last_panel",
-              "descending_lat_shifted_lon", "ratio2_odd_targets_regional"}  # coarsening by exactly two
+_LON01 = np.round(np.arange(0, 359.95, 0.1), 10)
+PANEL_CASES["ratio2p5_five_block_panels"] = (np.round(np.arange(-6.0, 6.05, 0.1), 10), _LON01,   # W = 3600
+                                             np.arange(-6.0, 6.1, 0.25), np.arange(0.0, 360.0, 0.25))
+PANEL_CASES["ratio3"] = (np.arange(-60.0, 60.1, 0.5), np.arange(0.0, 360.0, 0.5),
+                         np.arange(-60.0, 60.1, 1.5), np.arange(0.0, 360.0, 1.5))
+PANEL_CASES["ratio2p5_offset_regional"] = (np.arange(-30.0, 30.1, 1.0), np.arange(-20.0, 100.0, 1.0),
+                                           np.arange(-28.0, 28.1, 2.5), np.arange(-15.0, 95.0, 2.5))
 
 
 @pytest.mark.parametrize("case", sorted(PANEL_CASES))
@@ -324,12 +329,11 @@ PAIR_CASES = {"ratio2_centred", "ratio2_edge_aligned_poles", "ratio2_wide_two_pa
 def test_panel_layouts_match_oracle_and_generic_kernel(engine, case, dtype, layout):
     """Coarsening ratios of 2 - 2.5.  ``panels``: the two-phase ring kernel in its column-panel layout (several
     CTAs per SM, strips of up to 64 targets, panels that wrap the date line, panels with fewer strips than
-    consumer warps, synthetic pole rows with weight).  ``default``: ratio 2 runs the register-resident kernel with
-    two targets per lane (halo lanes at both ends of a warp, odd target counts, regional axes, the date line inside
-    a warp).  Every NaN mode against the oracle and against the generic kernel."""
+    consumer warps, synthetic pole rows with weight).  ``default``: ratios 2 - 3 run the register-resident kernel in
+    its block layout (a lane owns 4 source columns and up to two targets; halo lanes at both ends of a warp, one- and
+    two-column halos, odd target counts, regional axes, the date line inside a warp, column panels of blocks for
+    W = 3600).  Every NaN mode against the oracle and against the generic kernel."""
     lat, lon, tlat, tlon = PANEL_CASES[case]
-    if layout == "default" and case not in PAIR_CASES:
-        pytest.skip("the default layout of this case is the panel one")
     rng = np.random.default_rng(77)
     x = (0.5 + rng.random((5, lat.size, lon.size))).astype(dtype)
     x[rng.random(x.shape) < 0.06] = np.nan
@@ -344,8 +348,11 @@ def test_panel_layouts_match_oracle_and_generic_kernel(engine, case, dtype, layo
     ring = plan._ring(5, lat.size, lon.size, xt.dtype)
     assert ring is not None
     if layout == "default":
-        assert ring.host.lane_cols == 2 and ring.host.n_warps <= 12, "two targets per lane expected"
-        assert int(np.diff(ring.host.strip_l0).max()) <= 60
+        assert ring.host.lane_cols == 2 and ring.host.n_warps <= 12, "block layout expected"
+        assert int(np.diff(ring.host.strip_l0).max()) <= 60 and int(np.diff(ring.host.strip_b0).max()) <= 30
+        assert (ring.host.n_panels > 1) == (case == "ratio2p5_five_block_panels")
+        if case.startswith("ratio2p5") or case == "ratio3":
+            assert max(ring.host.halo_l, ring.host.halo_r) == 2 and np.diff(ring.host.block_l0).min() < 2
         # the interpolation (NaN-propagating) mode never takes that layout
         assert plan._ring(5, lat.size, lon.size, xt.dtype, pairs=False).host.lane_cols == 0
     else:

@@ -262,27 +262,47 @@ def test_lane_owned_columns_eligibility():
         assert all(b - a <= 31 for a, b in zip(ring.strip_l0[:-1], ring.strip_l0[1:]))
         first = cols.idx[0].astype(np.int64)
         assert (first % 2 == 0).all() and ((np.diff(first) - 4) % cols.n_src == 0).all()
-    # 2:1 coarsening takes the two-targets-per-lane layout: <= 30 pairs per warp, own blocks start on even columns,
-    # every tap of pair p inside [c0 + 4p - 1, c0 + 4p + 4]
-    for lon_t in (np.arange(0, 360, 2.0), np.arange(0.5, 360, 2.0), np.arange(0, 357, 2.0)):
-        ring, cols = ring_for(lat1, lon1, np.arange(-90, 91, 2.0), lon_t)
-        assert ring.lane_cols == 2 and ring.n_strips == ring.n_warps <= 12 and ring.n_panels == 1
-        assert (ring.strip_c0 % 2 == 0).all() and (np.diff(ring.strip_l0) <= 60).all()
-        assert ring.strip_l0[0] == 0 and ring.strip_l0[-1] == cols.n_out
-        for s in range(ring.n_strips):
-            for l in range(ring.strip_l0[s], ring.strip_l0[s + 1]):
-                c0 = ring.strip_c0[s] + 4 * ((l - ring.strip_l0[s]) // 2)
-                q = (cols.idx[: cols.cnt[l], l].astype(np.int64) - (c0 - 1)) % cols.n_src
-                assert (q < 6).all(), (s, l, q)
-        # ... but not for the NaN-propagating interpolation mode
-        rows = tables.conservative_band(engine._axis(engine.AxisSpec(lat1, np.arange(-90, 91, 2.0), "lat"), True),
-                                        np.arange(-90, 91, 2.0), spherical=True)
-        assert tables.row_ring_schedule(rows, 4, cols, 2, allow_pairs=False).lane_cols == 0
+    # coarsening by 2 - 3 takes the block layout: a lane owns 4 source columns and <= 2 consecutive targets whose
+    # taps all lie within halo_l / halo_r <= 2 columns of the block; <= 30 blocks per warp; panels of blocks for
+    # rows wider than 12 warps
+    lat01, lon01 = np.round(np.arange(-9, 9.05, 0.1), 10), np.round(np.arange(0, 359.95, 0.1), 10)
+    block_cases = [(lat1, lon1, np.arange(-90, 91, 2.0), t) for t in
+                   (np.arange(0, 360, 2.0), np.arange(0.5, 360, 2.0), np.arange(0, 357, 2.0), np.arange(0, 360, 2.5),
+                    np.arange(0, 360, 3.0), np.arange(7.0, 300, 2.5))]
+    block_cases.append((lat01, lon01, np.arange(-9, 9.1, 0.25), np.arange(0, 360, 0.25)))
+    for vec in (2, 4):
+        for la, lo, tla, tlo in block_cases:
+            ring, cols = ring_for(la, lo, tla, tlo, vec)
+            W = cols.n_src
+            assert ring.lane_cols == 2 and ring.n_warps <= 12
+            assert 1 <= ring.halo_l <= 2 and 1 <= ring.halo_r <= 2
+            assert (ring.strip_c0 % (4 if vec == 4 and ring.n_panels > 1 else 2) == 0).all()
+            assert (np.diff(ring.strip_l0) <= 60).all() and (np.diff(ring.strip_b0) <= 30).all()
+            assert ring.strip_l0[0] == 0 and ring.strip_l0[-1] == cols.n_out == ring.block_l0[-1]
+            assert (np.diff(ring.block_l0) >= 0).all() and (np.diff(ring.block_l0) <= 2).all()
+            assert (np.diff(ring.panel_strip0) <= ring.n_warps).all() and ring.panel_strip0[-1] == ring.n_strips
+            assert (ring.n_panels > 1) == (W == 3600)
+            for p in range(ring.n_panels):
+                for s in range(ring.panel_strip0[p], ring.panel_strip0[p + 1]):
+                    for j in range(ring.strip_b0[s + 1] - ring.strip_b0[s]):
+                        c0 = int(ring.strip_c0[s]) + 4 * j
+                        if ring.n_panels > 1:  # the block and both halo blocks lie inside the panel's ring row
+                            rel = (c0 - int(ring.panel_c0[p])) % W
+                            assert rel >= 4 and rel + 8 <= ring.panel_nc[p] and ring.panel_nc[p] % 4 == 0
+                        b = ring.strip_b0[s] + j
+                        for l in range(ring.block_l0[b], ring.block_l0[b + 1]):
+                            q = (cols.idx[: cols.cnt[l], l].astype(np.int64) - (c0 - ring.halo_l)) % W
+                            assert (q < 4 + ring.halo_l + ring.halo_r).all(), (s, l, q)
+            # ... but never for the NaN-propagating interpolation mode
+            rows = tables.conservative_band(engine._axis(engine.AxisSpec(la, tla, "lat"), True), tla, spherical=True)
+            assert tables.row_ring_schedule(rows, 4, cols, vec, allow_pairs=False).lane_cols == 0
     # a regional target with uncovered edge cells and a non-integer ratio do not qualify for either
     ring, _ = ring_for(lat025[200:400], lon025[100:700], lat1[40:110], lon1[20:180])
     assert ring is None or ring.lane_cols == 0
     ring, _ = ring_for(lat025, lon025, np.arange(-90, 90.1, 0.7), np.arange(0, 360, 0.7))
-    assert ring is None or ring.lane_cols == 0
+    assert ring.lane_cols == 2  # (ratio 2.8: blocks)
+    ring, _ = ring_for(lat025, lon025, np.arange(-90, 90.1, 0.4), np.arange(0, 360, 0.4))
+    assert ring is None or ring.lane_cols == 0  # ratio 1.6: more than two targets per block of 4 columns
 
 
 def test_band_window_rows_is_exact():

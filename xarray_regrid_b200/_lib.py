@@ -12,7 +12,7 @@ from pathlib import Path
 _CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = _CSRC / "libregrid_b200.so"
 
-RG_ABI_VERSION = 3
+RG_ABI_VERSION = 4
 
 
 class RegridB200Error(RuntimeError):
@@ -58,6 +58,10 @@ class rg_row_ring_t(C.Structure):  # noqa: N801 - mirrors the C name
         ("n_panels", C.c_int32),
         ("panel_cols_max", C.c_int32),
         ("strip_targets_max", C.c_int32),
+        ("strip_b0", C.c_void_p),
+        ("block_l0", C.c_void_p),
+        ("halo_l", C.c_int32),
+        ("halo_r", C.c_int32),
     ]
 
 

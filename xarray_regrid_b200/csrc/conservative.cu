@@ -233,11 +233,16 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
 
   // ---- fast path: TMA row-ring kernels (need 16-byte aligned rows, <= 8 taps per
   //      axis, a ring that fits shared memory)
-  // lane_cols == 2: the register-resident kernel with two targets per lane (<= 30 pairs per warp, conservative
-  // NaN modes only).  That strip layout has no two-phase form: anything else goes to the generic kernel.
-  const bool lanes2 = ring_c && ring_c->lane_cols == 2 && cols.k_max <= 3 && rows.k_max <= 5 &&
-                      (skipna || zero_fill) && ring_c->strip_targets_max <= 60 && ring_c->n_panels == 1 &&
-                      ring_c->n_strips <= ring_c->n_warps && ring_c->n_warps + 2 <= 14 && W % 2 == 0;
+  // lane_cols == 2: the register-resident kernel in its block layout (up to two targets per lane, <= 30 blocks
+  // per warp, conservative NaN modes only).  That layout has no two-phase form: anything else goes to the generic
+  // kernel.
+  const bool lanes2 = ring_c && ring_c->lane_cols == 2 && cols.k_max <= 6 && rows.k_max <= 5 &&
+                      (skipna || zero_fill) && ring_c->strip_targets_max <= 60 && ring_c->strip_b0 &&
+                      ring_c->block_l0 && ring_c->halo_l >= 1 && ring_c->halo_l <= 2 && ring_c->halo_r >= 1 &&
+                      ring_c->halo_r <= 2 && ring_c->n_panels >= 1 && ring_c->panel_strip0 && ring_c->panel_c0 &&
+                      ring_c->panel_nc && ring_c->n_warps + 2 <= 14 && W % 2 == 0 &&
+                      ring_c->panel_cols_max <= W && (ring_c->panel_cols_max * sizeof(T)) % 16 == 0 &&
+                      (ring_c->n_panels == 1 || W % 4 == 0);
   if (ring_c && ring_c->lane_cols == 2 && !lanes2) ring_c = nullptr;
   if (ring_c && aligned && (static_cast<size_t>(W) * sizeof(T)) % 16 == 0 &&
       (!pole || reinterpret_cast<uintptr_t>(pole) % 16 == 0) &&
@@ -255,17 +260,19 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     const int wp = have_panels ? ring_c->panel_cols_max : W;  // columns of a ring row
     // lane-owned columns variant (4 source columns + 1 per target, see conservative_ring.cuh): no strip buffers
     // (the staged per-row record packs need / release into 16 bits each)
-    const bool lanes = ((ring_c->lane_cols == 4 && cols.k_max <= 5) || lanes2) && ring_c->n_strips <= ring_c->n_warps &&
-                       ring_c->n_warps + 2 <= 14 && W % 2 == 0 && ring_c->n_sched < 65536 && n_panels == 1 && wp == W;
+    const bool lanes = lanes2 || (ring_c->lane_cols == 4 && cols.k_max <= 5 && ring_c->n_strips <= ring_c->n_warps &&
+                                  ring_c->n_warps + 2 <= 14 && W % 2 == 0 && n_panels == 1 && wp == W);
     // panel layouts of the two-phase kernel: 6 consumer warps, several CTAs per SM
     const bool panel_cta = !lanes && have_panels && ring_c->n_warps <= 6 && kw >= 3;
     const bool panel_tg2 = panel_cta && ring_c->strip_targets_max > 32;
-    // (register-resident kernel: 14 warps of fp64 fill an SM's registers; rows of <= 6 consumer warps leave room
-    // for a second -- fp32: third -- CTA)
-    const int min_ctas = lanes ? ((sizeof(T) == 4 ? 2 : 1) + (ring_c->n_warps <= 6 ? 1 : 0))
+    // (register-resident kernel: 14 warps of fp64 fill an SM's registers; rows of fewer consumer warps leave
+    // room for more CTAs: <= 120 (fp64) / 72 (fp32) registers per thread, see -Xptxas -v)
+    const int lane_threads = (ring_c->n_warps + 2) * 32;
+    const int lane_ctas = 65536 / (lane_threads * (sizeof(T) == 8 ? 120 : 72));
+    const int min_ctas = lanes ? (lane_ctas > 4 ? 4 : lane_ctas < 1 ? 1 : lane_ctas)
                          : panel_cta ? ((rows.k_max <= 4 && !(panel_tg2 && kw >= 5)) ? 3 : 2) : 1;
     const RingLayout probe =
-        lanes ? ring_layout<T>(W, 31, false, 0, 0, 0)
+        lanes ? ring_layout<T>(wp, 31, false, 0, 0, 0)
               : ring_layout<T>(wp, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, 0);
     // all variants stage the per-row records and weights (16 + 8 * sizeof(T) bytes per target row) and the row
     // load order (4 bytes per scheduled row) in shared memory
@@ -292,7 +299,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     }
     if (slots >= ring_c->max_live + 1 && slots >= 2) {
       const RingLayout L =
-          lanes ? ring_layout<T>(W, 31, false, 0, 0, slots)
+          lanes ? ring_layout<T>(wp, 31, false, 0, 0, slots)
                 : ring_layout<T>(wp, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, slots);
       RingDev ring{ring_c->sched_row,
                    reinterpret_cast<const int4*>(ring_c->krec),
@@ -317,7 +324,11 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
                    ring_c->panel_c0,
                    ring_c->panel_nc,
                    n_panels,
-                   wp};
+                   wp,
+                   ring_c->strip_b0,
+                   ring_c->block_l0,
+                   ring_c->halo_l,
+                   ring_c->halo_r};
       if (!have_panels) return RG_ERR_NULL;  // (the host layer always provides the panel tables)
       using RingKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev,
                                   T, int, int);
@@ -353,12 +364,18 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       long long grid = static_cast<long long>(dev.sm_count) * ctas;
       if (grid > tasks) grid = tasks;
       if (lanes) {
-        auto lk = lanes2 ? (skipna ? conservative_lanes_kernel<T, true, 14, 5, 2> : conservative_lanes_kernel<T, false, 14, 5, 2>)
+        const bool halo2 = lanes2 && (ring_c->halo_l > 1 || ring_c->halo_r > 1);
+        auto lk = halo2 ? (skipna ? conservative_lanes_kernel<T, true, 14, 5, 3> : conservative_lanes_kernel<T, false, 14, 5, 3>)
+                  : lanes2 ? (skipna ? conservative_lanes_kernel<T, true, 14, 5, 2> : conservative_lanes_kernel<T, false, 14, 5, 2>)
                   : rows.k_max <= 5
                       ? (skipna ? conservative_lanes_kernel<T, true, 14, 5> : conservative_lanes_kernel<T, false, 14, 5>)
                       : (skipna ? conservative_lanes_kernel<T, true, 14, 8> : conservative_lanes_kernel<T, false, 14, 8>);
         const size_t smem_l = L.total + row_tables;
         RG_CUDA(cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_l)));
+        if (lanes2 && n_panels > 1) {  // a CTA stays on one panel: task % n_panels must not depend on the iteration
+          if (grid < n_panels) return RG_ERR_UNSUPPORTED;  // (tasks >= n_panels always)
+          grid -= grid % n_panels;
+        }
         lk<<<static_cast<unsigned>(grid), warps * 32, smem_l, stream>>>(x, y, batch, xbs, xrs, ybs, cols, ring, thr,
                                                                        slots, rows.n_out);
         return static_cast<int>(cudaGetLastError());

@@ -42,6 +42,10 @@ struct RingDev {
   const int32_t* __restrict__ panel_c0;
   const int32_t* __restrict__ panel_nc;
   int n_panels, panel_cols_max;
+  // block layout of the register-resident kernel (lane_cols == 2)
+  const int32_t* __restrict__ strip_b0;
+  const int32_t* __restrict__ block_l0;
+  int halo_l, halo_r;
 };
 
 constexpr int kRingMaxSlots = 32;  // ring depth cap (a tap reaches at most 15 rows back: 4-bit tap_back)
@@ -634,10 +638,13 @@ __device__ __forceinline__ void lane_phase1_dispatch(int cnt, uint32_t baseA, ui
 }
 
 //
-// M = 2 (rg_row_ring_t.lane_cols == 2, coarsening by two, conservative NaN modes only): a lane still owns 4
-// source columns but produces the PAIR of targets whose (<= 3 contiguous) taps lie in its block and the two
-// columns next to it: the left one comes from the previous lane, the right one from the next.  Lane 0 of a warp
-// and the lane after its last pair only produce those halos; strip_c0[warp] = first own column of the first pair.
+// M = 2 (rg_row_ring_t.lane_cols == 2, coarsening by 2 - 3, conservative NaN modes only): a lane still owns a
+// block of 4 source columns but produces the (at most two) targets the host assigned to its block; their taps lie
+// in the block or within halo_l / halo_r <= 2 columns of it, and those come from the previous / next lane with
+// shuffles.  Lane 0 of a warp and the lane after its last block only produce halos.  A row wider than 12 warps
+// of 30 blocks is cut into column panels (ring rows = the panel's blocks + one halo block either side); the
+// launcher makes the grid a multiple of the panel count, so a CTA stays on ONE panel and the lanes' column
+// offsets and weights are kernel-lifetime constants.  M = 3: the same with two halo columns either side (M = 2: one).
 template <typename T, bool SKIPNA, int MAXWARPS, int RMAX, int M = 1>
 __global__ void __launch_bounds__(MAXWARPS * 32, sizeof(T) == 4 ? 2 : 1)
 conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
@@ -646,7 +653,7 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   extern __shared__ __align__(128) unsigned char smem[];
   const int W = cols.n_src, Wo = cols.n_out;
   const int n_warps = ring.n_warps;  // consumer warps; then one producer warp and one sync warp
-  const RingLayout L = ring_layout<T>(W, 31, false, 0, 0, ring_slots);  // no strip buffers
+  const RingLayout L = ring_layout<T>(ring.panel_cols_max, 31, false, 0, 0, ring_slots);  // no strip buffers
   unsigned long long* s_full = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
   uint32_t* s_flags = reinterpret_cast<uint32_t*>(smem + L.off_flags);
   // per target row tables, staged once: 16-byte record + 8 tap weights (host contract: they fit)
@@ -666,7 +673,7 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
   __syncthreads();
 
-  const long long tasks = batch * ring.n_runs;
+  const long long tasks = batch * ring.n_runs * ring.n_panels;  // (M = 1: one panel)
   const uint32_t row_bytes = static_cast<uint32_t>(W) * sizeof(T);
   const uint32_t full0 = smem_u32(s_full), flags0 = smem_u32(s_flags), ring0 = smem_u32(smem);
 
@@ -683,24 +690,36 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
 
   // ================================================================ consumer warps (strip = warp)
   const T nan = quiet_nan<T>();
-  const bool has_strip = warp < ring.n_strips;  // host contract: n_strips <= n_warps
-  const int l0 = has_strip ? ring.strip_l0[warp] : 0;
-  const int nl = has_strip ? ring.strip_l0[warp + 1] - l0 : 0;  // host contract: <= 31
+  // M = 2: gridDim.x is a multiple of n_panels, so task % n_panels is the same for every task of this CTA
+  const int panel = M >= 2 ? static_cast<int>(blockIdx.x % static_cast<unsigned>(ring.n_panels)) : 0;
+  const int strip = (M >= 2 ? ring.panel_strip0[panel] : 0) + warp;
+  // host contract: strips of a panel <= n_warps
+  const bool has_strip = M >= 2 ? strip < ring.panel_strip0[panel + 1] : warp < ring.n_strips;
+  const int l0 = has_strip ? ring.strip_l0[strip] : 0;
+  const int nl = has_strip ? ring.strip_l0[strip + 1] - l0 : 0;  // host contract: <= 31 (M = 2: <= 60)
   const int m = lane < nl ? lane : (nl > 0 ? nl - 1 : 0);
   const int l = l0 + m;
   // first source column of this lane's group of 4 (the halo lane continues one group further)
   int cfirst = (has_strip && nl > 0) ? cols.idx[l] + 4 * ((lane < nl ? lane : nl) - m) : 0;
-  const int n_pairs = (nl + 1) >> 1;  // M = 2: host contract <= 30
-  if constexpr (M == 2) {
-    const int blk = (lane <= n_pairs ? lane : n_pairs + 1) - 1;  // -1: left halo block, n_pairs: right halo block
-    cfirst = has_strip ? ring.strip_c0[warp] + 4 * blk : 0;
-    cfirst = ((cfirst % W) + W) % W;
+  int b0 = 0, nb = 0, cabs = 0;  // M = 2: first block / blocks of the strip (<= 30), this lane's first own column
+  bool wrap_cols = true;
+  if constexpr (M >= 2) {
+    b0 = has_strip ? ring.strip_b0[strip] : 0;
+    nb = has_strip ? ring.strip_b0[strip + 1] - b0 : 0;
+    const int blk = (lane <= nb ? lane : nb + 1) - 1;  // -1: left halo block, nb: right halo block
+    cabs = has_strip ? ring.strip_c0[strip] + 4 * blk : 0;
+    // column inside the ring row: rows hold the panel's columns [pc0, pc0 + pnc) (mod W)
+    const int pc0 = ring.panel_c0[panel];
+    wrap_cols = ring.panel_nc[panel] == W;  // a full-circle row: blocks may straddle its end
+    cfirst = has_strip ? (((cabs - pc0) % W) + W) % W : 0;
   }
   constexpr int SWZ = sizeof(T) == 8 ? 2 : 3;
   const int swz = (lane >> SWZ) & 1;
   int jA = cfirst + 2 * swz, jB = cfirst + 2 * (1 - swz);
-  jA %= W;
-  jB %= W;
+  if (wrap_cols) {
+    jA %= W;
+    jB %= W;
+  }
   const uint32_t baseA = ring0 + static_cast<uint32_t>(jA) * sizeof(T);
   const uint32_t baseB = ring0 + static_cast<uint32_t>(jB) * sizeof(T);
   // longitude taps of this lane's target: weights in register order {A.a, A.b, B.a, B.b, neighbour}
@@ -711,49 +730,56 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   const T twA0 = swz ? tw[2] : tw[0], twA1 = swz ? tw[3] : tw[1];
   const T twB0 = swz ? tw[0] : tw[2], twB1 = swz ? tw[1] : tw[3];
   const T tw4 = tw[4];
-  // M = 2: weights of the lane's two targets over {left halo, own 4 columns in register order, right halo}
-  T tw2[M == 2 ? 2 : 1][6];
+  // M = 2: weights of the lane's targets over the window {2 left halo columns, own 4 in register order, 2 right}
+  T tw2[M >= 2 ? 2 : 1][8];
   bool have2[2] = {false, false};
+  int ntg = 0, tgt0 = 0;
   bool pair_store = false;
-  if constexpr (M == 2) {
-    const int c_left = (cfirst + W - 1) % W;
+  if constexpr (M >= 2) {
+    if (has_strip && lane >= 1 && lane <= nb) {
+      tgt0 = ring.block_l0[b0 + lane - 1];
+      ntg = ring.block_l0[b0 + lane] - tgt0;  // host contract: 0..2
+    }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int lj = 2 * (lane - 1) + j;  // target inside the strip
-      const bool live = has_strip && lane >= 1 && lj < nl;
-      have2[j] = live && cols.cover[live ? l0 + lj : 0] != 0;
-      T nat[6];
+      const bool live = j < ntg;
+      const int lj = live ? tgt0 + j : 0;
+      have2[j] = live && cols.cover[lj] != 0;
+      T nat[8];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) nat[q] = T(0);
+      for (int q = 0; q < 8; ++q) nat[q] = T(0);
       if (have2[j]) {
-        const int cj = cols.cnt[l0 + lj];
+        const int cj = cols.cnt[lj];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 6; ++i) {
           if (i < cj && i < cols.k_max) {
-            const int q = (cols.idx[i * Wo + l0 + lj] - c_left + W) % W;
-            const T wv = cols.w[i * Wo + l0 + lj];
+            const int q = (((cols.idx[i * Wo + lj] - (cabs - 2)) % W) + W) % W;
+            const T wv = cols.w[i * Wo + lj];
 #pragma unroll
-            for (int qq = 0; qq < 6; ++qq)
+            for (int qq = 0; qq < 8; ++qq)
               if (qq == q) nat[qq] = wv;
           }
         }
       }
       tw2[j][0] = nat[0];
-      tw2[j][1] = swz ? nat[3] : nat[1];
+      tw2[j][1] = nat[1];
       tw2[j][2] = swz ? nat[4] : nat[2];
-      tw2[j][3] = swz ? nat[1] : nat[3];
+      tw2[j][3] = swz ? nat[5] : nat[3];
       tw2[j][4] = swz ? nat[2] : nat[4];
-      tw2[j][5] = nat[5];
+      tw2[j][5] = swz ? nat[3] : nat[5];
+      tw2[j][6] = nat[6];
+      tw2[j][7] = nat[7];
     }
-    // both targets of a pair in one 2-element store where every such address is aligned
-    pair_store = (Wo % 2 == 0) && (ybs % 2 == 0) && (l0 % 2 == 0) &&
+    // both targets of a lane in one 2-element store where that address is aligned
+    pair_store = ntg == 2 && (Wo % 2 == 0) && (ybs % 2 == 0) && (tgt0 % 2 == 0) &&
                  reinterpret_cast<uintptr_t>(y) % (2 * sizeof(T)) == 0;
   }
+  constexpr bool halo_l2 = M == 3, halo_r2 = M == 3;  // (compile time: a predicated fp64 FMA costs three instructions)
   // zero-weight taps must not see the data (0 * NaN) -- only where NaNs survive the latitude pass
   const bool padded = !SKIPNA && !ring.zero_fill && ccnt >= 0 && ccnt < 5;
   const bool zero_fill = !SKIPNA && ring.zero_fill;
-  const bool writer = M == 2 ? (lane >= 1 && 2 * (lane - 1) < nl) : lane < nl;
-  T* const ylane = y + l0 + (M == 2 ? 2 * (lane - 1) : lane);
+  const bool writer = M >= 2 ? ntg > 0 : lane < nl;
+  T* const ylane = y + (M >= 2 ? tgt0 : l0 + lane);
 
   const uint32_t wrec0 = smem_u32(s_wrec);
   const uint32_t row_stride = static_cast<uint32_t>(L.row_stride), slots = static_cast<uint32_t>(ring_slots);
@@ -774,8 +800,9 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   uint32_t rot = 0;    // gbase % ring_slots
 
   for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
-    const int run = static_cast<int>(task % ring.n_runs);
-    const long long b = task / ring.n_runs;
+    const long long unit = M >= 2 ? task / ring.n_panels : task;
+    const int run = static_cast<int>(unit % ring.n_runs);
+    const long long b = unit / ring.n_runs;
     const int k0 = ring.run_first[run], k1 = ring.run_first[run + 1];
     const uint32_t rot4 = rot * 0x01010101u;
     T* yrow = ylane + b * ybs + static_cast<long long>(k0) * Wo;
@@ -800,15 +827,19 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
       __syncwarp();
       if (lane == 0) st_relaxed_smem(flags0 + 4u * (1 + warp), gbase + (static_cast<uint32_t>(rec.x) >> 16));
 
-      if constexpr (M == 2) {
-        // halos: the previous lane's last column, the next lane's first one
-        const T t_lo = swz ? t[2] : t[0], t_hi = swz ? t[1] : t[3];
-        const T tl = __shfl_up_sync(0xffffffffu, t_hi, 1), tr = __shfl_down_sync(0xffffffffu, t_lo, 1);
-        T vl = T(0), vr = T(0);
+      if constexpr (M >= 2) {
+        // halos: the previous lane's last (two) columns, the next lane's first (two)
+        const T t_n0 = swz ? t[2] : t[0], t_n1 = swz ? t[3] : t[1], t_n2 = swz ? t[0] : t[2], t_n3 = swz ? t[1] : t[3];
+        const T tl1 = __shfl_up_sync(0xffffffffu, t_n3, 1), tr0 = __shfl_down_sync(0xffffffffu, t_n0, 1);
+        T tl0 = T(0), tr1 = T(0), vl0 = T(0), vl1 = T(0), vr0 = T(0), vr1 = T(0);
+        if constexpr (halo_l2) tl0 = __shfl_up_sync(0xffffffffu, t_n2, 1);
+        if constexpr (halo_r2) tr1 = __shfl_down_sync(0xffffffffu, t_n1, 1);
         if constexpr (SKIPNA) {
-          const T v_lo = swz ? v[2] : v[0], v_hi = swz ? v[1] : v[3];
-          vl = __shfl_up_sync(0xffffffffu, v_hi, 1);
-          vr = __shfl_down_sync(0xffffffffu, v_lo, 1);
+          const T v_n0 = swz ? v[2] : v[0], v_n1 = swz ? v[3] : v[1], v_n2 = swz ? v[0] : v[2], v_n3 = swz ? v[1] : v[3];
+          vl1 = __shfl_up_sync(0xffffffffu, v_n3, 1);
+          vr0 = __shfl_down_sync(0xffffffffu, v_n0, 1);
+          if constexpr (halo_l2) vl0 = __shfl_up_sync(0xffffffffu, v_n2, 1);
+          if constexpr (halo_r2) vr1 = __shfl_down_sync(0xffffffffu, v_n1, 1);
         }
         if (writer) {
           T out[2];
@@ -816,31 +847,34 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
           for (int j = 0; j < 2; ++j) {
             out[j] = nan;
             if (rec.y >= 0 && have2[j]) {
-              T so = tw2[j][0] * tl;
-              so = fma(tw2[j][1], t[0], so);
-              so = fma(tw2[j][2], t[1], so);
-              so = fma(tw2[j][3], t[2], so);
-              so = fma(tw2[j][4], t[3], so);
-              so = fma(tw2[j][5], tr, so);
+              T so = tw2[j][1] * tl1;
+              so = fma(tw2[j][2], t[0], so);
+              so = fma(tw2[j][3], t[1], so);
+              so = fma(tw2[j][4], t[2], so);
+              so = fma(tw2[j][5], t[3], so);
+              so = fma(tw2[j][6], tr0, so);
+              if constexpr (halo_l2) so = fma(tw2[j][0], tl0, so);
+              if constexpr (halo_r2) so = fma(tw2[j][7], tr1, so);
               if constexpr (SKIPNA) {
-                T sv = tw2[j][0] * vl;
-                sv = fma(tw2[j][1], v[0], sv);
-                sv = fma(tw2[j][2], v[1], sv);
-                sv = fma(tw2[j][3], v[2], sv);
-                sv = fma(tw2[j][4], v[3], sv);
-                sv = fma(tw2[j][5], vr, sv);
+                T sv = tw2[j][1] * vl1;
+                sv = fma(tw2[j][2], v[0], sv);
+                sv = fma(tw2[j][3], v[1], sv);
+                sv = fma(tw2[j][4], v[2], sv);
+                sv = fma(tw2[j][5], v[3], sv);
+                sv = fma(tw2[j][6], vr0, sv);
+                if constexpr (halo_l2) sv = fma(tw2[j][0], vl0, sv);
+                if constexpr (halo_r2) sv = fma(tw2[j][7], vr1, sv);
                 out[j] = (sv >= thr) ? normalise_div(so, sv) : nan;
               } else {
                 out[j] = so;
               }
             }
           }
-          const bool both = 2 * (lane - 1) + 1 < nl;
-          if (both && pair_store) {
+          if (pair_store) {
             st_stream2(yrow, out[0], out[1]);
           } else {
             st_stream(yrow, out[0]);
-            if (both) st_stream(yrow + 1, out[1]);
+            if (ntg == 2) st_stream(yrow + 1, out[1]);
           }
         }
         continue;

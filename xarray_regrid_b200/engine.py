@@ -80,6 +80,9 @@ class DeviceRing:
         self.run_first, self.run_sched = up(ring.run_first), up(ring.run_sched)
         self.strip_l0, self.strip_c0, self.strip_nc = up(ring.strip_l0), up(ring.strip_c0), up(ring.strip_nc)
         self.panel_strip0, self.panel_c0, self.panel_nc = up(ring.panel_strip0), up(ring.panel_c0), up(ring.panel_nc)
+        blocks = ring.block_l0 is not None
+        self.strip_b0 = up(ring.strip_b0) if blocks else None
+        self.block_l0 = up(ring.block_l0) if blocks else None
         self.c = rg_row_ring_t(
             self.sched_row.data_ptr(), self.krec.data_ptr(), self.wrec.data_ptr(),
             self.run_first.data_ptr(), self.run_sched.data_ptr(), self.strip_l0.data_ptr(),
@@ -88,6 +91,8 @@ class DeviceRing:
             ring.n_strips, ring.strip_cols_max, ring.n_warps, ring.lane_cols,
             self.panel_strip0.data_ptr(), self.panel_c0.data_ptr(), self.panel_nc.data_ptr(),
             ring.n_panels, ring.panel_cols_max, int(np.diff(ring.strip_l0).max()),
+            self.strip_b0.data_ptr() if blocks else None, self.block_l0.data_ptr() if blocks else None,
+            int(ring.halo_l), int(ring.halo_r),
         )
 
     @property

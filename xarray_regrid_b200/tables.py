@@ -344,6 +344,12 @@ class RowRing:
     panel_strip0: np.ndarray = None  # int32 [n_panels + 1]
     panel_c0: np.ndarray = None  # int32 [n_panels]
     panel_nc: np.ndarray = None  # int32 [n_panels]
+    # block layout of the register-resident kernel (lane_cols == 2, see ``lane_blocks_layout``); strip_c0 is then
+    # the ABSOLUTE source column of the strip's first own block
+    strip_b0: np.ndarray = None  # int32 [n_strips + 1]: first block of every strip
+    block_l0: np.ndarray = None  # int32 [n_blocks + 1]: first target of every block
+    halo_l: int = 0
+    halo_r: int = 0
 
     @property
     def n_strips(self) -> int:
@@ -610,13 +616,13 @@ def row_ring_schedule(rows: Band, n_runs: int, cols: Band | None = None, vec: in
                     ring.strip_l0, ring.strip_c0, ring.strip_nc, ring.n_warps = l0, c0, nc, n_warps
                     ring.lane_cols = lane_owned_columns(cols, l0, n_warps)
                     ring.single_panel(cols.n_src)
-        pairs = lane_pairs_layout(cols) if (allow_pairs and not ring.lane_cols and rows.k_max <= 5) else None
-        if pairs is not None:
-            # coarsening by two: the register-resident kernel with two targets per lane (conservative modes only:
-            # its zero-weight taps would let a NaN through in the NaN-propagating interpolation mode)
-            ring.strip_l0, ring.strip_c0, ring.n_warps = pairs
+        blocks = lane_blocks_layout(cols, vec) if (allow_pairs and not ring.lane_cols and rows.k_max <= 5) else None
+        if blocks is not None:
+            # coarsening by 2 - 3: the register-resident kernel with up to two targets per lane (conservative
+            # modes only: its zero-weight taps would let a NaN through in the NaN-propagating interpolation mode)
+            for name, val in blocks.items():
+                setattr(ring, name, val)
             ring.strip_nc = np.full(ring.strip_c0.size, 4 * 32, np.int32)
-            ring.single_panel(cols.n_src)
             ring.lane_cols = 2
         elif too_wide or (not ring.lane_cols and (ring.n_warps < 8 or rows.k_max <= 4)):
             # more than 12 x 32 target columns (a warp would own several strips and reload its column taps for
@@ -661,19 +667,25 @@ def lane_owned_columns(cols: Band, strip_l0: np.ndarray, n_warps: int, step: int
     return step
 
 
-def lane_pairs_layout(cols: Band, max_warps: int = 12, pairs_per_warp: int = 30):
-    """Strip layout of the register-resident kernel's TWO-TARGETS-PER-LANE variant (``lane_cols == 2``), or None.
+def lane_blocks_layout(cols: Band, vec: int = 2, max_warps: int = 12, panel_warps: int = 6,
+                       blocks_per_warp: int = 30):
+    """Layout of the register-resident kernel's BLOCK variant (``rg_row_ring_t.lane_cols == 2``), or None.
 
-    Coarsening by two: every target covered with 1..3 contiguous taps (modulo n_src) and consecutive targets
-    exactly two source columns apart.  A lane then owns a block of 4 source columns and produces the PAIR of
-    targets whose taps lie in the block and its two neighbouring columns (left halo from the previous lane, right
-    halo from the next one).  Returns ``(strip_l0, strip_c0, n_warps)``: ``strip_c0[s]`` is the first own column
-    (even) of the first pair of strip ``s``; a strip holds at most ``pairs_per_warp`` pairs (lane 0 and the lane
-    after the last pair only produce the halos)."""
+    Coarsening by 2 - 3: a lane owns a block of 4 source columns ``[c00 + 4b, c00 + 4b + 3]`` and produces the (at
+    most two, consecutive) targets assigned to its block; every tap of such a target lies in the block or within
+    two columns of it (``halo_l`` / ``halo_r`` <= 2: fetched from the neighbouring lanes with shuffles).  Needs all
+    targets covered with 1..6 contiguous taps (modulo n_src).  Lane 0 of a warp and the lane after its last block
+    only produce halos, so a warp (= strip) holds at most ``blocks_per_warp`` blocks.  More than ``max_warps``
+    strips are split into column panels of about ``panel_warps`` strips, each panel a ring row of its own blocks
+    plus one halo block either side.
+
+    Returns a dict: ``block_l0`` (CSR: first target of every block), ``strip_b0``, ``strip_l0``, ``strip_c0``
+    (absolute source column of a strip's first own block), ``n_warps``, ``halo_l``, ``halo_r``, ``panel_strip0``,
+    ``panel_c0``, ``panel_nc``."""
     n_src, n_out = cols.n_src, cols.n_out
-    if n_out < 2 or n_src % 2 or cols.k_max > 3:
+    if n_out < 2 or n_src % 2 or n_src < 16 or cols.k_max > 6:
         return None
-    if not (cols.cover > 0).all() or (cols.cnt < 1).any() or (cols.cnt > 3).any():
+    if not (cols.cover > 0).all() or (cols.cnt < 1).any():
         return None
     first = cols.idx[0].astype(np.int64)
     for i in range(1, cols.k_max):
@@ -682,26 +694,70 @@ def lane_pairs_layout(cols: Band, max_warps: int = 12, pairs_per_warp: int = 30)
             return None
     # unwrapped first taps (forward steps of a few columns, the date line crossed at most once)
     step = (first[1:] - first[:-1]) % n_src
-    if (step > 4).any():
+    if (step > 8).any():
         return None
     first_u = first[0] + np.concatenate([[0], np.cumsum(step)])
-    if first_u[-1] + int(cols.cnt[-1]) - first_u[0] > n_src + 2:
+    last_u = first_u + cols.cnt - 1
+    if last_u[-1] - first_u[0] > n_src + 4:
         return None
-    # every tap of pair p must lie in [c00 + 4p - 1, c00 + 4p + 4] for one even c00
-    rel = first_u - 4 * (np.arange(n_out) // 2)
-    lo, hi = int(rel.min()), int((rel + cols.cnt - 1).max())
-    c00 = hi - 4 + ((hi - 4) % 2)
-    if c00 > lo + 1:
+    best = None
+    align = 4 if vec == 4 else 2  # (panel rows start at c00 - 4 + 4k: 16-byte aligned bulk copies)
+    for c00 in range(int(first_u[0]) - 4, int(first_u[0]) + 3):
+        if c00 % align:
+            continue
+        blk = np.empty(n_out, np.int64)
+        cur, fill, ok = -1, 0, True
+        for l in range(n_out):
+            lo_b = -((-(int(last_u[l]) - c00 - 5)) // 4)  # ceil
+            hi_b = (int(first_u[l]) - c00 + 2) // 4
+            b = max(lo_b, 0, cur if fill < 2 else cur + 1)
+            if b > hi_b:
+                ok = False
+                break
+            cur, fill = (cur, fill + 1) if b == cur else (b, 1)
+            blk[l] = b
+        if not ok:
+            continue
+        own0 = c00 + 4 * blk
+        halo_l = int(max(0, (own0 - first_u).max()))
+        halo_r = int(max(0, (last_u - own0 - 3).max()))
+        score = (int(blk[-1]) + 1, halo_l + halo_r)
+        if best is None or score < best[0]:
+            best = (score, c00, blk, halo_l, halo_r)
+    if best is None:
         return None
-    n_pairs = -(-n_out // 2)
-    n_warps = -(-n_pairs // pairs_per_warp)
-    if n_warps > max_warps:
+    (n_blocks, _), c00, blk, halo_l, halo_r = best
+    if 4 * n_blocks > n_src + 4:
         return None
-    per = -(-n_pairs // n_warps)
-    p0 = np.append(np.arange(0, n_pairs, per), n_pairs)
-    strip_l0 = np.minimum(2 * p0, n_out).astype(np.int32)
-    strip_c0 = ((c00 + 4 * p0[:-1]) % n_src).astype(np.int32)
-    return strip_l0, strip_c0, int(p0.size - 1)
+    block_l0 = np.searchsorted(blk, np.arange(n_blocks + 1)).astype(np.int32)  # CSR over blocks
+    total_warps = -(-n_blocks // blocks_per_warp)
+    if total_warps <= max_warps:
+        n_panels, n_warps = 1, total_warps
+    else:
+        n_panels = -(-total_warps // panel_warps)
+        n_warps = -(-total_warps // n_panels)
+    n_strips = n_panels * n_warps
+    per = -(-n_blocks // n_strips)
+    if per > blocks_per_warp:
+        return None
+    strip_b0 = np.minimum(np.arange(n_strips + 1) * per, n_blocks).astype(np.int32)
+    strip_b0 = strip_b0[: int(np.searchsorted(strip_b0, n_blocks)) + 1]  # drop empty strips at the end
+    n_strips = strip_b0.size - 1
+    panel_strip0 = np.minimum(np.arange(n_panels + 1) * n_warps, n_strips).astype(np.int32)
+    panel_strip0 = panel_strip0[: int(np.searchsorted(panel_strip0, n_strips)) + 1]
+    n_panels = panel_strip0.size - 1
+    if n_panels == 1:
+        panel_c0, panel_nc = np.zeros(1, np.int32), np.asarray([n_src], np.int32)
+    else:
+        pb0, pb1 = strip_b0[panel_strip0[:-1]], strip_b0[panel_strip0[1:]]
+        panel_c0 = ((c00 + 4 * pb0.astype(np.int64) - 4) % n_src).astype(np.int32)
+        panel_nc = (4 * (pb1 - pb0 + 2)).astype(np.int32)
+        if n_src % 4 or (panel_nc > n_src).any():
+            return None
+    return dict(block_l0=block_l0, strip_b0=strip_b0, strip_l0=block_l0[strip_b0].astype(np.int32),
+                strip_c0=((c00 + 4 * strip_b0[:-1].astype(np.int64)) % n_src).astype(np.int32),
+                n_warps=int(min(n_warps, n_strips)), halo_l=max(halo_l, 1), halo_r=max(halo_r, 1),
+                panel_strip0=panel_strip0, panel_c0=panel_c0, panel_nc=panel_nc)
 
 
 def band_window_rows(band: "Band", cap: int = 16, max_rows: int = 32, step: int = 4) -> int:
