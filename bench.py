@@ -548,6 +548,7 @@ def run_ops(device, peak: float, sampler_index) -> dict:
     # ---- conservative off the headline shape (fp64, 5 % NaN, skipna) and the headline shape in fp32
     shapes = {
         "cons_0p25_to_0p5_f64": (lat025, lon025, np.arange(-90.0, 90.1, 0.5), np.arange(0.0, 360, 0.5), 256, np.float64),
+        "cons_0p5_to_1_f64": (np.arange(-90.0, 90.1, 0.5), np.arange(0.0, 360, 0.5), lat1, lon1, 1024, np.float64),
         "cons_0p1_to_0p25_f64": (lat01, lon01, lat025, lon025, 48, np.float64),
         "cons_1_to_2p5_f64": (lat1, lon1, np.arange(-90.0, 90.1, 2.5), np.arange(0.0, 360, 2.5), 2048, np.float64),
         "cons_0p25_to_1_f32": (lat025, lon025, lat1, lon1, 512, np.float32),
@@ -559,7 +560,9 @@ def run_ops(device, peak: float, sampler_index) -> dict:
         x[torch.rand(x.shape, device=device, generator=g) < 0.05] = float("nan")
         y = torch.empty((Bc, tla.size, tlo.size), device=device, dtype=tdt)
         ring = plan._ring(Bc, la.size, lo.size, tdt)
-        kern = "generic" if ring is None else ("lanes" if ring.host.lane_cols else "ring")
+        kern = ("generic" if ring is None else "lanes (one target per lane)" if ring.host.lane_cols == 4
+                else f"lanes (blocks, {ring.host.n_panels} panel(s) x {ring.host.n_warps} warps)" if ring.host.lane_cols == 2
+                else "two-phase ring")
         esz = 8 if tdt == torch.float64 else 4
         record(name, lambda: plan(x, skipna=True, nan_threshold=0.5, out=y),
                Bc * (la.size * lo.size + tla.size * tlo.size) * esz, Bc * la.size * lo.size, "source cells",

@@ -266,9 +266,28 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     const bool panel_cta = !lanes && have_panels && ring_c->n_warps <= 6 && kw >= 3;
     const bool panel_tg2 = panel_cta && ring_c->strip_targets_max > 32;
     // (register-resident kernel: 14 warps of fp64 fill an SM's registers; rows of fewer consumer warps leave
-    // room for more CTAs: <= 120 (fp64) / 72 (fp32) registers per thread, see -Xptxas -v)
-    const int lane_threads = (ring_c->n_warps + 2) * 32;
-    const int lane_ctas = 65536 / (lane_threads * (sizeof(T) == 8 ? 120 : 72));
+    // room for more CTAs)
+    using LanesKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev, T, int, int);
+    LanesKernel lk = nullptr;
+    int lane_ctas = 1;
+    if (lanes) {
+      // block layout: M = 2 / 3 / 4 = halo columns (1, 1) / (2, 2) / (1, 2); narrow rows (<= 3 consumer warps per
+      // CTA) run four CTAs per SM -- the register cap of (160 threads, 4 CTAs) is 96
+      const bool narrow = ring_c->n_warps <= 3;
+      const int m = !lanes2 ? 1 : ring_c->halo_l > 1 ? 3 : ring_c->halo_r > 1 ? 4 : 2;
+#define RG_BLOCKS(MV)                                                                                          \
+  (narrow ? (skipna ? conservative_lanes_kernel<T, true, 5, 5, MV, 4> : conservative_lanes_kernel<T, false, 5, 5, MV, 4>) \
+          : (skipna ? conservative_lanes_kernel<T, true, 14, 5, MV> : conservative_lanes_kernel<T, false, 14, 5, MV>))
+      lk = m == 3 ? RG_BLOCKS(3) : m == 4 ? RG_BLOCKS(4) : m == 2 ? RG_BLOCKS(2)
+#undef RG_BLOCKS
+           : rows.k_max <= 5
+               ? (skipna ? conservative_lanes_kernel<T, true, 14, 5> : conservative_lanes_kernel<T, false, 14, 5>)
+               : (skipna ? conservative_lanes_kernel<T, true, 14, 8> : conservative_lanes_kernel<T, false, 14, 8>);
+      cudaFuncAttributes fa;
+      RG_CUDA(cudaFuncGetAttributes(&fa, lk));
+      const int regs = (fa.numRegs + 7) / 8 * 8;  // allocated per warp in units of 8 registers per thread
+      lane_ctas = 65536 / ((ring_c->n_warps + 2) * 32 * regs);
+    }
     const int min_ctas = lanes ? (lane_ctas > 4 ? 4 : lane_ctas < 1 ? 1 : lane_ctas)
                          : panel_cta ? ((rows.k_max <= 4 && !(panel_tg2 && kw >= 5)) ? 3 : 2) : 1;
     const RingLayout probe =
@@ -364,12 +383,6 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       long long grid = static_cast<long long>(dev.sm_count) * ctas;
       if (grid > tasks) grid = tasks;
       if (lanes) {
-        const bool halo2 = lanes2 && (ring_c->halo_l > 1 || ring_c->halo_r > 1);
-        auto lk = halo2 ? (skipna ? conservative_lanes_kernel<T, true, 14, 5, 3> : conservative_lanes_kernel<T, false, 14, 5, 3>)
-                  : lanes2 ? (skipna ? conservative_lanes_kernel<T, true, 14, 5, 2> : conservative_lanes_kernel<T, false, 14, 5, 2>)
-                  : rows.k_max <= 5
-                      ? (skipna ? conservative_lanes_kernel<T, true, 14, 5> : conservative_lanes_kernel<T, false, 14, 5>)
-                      : (skipna ? conservative_lanes_kernel<T, true, 14, 8> : conservative_lanes_kernel<T, false, 14, 8>);
         const size_t smem_l = L.total + row_tables;
         RG_CUDA(cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_l)));
         if (lanes2 && n_panels > 1) {  // a CTA stays on one panel: task % n_panels must not depend on the iteration

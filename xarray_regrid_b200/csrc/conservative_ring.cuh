@@ -644,9 +644,10 @@ __device__ __forceinline__ void lane_phase1_dispatch(int cnt, uint32_t baseA, ui
 // shuffles.  Lane 0 of a warp and the lane after its last block only produce halos.  A row wider than 12 warps
 // of 30 blocks is cut into column panels (ring rows = the panel's blocks + one halo block either side); the
 // launcher makes the grid a multiple of the panel count, so a CTA stays on ONE panel and the lanes' column
-// offsets and weights are kernel-lifetime constants.  M = 3: the same with two halo columns either side (M = 2: one).
-template <typename T, bool SKIPNA, int MAXWARPS, int RMAX, int M = 1>
-__global__ void __launch_bounds__(MAXWARPS * 32, sizeof(T) == 4 ? 2 : 1)
+// offsets and weights are kernel-lifetime constants.  M = 3: the same with two halo columns either side (M = 2: one),
+// M = 4: one on the left, two on the right.
+template <typename T, bool SKIPNA, int MAXWARPS, int RMAX, int M = 1, int MINB = (sizeof(T) == 4 ? 2 : 1)>
+__global__ void __launch_bounds__(MAXWARPS * 32, MINB)
 conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs,
                           long long xrs, long long ybs, Band<T> cols, RingDev ring, T thr, int ring_slots,
                           int n_rows_out) {
@@ -774,7 +775,7 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
     pair_store = ntg == 2 && (Wo % 2 == 0) && (ybs % 2 == 0) && (tgt0 % 2 == 0) &&
                  reinterpret_cast<uintptr_t>(y) % (2 * sizeof(T)) == 0;
   }
-  constexpr bool halo_l2 = M == 3, halo_r2 = M == 3;  // (compile time: a predicated fp64 FMA costs three instructions)
+  constexpr bool halo_l2 = M == 3, halo_r2 = M == 3 || M == 4;  // (compile time: a predicated fp64 FMA costs three instructions)
   // zero-weight taps must not see the data (0 * NaN) -- only where NaNs survive the latitude pass
   const bool padded = !SKIPNA && !ring.zero_fill && ccnt >= 0 && ccnt < 5;
   const bool zero_fill = !SKIPNA && ring.zero_fill;
@@ -847,23 +848,24 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
           for (int j = 0; j < 2; ++j) {
             out[j] = nan;
             if (rec.y >= 0 && have2[j]) {
-              T so = tw2[j][1] * tl1;
+              // two short chains per sum (a dependent fp64 FMA waits ~10 cycles)
+              T so = tw2[j][1] * tl1, so2 = tw2[j][4] * t[2];
               so = fma(tw2[j][2], t[0], so);
+              so2 = fma(tw2[j][5], t[3], so2);
               so = fma(tw2[j][3], t[1], so);
-              so = fma(tw2[j][4], t[2], so);
-              so = fma(tw2[j][5], t[3], so);
-              so = fma(tw2[j][6], tr0, so);
+              so2 = fma(tw2[j][6], tr0, so2);
               if constexpr (halo_l2) so = fma(tw2[j][0], tl0, so);
-              if constexpr (halo_r2) so = fma(tw2[j][7], tr1, so);
+              if constexpr (halo_r2) so2 = fma(tw2[j][7], tr1, so2);
+              so += so2;
               if constexpr (SKIPNA) {
-                T sv = tw2[j][1] * vl1;
+                T sv = tw2[j][1] * vl1, sv2 = tw2[j][4] * v[2];
                 sv = fma(tw2[j][2], v[0], sv);
+                sv2 = fma(tw2[j][5], v[3], sv2);
                 sv = fma(tw2[j][3], v[1], sv);
-                sv = fma(tw2[j][4], v[2], sv);
-                sv = fma(tw2[j][5], v[3], sv);
-                sv = fma(tw2[j][6], vr0, sv);
+                sv2 = fma(tw2[j][6], vr0, sv2);
                 if constexpr (halo_l2) sv = fma(tw2[j][0], vl0, sv);
-                if constexpr (halo_r2) sv = fma(tw2[j][7], vr1, sv);
+                if constexpr (halo_r2) sv2 = fma(tw2[j][7], vr1, sv2);
+                sv += sv2;
                 out[j] = (sv >= thr) ? normalise_div(so, sv) : nan;
               } else {
                 out[j] = so;

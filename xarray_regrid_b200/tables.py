@@ -667,8 +667,8 @@ def lane_owned_columns(cols: Band, strip_l0: np.ndarray, n_warps: int, step: int
     return step
 
 
-def lane_blocks_layout(cols: Band, vec: int = 2, max_warps: int = 12, panel_warps: int = 6,
-                       blocks_per_warp: int = 30):
+def lane_blocks_layout(cols: Band, vec: int = 2, max_warps: int = 12, panel_warps: int = 12,
+                       blocks_per_warp: int = 30, warp_choices=()):
     """Layout of the register-resident kernel's BLOCK variant (``rg_row_ring_t.lane_cols == 2``), or None.
 
     Coarsening by 2 - 3: a lane owns a block of 4 source columns ``[c00 + 4b, c00 + 4b + 3]`` and produces the (at
@@ -676,7 +676,8 @@ def lane_blocks_layout(cols: Band, vec: int = 2, max_warps: int = 12, panel_warp
     two columns of it (``halo_l`` / ``halo_r`` <= 2: fetched from the neighbouring lanes with shuffles).  Needs all
     targets covered with 1..6 contiguous taps (modulo n_src).  Lane 0 of a warp and the lane after its last block
     only produce halos, so a warp (= strip) holds at most ``blocks_per_warp`` blocks.  More than ``max_warps``
-    strips are split into column panels of about ``panel_warps`` strips, each panel a ring row of its own blocks
+    strips are split into the fewest column panels of at most ``panel_warps`` strips (wide CTAs beat
+    several narrow ones: 0.1 -> 0.25 deg 3 panels of 10 warps 5.06 TB/s, 5 of 6 warps 4.5 TB/s), each panel a ring row of its own blocks
     plus one halo block either side.
 
     Returns a dict: ``block_l0`` (CSR: first target of every block), ``strip_b0``, ``strip_l0``, ``strip_c0``
@@ -721,18 +722,22 @@ def lane_blocks_layout(cols: Band, vec: int = 2, max_warps: int = 12, panel_warp
         own0 = c00 + 4 * blk
         halo_l = int(max(0, (own0 - first_u).max()))
         halo_r = int(max(0, (last_u - own0 - 3).max()))
-        score = (int(blk[-1]) + 1, halo_l + halo_r)
+        score = (int(blk[-1]) + 1, halo_l + halo_r, halo_l)  # (the kernel has a (1, 2) halo instance, no (2, 1))
         if best is None or score < best[0]:
             best = (score, c00, blk, halo_l, halo_r)
     if best is None:
         return None
-    (n_blocks, _), c00, blk, halo_l, halo_r = best
+    (n_blocks, _, _), c00, blk, halo_l, halo_r = best
     if 4 * n_blocks > n_src + 4:
         return None
     block_l0 = np.searchsorted(blk, np.arange(n_blocks + 1)).astype(np.int32)  # CSR over blocks
     total_warps = -(-n_blocks // blocks_per_warp)
     if total_warps <= max_warps:
-        n_panels, n_warps = 1, total_warps
+        # (as few warps as the blocks need: full warps beat more, emptier ones -- 1 -> 2.5 deg: 3 warps of 30 blocks
+        # 4.2 TB/s, 4 warps of 23 blocks 2.7 TB/s; ``warp_choices`` is the experiment's knob)
+        n_panels = 1
+        n_warps = next((w for w in warp_choices if w >= total_warps), total_warps)
+        n_warps = max(total_warps, min(n_warps, n_blocks // 8))
     else:
         n_panels = -(-total_warps // panel_warps)
         n_warps = -(-total_warps // n_panels)
