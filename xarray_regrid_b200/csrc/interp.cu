@@ -90,15 +90,133 @@ poison_kernel(T* __restrict__ y, long long n, const int32_t* __restrict__ flag) 
 // value is folded in first).  O(n) per line instead of the O(n * 63) of the truncated inverse.
 //   forward   z_i = y_i - l1_i z_{i-1} - l2_i z_{i-2}
 //   backward  c_i = (z_i - u1_i c_{i+1} - u2_i c_{i+2}) * dinv_i
+// Factors as the kernels keep them in shared memory: [5][n] = -l1, -l2, dinv, -u1 * dinv, -u2 * dinv, so that a step
+// of either substitution has ONE fused multiply-add on its critical path:
+//   forward   z_i = fma(-l1_i, z_{i-1}, fma(-l2_i, z_{i-2}, y_i))
+//   backward  c_i = fma(-u1_i dinv_i, c_{i+1}, fma(-u2_i dinv_i, c_{i+2}, z_i dinv_i))
+__device__ __forceinline__ void spline_stage_factors(double* s_fac, const double* __restrict__ lower,
+                                                     const double* __restrict__ upper, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = upper[i];
+    s_fac[i] = -lower[i];
+    s_fac[n + i] = -lower[n + i];
+    s_fac[2 * n + i] = d;
+    s_fac[3 * n + i] = -upper[n + i] * d;
+    s_fac[4 * n + i] = -upper[2 * n + i] * d;
+  }
+}
+
+// One substitution over the elements [lo, hi) of a line p[0], p[step], ... (forward: ascending from the state
+// (s1, s2) = (z_{lo-1}, z_{lo-2}); backward: descending from (c_hi, c_{hi+1})).  Batches of 8: the next batch's values
+// and factors are fetched before the current batch's dependent chain runs (the solve is in place, so the compiler
+// may not move loads above the stores by itself); full batches carry no bounds test on the chain.  STORE = false
+// only advances the state (warm-up over a neighbouring segment, see the tile kernel).
+template <bool STORE, typename Ptr>
+__device__ __forceinline__ void spline_forward(Ptr p, long long step, int lo, int hi, const double* l1,
+                                               const double* l2, double& z1, double& z2) {
+  double v[8], a1[8], a2[8], vn[8], a1n[8], a2n[8];
+  const int full = lo + ((hi - lo) & ~7);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int i = min(lo + e, hi - 1);
+    v[e] = p[i * step];
+    a1[e] = l1[i];
+    a2[e] = l2[i];
+  }
+  for (int i0 = lo; i0 < full; i0 += 8) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = min(i0 + 8 + e, hi - 1);
+      vn[e] = p[i * step];
+      a1n[e] = l1[i];
+      a2n[e] = l2[i];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const double zi = fma(a1[e], z1, fma(a2[e], z2, v[e]));  // the inner term does not wait for z1
+      z2 = z1;
+      z1 = zi;
+      if constexpr (STORE) p[(i0 + e) * step] = zi;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = vn[e];
+      a1[e] = a1n[e];
+      a2[e] = a2n[e];
+    }
+  }
+  for (int i = full; i < hi; ++i) {
+    const double zi = fma(l1[i], z1, fma(l2[i], z2, p[i * step]));
+    z2 = z1;
+    z1 = zi;
+    if constexpr (STORE) p[i * step] = zi;
+  }
+}
+
+template <bool STORE, typename Ptr>
+__device__ __forceinline__ void spline_backward(Ptr p, long long step, int lo, int hi, const double* dinv,
+                                                const double* u1, const double* u2, double& c1, double& c2) {
+  double v[8], a1[8], a2[8], d[8], vn[8], a1n[8], a2n[8], dn[8];
+  const int tail = (hi - lo) & 7;  // the descending walk starts with the partial batch
+  for (int i = hi - 1; i >= hi - tail; --i) {
+    const double ci = fma(u1[i], c1, fma(u2[i], c2, p[i * step] * dinv[i]));
+    c2 = c1;
+    c1 = ci;
+    if constexpr (STORE) p[i * step] = ci;
+  }
+  const int top = hi - tail - 1;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int i = max(top - e, lo);
+    v[e] = p[i * step];
+    a1[e] = u1[i];
+    a2[e] = u2[i];
+    d[e] = dinv[i];
+  }
+  for (int i0 = top; i0 >= lo; i0 -= 8) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = max(i0 - 8 - e, lo);
+      vn[e] = p[i * step];
+      a1n[e] = u1[i];
+      a2n[e] = u2[i];
+      dn[e] = dinv[i];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const double ci = fma(a1[e], c1, fma(a2[e], c2, v[e] * d[e]));
+      c2 = c1;
+      c1 = ci;
+      if constexpr (STORE) p[(i0 - e) * step] = ci;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = vn[e];
+      a1[e] = a1n[e];
+      a2[e] = a2n[e];
+      d[e] = dn[e];
+    }
+  }
+}
+
+template <typename Ptr>
+__device__ __forceinline__ void spline_solve_line(Ptr p, long long step, int n, const double* l1, const double* l2,
+                                                  const double* dinv, const double* u1, const double* u2) {
+  double s1 = 0.0, s2 = 0.0;
+  spline_forward<true>(p, step, 0, n, l1, l2, s1, s2);
+  s1 = 0.0;
+  s2 = 0.0;
+  spline_backward<true>(p, step, 0, n, dinv, u1, u2, s1, s2);
+}
+
 template <int AXIS>
 __global__ void __launch_bounds__(128)
 spline_solve_kernel(double* __restrict__ y, long long batch, long long ybs, long long yrs, int H, int W,
                     const double* __restrict__ lower, const double* __restrict__ upper) {
-  extern __shared__ double s_fac[];  // [5][n]: l1, l2, dinv, u1, u2
+  extern __shared__ double s_fac[];  // [5][n], see spline_stage_factors
   const int n = AXIS == 0 ? H : W;
   const int per_slab = AXIS == 0 ? W : H;
-  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s_fac[i] = lower[i];
-  for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_fac[2 * n + i] = upper[i];
+  spline_stage_factors(s_fac, lower, upper, n);
   __syncthreads();
   const double *l1 = s_fac, *l2 = s_fac + n, *dinv = s_fac + 2 * n, *u1 = s_fac + 3 * n, *u2 = s_fac + 4 * n;
   const long long line = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -106,130 +224,105 @@ spline_solve_kernel(double* __restrict__ y, long long batch, long long ybs, long
   const long long b = line / per_slab;
   const int j = static_cast<int>(line % per_slab);
   double* p = y + b * ybs + (AXIS == 0 ? static_cast<long long>(j) : static_cast<long long>(j) * yrs);
-  const long long step = AXIS == 0 ? yrs : 1;
-
-  // The solve is in place, so the compiler may not move the next 8 loads above this batch's stores: they are issued
-  // by hand one batch ahead (the batches touch disjoint elements), otherwise every batch waits a full DRAM latency.
-  double z1 = 0.0, z2 = 0.0;
-  double v[8], vn[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = (e < n) ? p[e * step] : 0.0;
-  for (int i0 = 0; i0 < n; i0 += 8) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) vn[e] = (i0 + 8 + e < n) ? p[(i0 + 8 + e) * step] : 0.0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int i = i0 + e;
-      if (i < n) {
-        const double zi = fma(-l1[i], z1, fma(-l2[i], z2, v[e]));  // the inner term does not wait for z1
-        z2 = z1;
-        z1 = zi;
-        p[i * step] = zi;
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = vn[e];
-  }
-  double c1 = 0.0, c2 = 0.0;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = (n - 1 - e >= 0) ? p[(n - 1 - e) * step] : 0.0;
-  for (int i0 = n - 1; i0 >= 0; i0 -= 8) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) vn[e] = (i0 - 8 - e >= 0) ? p[(i0 - 8 - e) * step] : 0.0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int i = i0 - e;
-      if (i >= 0) {
-        const double ci = fma(-u1[i], c1, fma(-u2[i], c2, v[e])) * dinv[i];
-        c2 = c1;
-        c1 = ci;
-        p[i * step] = ci;
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = vn[e];
-  }
+  spline_solve_line(p, AXIS == 0 ? yrs : 1, n, l1, l2, dinv, u1, u2);
 }
 
 // Lines along the contiguous axis: a CTA stages kTileLines whole lines in shared memory with coalesced
-// loads (odd row pitch: the per-line walkers hit distinct banks), one thread per line runs both
-// substitutions out of shared memory, the CTA writes the tile back.  One read and one write of the data.
+// loads (odd row pitch: the per-line walkers hit distinct banks), runs both substitutions out of shared memory and
+// writes the tile back.  One read and one write of the data.
+//
+// Four threads per line (warp s = segment s of every line of the tile): both recurrences are contractions (interior
+// factors of a spline on a near-regular axis: 0.268 per step), so a segment may start from a ZERO state kWarm
+// elements early -- what it forgets is below 0.35^40 = 6e-19 of the data -- instead of waiting for the segment before
+// it.  Phases, a CTA barrier between them: forward warm-up over the previous segment's tail (read only), forward
+// over the own segment (in place), backward warm-up over the next segment's head (read only), backward over the own
+// segment.  262 instead of 724 dependent steps per thread for 362-element lines (ncu before: one warp per CTA
+// walking the lines, 4.3 cycles per instruction of its serial stream, 66 us).  The CTA checks the factors of every
+// warm-up window first and walks whole lines with one thread each when a window is not contractive enough
+// (irregular axes) or the line is too short.
 constexpr int kTileLines = 32;
+constexpr int kSplineWarm = 40;
+constexpr double kSplineRho = 0.35;  // max |a1| + |a2| per step inside a warm-up window
 __global__ void __launch_bounds__(128)
 spline_solve_tile_kernel(double* __restrict__ y, long long n_lines, int H, long long ybs, long long yrs, int W,
                          const double* __restrict__ lower, const double* __restrict__ upper) {
   extern __shared__ double s_fac[];  // [5][W] factors, then [kTileLines][W | 1] data
   const int n = W, pitch = W | 1;
   double* tile = s_fac + 5 * n;
-  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s_fac[i] = lower[i];
-  for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_fac[2 * n + i] = upper[i];
+  spline_stage_factors(s_fac, lower, upper, n);
   const long long line0 = static_cast<long long>(blockIdx.x) * kTileLines;
   const int lines = static_cast<int>(min(static_cast<long long>(kTileLines), n_lines - line0));
   // all lines of the tile in flight at once (LDGSTS, 8 bytes per request: the odd pitch allows no wider one); with
   // plain loads + stores the lines were fetched one after the other and the kernel spent its time on their latency
   // (ncu: long-scoreboard 9.5 warps per issue, 11 % issue activity)
-  for (int l = 0; l < lines; ++l) {
-    const long long line = line0 + l;
-    const double* src = y + (line / H) * ybs + (line % H) * yrs;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(tile + l * pitch + j));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + j) : "memory");
+  // (slab, row) of the tile's lines advance with a carry: a 64-bit division per line was most of the kernel's
+  // instructions (ncu: 34 K warp instructions per tile, 8 K of them per warp in these two copy loops)
+  const long long b0 = line0 / H;
+  const int r0 = static_cast<int>(line0 - b0 * H);
+  {
+    const double* src = y + b0 * ybs + static_cast<long long>(r0) * yrs;
+    int r = r0;
+    const uint32_t t0 = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+    for (int l = 0; l < lines; ++l) {
+      for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const uint32_t d = t0 + static_cast<uint32_t>(l * pitch + j) * 8u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + j) : "memory");
+      }
+      src += yrs;
+      if (++r == H) {  // next slab
+        r = 0;
+        src += ybs - static_cast<long long>(H) * yrs;
+      }
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  if (threadIdx.x < lines) {
-    const double *l1 = s_fac, *l2 = s_fac + n, *dinv = s_fac + 2 * n, *u1 = s_fac + 3 * n, *u2 = s_fac + 4 * n;
-    double* p = tile + threadIdx.x * pitch;
-    // values and factors are fetched 8 at a time so that only the recurrence itself is serial
-    double z1 = 0.0, z2 = 0.0;
-    for (int i0 = 0; i0 < n; i0 += 8) {
-      double v[8], a1[8], a2[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = min(i0 + e, n - 1);
-        v[e] = p[i];
-        a1[e] = l1[i];
-        a2[e] = l2[i];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const double zi = fma(-a1[e], z1, fma(-a2[e], z2, v[e]));  // the inner term does not wait for z1
-        if (i0 + e < n) {
-          z2 = z1;
-          z1 = zi;
-          p[i0 + e] = zi;
-        }
-      }
-    }
-    double c1 = 0.0, c2 = 0.0;
-    for (int i0 = n - 1; i0 >= 0; i0 -= 8) {
-      double v[8], a1[8], a2[8], d[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = max(i0 - e, 0);
-        v[e] = p[i];
-        a1[e] = u1[i];
-        a2[e] = u2[i];
-        d[e] = dinv[i];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const double ci = fma(-a1[e], c1, fma(-a2[e], c2, v[e])) * d[e];
-        if (i0 - e >= 0) {
-          c2 = c1;
-          c1 = ci;
-          p[i0 - e] = ci;
-        }
-      }
+  const double *l1 = s_fac, *l2 = s_fac + n, *dinv = s_fac + 2 * n, *u1 = s_fac + 3 * n, *u2 = s_fac + 4 * n;
+  // segments [s * seg, (s + 1) * seg): are all warm-up windows inside the line and contractive?
+  const int seg = (n + 3) / 4;
+  int bad = (seg < kSplineWarm + 1 || 3 * seg + kSplineWarm > n) ? 1 : 0;
+  if (!bad) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int r = i % seg, s = i / seg;
+      const bool fwd_win = s <= 2 && r >= seg - kSplineWarm;  // tail of segments 0..2: forward warm-up of s + 1
+      const bool bwd_win = s >= 1 && r < kSplineWarm;         // head of segments 1..3: backward warm-up of s - 1
+      if (fwd_win && fabs(l1[i]) + fabs(l2[i]) > kSplineRho) bad = 1;
+      if (bwd_win && fabs(u1[i]) + fabs(u2[i]) > kSplineRho) bad = 1;
     }
   }
-  __syncthreads();
-  for (int l = 0; l < lines; ++l) {
-    const long long line = line0 + l;
-    double* dst = y + (line / H) * ybs + (line % H) * yrs;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) dst[j] = tile[l * pitch + j];
+  bad = __syncthreads_or(bad);
+  if (bad) {
+    if (threadIdx.x < lines) spline_solve_line(tile + threadIdx.x * pitch, 1, n, l1, l2, dinv, u1, u2);
+    __syncthreads();
+  } else {
+    const int s = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const bool on = l < lines;
+    double* p = tile + (on ? l : 0) * pitch;
+    const int lo = s * seg, hi = min(lo + seg, n);
+    double s1 = 0.0, s2 = 0.0;
+    if (on && s > 0) spline_forward<false>(p, 1, lo - kSplineWarm, lo, l1, l2, s1, s2);
+    __syncthreads();
+    if (on) spline_forward<true>(p, 1, lo, hi, l1, l2, s1, s2);
+    __syncthreads();
+    s1 = 0.0;
+    s2 = 0.0;
+    if (on && s < 3) spline_backward<false>(p, 1, hi, hi + kSplineWarm, dinv, u1, u2, s1, s2);
+    __syncthreads();
+    if (on) spline_backward<true>(p, 1, lo, hi, dinv, u1, u2, s1, s2);
+    __syncthreads();
+  }
+  {
+    double* dst = y + b0 * ybs + static_cast<long long>(r0) * yrs;
+    int r = r0;
+    for (int l = 0; l < lines; ++l) {
+      for (int j = threadIdx.x; j < n; j += blockDim.x) dst[j] = tile[l * pitch + j];
+      dst += yrs;
+      if (++r == H) {
+        r = 0;
+        dst += ybs - static_cast<long long>(H) * yrs;
+      }
+    }
   }
 }
 

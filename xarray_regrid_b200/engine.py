@@ -742,7 +742,9 @@ class InterpPlan:
         work = torch.float64
         if self.method == "linear" and out_dtype == "same" and x.dtype in (torch.float32, torch.float16, torch.bfloat16):
             work = torch.float32
-        x3, lead = _as_batch(x, work)
+        # (cubic on fp32 data: the gather in front of the solves converts, no separate cast pass)
+        keep32 = self.method == "cubic" and x.dtype == torch.float32
+        x3, lead = _as_batch(x, torch.float32 if keep32 else work)
         if self.method == "linear":
             y = self.op.run(x3, NAN_PROPAGATE, 0.0, out=out)
             return y.view(tuple(lead) + tuple(y.shape[-2:]))
@@ -758,13 +760,14 @@ class InterpPlan:
         flag = nan_flag if nan_flag is not None else torch.zeros(1, dtype=torch.int32, device=x3.device)
         stream = _stream_ptr(x3.device)
         if B:
-            check(lib.rg_nan_flag_f64(x3.data_ptr(), B, H, W, x3.stride(0) if B > 1 else H * x3.stride(1),
-                                      x3.stride(1), flag.data_ptr(), stream), "rg_nan_flag")
+            flag_fn = lib.rg_nan_flag_f32 if keep32 else lib.rg_nan_flag_f64
+            check(flag_fn(x3.data_ptr(), B, H, W, x3.stride(0) if B > 1 else H * x3.stride(1),
+                          x3.stride(1), flag.data_ptr(), stream), "rg_nan_flag")
         for s0 in range(0, B, self.chunk):
             xs = x3[s0:s0 + self.chunk]
             coeff = self._coefficients_lu(xs, Hf, Wf) if (self._lu is not None and self.use_lu) else None
             if coeff is None:
-                coeff = self.pre.run(xs, NAN_PROPAGATE, 0.0)
+                coeff = self.pre.run(xs.to(work), NAN_PROPAGATE, 0.0)
             self.op.run(coeff, NAN_PROPAGATE, 0.0, out=y[s0:s0 + self.chunk])
         if B and nan_flag is None:
             check(lib.rg_poison_if_f64(y.data_ptr(), y.numel(), flag.data_ptr(), stream), "rg_poison_if")
