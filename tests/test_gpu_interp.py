@@ -69,16 +69,27 @@ def test_c3_cubic_upsampling(engine):
     _check(y, want, 1e-11)  # spec: 1e-5 for fp32 input; the fp64 pipeline is ~1e-13
 
 
-@pytest.mark.parametrize("case", ["global", "irregular", "rows_only", "descending"])
+@pytest.mark.parametrize("case", ["global", "irregular", "rows_only", "descending", "irregular_long",
+                                  "regular_long_regional"])
 def test_cubic_lu_prefilter_matches_band_prefilter_and_oracle(engine, case):
     """The O(n) banded LU substitution (rg_spline_solve_f64) and the truncated-inverse band pass are two
-    routes to scipy's spline coefficients: both must match the oracle (scipy itself) to 1e-11."""
+    routes to scipy's spline coefficients: both must match the oracle (scipy itself) to 1e-11.  Lines of 200+
+    elements along the contiguous axis are solved by four threads each, every segment warmed up from a zero state
+    over a contractive window (global, regular_long_regional); an irregular axis of that length is not contractive
+    and must take the one-thread-per-line walk (irregular_long)."""
     rng = np.random.default_rng(21)
     if case == "global":
         (lat, lon), (tlat, tlon) = GRID_1, (np.arange(-89.9, 90, 0.7), np.arange(0.05, 359.9, 0.9))
     elif case == "irregular":
         lat, lon = np.sort(rng.uniform(-60, 60, 75)), np.sort(rng.uniform(10, 200, 130))
         tlat, tlon = np.linspace(lat[0], lat[-1], 140), np.linspace(lon[0], lon[-1], 260)
+    elif case == "irregular_long":
+        lat, lon = np.sort(rng.uniform(-60, 60, 45)), np.sort(rng.uniform(10, 200, 300))
+        lon = lon[np.concatenate([[True], np.diff(lon) > 0.05])]  # (near-coincident knots: ill-conditioned for scipy too)
+        tlat, tlon = np.linspace(lat[0], lat[-1], 60), np.linspace(lon[0], lon[-1], 500)
+    elif case == "regular_long_regional":
+        lat, lon = np.arange(-20.0, 21.0, 1.0), np.arange(30.0, 93.0, 0.25)  # 252 columns, 41 x 3 = 123 lines
+        tlat, tlon = np.arange(-19.5, 20.0, 0.4), np.arange(30.1, 92.0, 0.1)
     elif case == "rows_only":
         lat, lon = np.arange(0.0, 40.0, 1.0), np.arange(100.0, 133.0, 1.0)
         tlat, tlon = np.arange(0.5, 38.0, 0.25), None
