@@ -22,7 +22,9 @@ namespace rg {
 constexpr int kUpMaxThreads = 512;
 constexpr int kUpRowCap = 16;      // source rows held in shared memory
 constexpr int kUpBandRows = 32;    // output rows per task
-constexpr int kUpRowsPerSync = 4;  // output rows produced per barrier
+constexpr int kUpRowsPerSync = 4;  // output rows produced per barrier (RPS; 8 for the 512-thread fp64 instances:
+                                   // 8 x 181 (row, vector) pairs fill three rounds of 512 threads to 94 %, 4 x 181 two
+                                   // rounds to 71 %, and the CTA meets at half as many barriers)
 
 template <typename T> struct Vec4;
 template <> struct alignas(16) Vec4<float> { float v[4]; };
@@ -50,7 +52,7 @@ __device__ __forceinline__ void st_stream4(double* p, const Vec4<double>& a) {
 // rg_band_t.group_span): the window is loaded once per group (KC + 2 loads instead of 4 * KC) and every output is a
 // (KC + 2)-term dot product with its taps shifted into place (zeros elsewhere).  Used for the 4-tap cubic evaluation,
 // where a NaN anywhere blanks the whole result anyway, so a zero weight times a NaN neighbour cannot matter.
-template <typename T, int KR, int KC, int G, int ZW, int NT, int BUF, int WIN>
+template <typename T, int KR, int KC, int G, int ZW, int NT, int BUF, int WIN, int RPS>
 __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, int nk, int W, int Wo,
                                         const T* s_x, T* s_z, const int (*s_off)[KR], const T (*s_rw)[KR],
                                         const int* s_state, const int (&ci)[G][4][KC],
@@ -65,7 +67,7 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
     for (int p = tid; p < nvec * nk; p += NT) {
       int q = 0;
 #pragma unroll
-      for (int i = 1; i < kUpRowsPerSync; ++i) q += (p >= i * nvec) ? 1 : 0;
+      for (int i = 1; i < RPS; ++i) q += (p >= i * nvec) ? 1 : 0;
       const int j = p - q * nvec;
       const int m = kb_local + q;
       Pack<T, V> acc;
@@ -78,7 +80,7 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
 #pragma unroll
         for (int e = 0; e < V; ++e) acc.v[e] = fma(w, xv.v[e], acc.v[e]);
       }
-      *reinterpret_cast<Pack<T, V>*>(s_z + (BUF * kUpRowsPerSync + q) * ZW + j * V) = acc;
+      *reinterpret_cast<Pack<T, V>*>(s_z + (BUF * RPS + q) * ZW + j * V) = acc;
     }
   } else {
     for (int q = 0; q < nk; ++q) {
@@ -87,7 +89,7 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
       T w[KR];
 #pragma unroll
       for (int t = 0; t < KR; ++t) { off[t] = s_off[m][t]; w[t] = s_rw[m][t]; }
-      T* z = s_z + (BUF * kUpRowsPerSync + q) * ZW;
+      T* z = s_z + (BUF * RPS + q) * ZW;
       for (int j = tid; j < W; j += NT) {
         T acc = T(0);
 #pragma unroll
@@ -99,10 +101,10 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
   __syncthreads();
   // ---- (B) longitude pass + 16-byte streaming stores
 #pragma unroll
-  for (int q = 0; q < kUpRowsPerSync; ++q) {
+  for (int q = 0; q < RPS; ++q) {
     if (q < nk) {
       T* yrow = y_band + static_cast<long long>(kb_local + q) * Wo;
-      const unsigned char* z = reinterpret_cast<const unsigned char*>(s_z + (BUF * kUpRowsPerSync + q) * ZW);
+      const unsigned char* z = reinterpret_cast<const unsigned char*>(s_z + (BUF * RPS + q) * ZW);
       const int state = s_state[kb_local + q];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -148,14 +150,14 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
   }
 }
 
-template <typename T, int KR, int KC, int G, int ZW, int NT, int WIN = 0>
+template <typename T, int KR, int KC, int G, int ZW, int NT, int WIN = 0, int RPS = kUpRowsPerSync>
 __global__ void __launch_bounds__(NT)
 upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, long long xbs, long long xrs,
                 long long ybs, Band<T> rows, Band<T> cols, int band_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int H = rows.n_src, W = cols.n_src, Ho = rows.n_out, Wo = cols.n_out;
-  T* s_z = reinterpret_cast<T*>(smem_raw);             // [2][kUpRowsPerSync][ZW] latitude-interpolated rows
-  T* s_x = s_z + 2 * kUpRowsPerSync * ZW;              // [2][kUpRowCap][W] staged source rows (this / next band)
+  T* s_z = reinterpret_cast<T*>(smem_raw);             // [2][RPS][ZW] latitude-interpolated rows
+  T* s_x = s_z + 2 * RPS * ZW;              // [2][kUpRowCap][W] staged source rows (this / next band)
   // per-band row metadata, filled by warp 0 (double-buffered like the rows)
   __shared__ int s_off[2][kUpBandRows][KR];  // element offset of tap t's row inside the window
   __shared__ T s_rw[2][kUpBandRows][KR];
@@ -165,7 +167,7 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
   const int tid = threadIdx.x;
   const T nan = quiet_nan<T>();
   if constexpr (WIN) {  // z columns W, W + 1 of every z row: read by windows at the right edge, weight 0
-    for (int i = tid; i < 2 * kUpRowsPerSync * 2; i += NT) s_z[(i >> 1) * ZW + W + (i & 1)] = T(0);
+    for (int i = tid; i < 2 * RPS * 2; i += NT) s_z[(i >> 1) * ZW + W + (i & 1)] = T(0);
   }
 
   // ---- longitude taps of the columns this thread owns (registers, loaded once): byte offsets into a
@@ -304,7 +306,7 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
     const long long b = task / n_bands;
     const int k0 = band * band_rows, k1 = min(k0 + band_rows, Ho);
     const long long next = task + gridDim.x;
-    const bool prefetch = next < tasks && (k1 - k0) > kUpRowsPerSync;  // needs two steps in this band
+    const bool prefetch = next < tasks && (k1 - k0) > RPS;  // needs two steps in this band
 
     if (!ready) {  // synchronous prologue (first band of the CTA, or after a one-step band)
       if (tid < 32) {
@@ -330,13 +332,13 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
 
     T* y_band = y + b * ybs + static_cast<long long>(k0) * Wo;
     const T* sx = s_x + cur * x_elems;
-    for (int kl = 0; kl < k1 - k0; kl += 2 * kUpRowsPerSync) {
-      up_rows<T, KR, KC, G, ZW, NT, 0, WIN>(y_band, kl, min(kUpRowsPerSync, k1 - k0 - kl), W, Wo, sx, s_z, s_off[cur],
+    for (int kl = 0; kl < k1 - k0; kl += 2 * RPS) {
+      up_rows<T, KR, KC, G, ZW, NT, 0, WIN, RPS>(y_band, kl, min(RPS, k1 - k0 - kl), W, Wo, sx, s_z, s_off[cur],
                                             s_rw[cur], s_state[cur], ci, cw, tid, nan);
       if (kl == 0 && prefetch && tid < 32) meta_store(next, cur ^ 1, nri, nrw, nn, ncov);
-      const int kl2 = kl + kUpRowsPerSync;
+      const int kl2 = kl + RPS;
       if (kl2 < k1 - k0)
-        up_rows<T, KR, KC, G, ZW, NT, 1, WIN>(y_band, kl2, min(kUpRowsPerSync, k1 - k0 - kl2), W, Wo, sx, s_z,
+        up_rows<T, KR, KC, G, ZW, NT, 1, WIN, RPS>(y_band, kl2, min(RPS, k1 - k0 - kl2), W, Wo, sx, s_z,
                                               s_off[cur], s_rw[cur], s_state[cur], ci, cw, tid, nan);
       // the barrier inside the second step ordered warp 0's table writes: everybody can start the row copies
       if (kl == 0 && prefetch) rows_issue(next, cur ^ 1);
@@ -366,8 +368,12 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     return RG_ERR_UNSUPPORTED;
   if (W > 1024) return RG_ERR_UNSUPPORTED;
   const int zw = W <= 512 ? 512 : 1024;
-  const size_t smem = (static_cast<size_t>(2 * kUpRowCap) * W + 2 * kUpRowsPerSync * zw) * sizeof(T);
+  size_t smem = (static_cast<size_t>(2 * kUpRowCap) * W + 2 * kUpRowsPerSync * zw) * sizeof(T);
   if (smem > static_cast<size_t>(dev.max_smem_optin)) return RG_ERR_UNSUPPORTED;
+  // eight rows per barrier (512-thread instances, rows of <= 512 columns, bands of a multiple of 8 rows)
+  const size_t smem8 = (static_cast<size_t>(2 * kUpRowCap) * W + 2 * 8 * zw) * sizeof(T);
+  const bool rps8 = nt == 512 && zw == 512 && band_rows % 8 == 0 && band_rows >= 16 && smem8 <= static_cast<size_t>(dev.max_smem_optin);
+  if (rps8) smem = smem8;
   const int groups = ((Wo + 3) / 4 + nt - 1) / nt;  // 1..4
   const int kr = rows.k_max <= 1 ? 1 : rows.k_max <= 2 ? 2 : 4;
   const int kc = cols.k_max <= 1 ? 1 : cols.k_max <= 2 ? 2 : 4;
@@ -377,7 +383,8 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   const bool win = kc == 4 && kr == 4 && cols.group_span > 0 && cols.group_span <= 6 && W + 2 <= zw;
   if (win) {
     if (nt == 512 && groups <= 2) {
-      if (groups == 1) kern = zw == 512 ? upsample_kernel<T, 4, 4, 1, 512, 512, 1> : upsample_kernel<T, 4, 4, 1, 1024, 512, 1>;
+      if (rps8) kern = groups == 1 ? upsample_kernel<T, 4, 4, 1, 512, 512, 1, 8> : upsample_kernel<T, 4, 4, 2, 512, 512, 1, 8>;
+      else if (groups == 1) kern = zw == 512 ? upsample_kernel<T, 4, 4, 1, 512, 512, 1> : upsample_kernel<T, 4, 4, 1, 1024, 512, 1>;
       else kern = zw == 512 ? upsample_kernel<T, 4, 4, 2, 512, 512, 1> : upsample_kernel<T, 4, 4, 2, 1024, 512, 1>;
     }
   }
@@ -385,6 +392,8 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   if (!kern && kr == KR_ && kc == KC_ && groups == G_) {                                                          \
     if (nt == 256)                                                                                       \
       kern = zw == 512 ? upsample_kernel<T, KR_, KC_, G_, 512, 256> : upsample_kernel<T, KR_, KC_, G_, 1024, 256>; \
+    else if (G_ <= 2 && rps8)                                                                            \
+      kern = upsample_kernel<T, KR_, KC_, (G_ <= 2 ? G_ : 1), 512, 512, 0, 8>;                           \
     else if (G_ <= 2)                                                                                    \
       kern = zw == 512 ? upsample_kernel<T, KR_, KC_, (G_ <= 2 ? G_ : 1), 512, 512>                      \
                        : upsample_kernel<T, KR_, KC_, (G_ <= 2 ? G_ : 1), 1024, 512>;                    \
