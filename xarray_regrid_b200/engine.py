@@ -325,6 +325,9 @@ def _as_batch(x: torch.Tensor, dtype: torch.dtype):
     return x3, lead
 
 
+TASKS_PER_SM = 32  # (slab, run, panel) tasks of the row-ring kernels per SM, see BandOp._ring
+MIN_RUN_ROWS = 16
+
 # What a NaN in the source does in ``BandOp.run``:
 NAN_PROPAGATE = 0  # poisons every output it touches (interpolation; rg_separable_*)
 NAN_SKIP = 1       # apply_weights(skipna=True): valid-mass normalisation + threshold
@@ -358,17 +361,27 @@ class BandOp:
         return rows, cols
 
     def _ring(self, batch: int, n_rows: int, n_cols: int, dtype: torch.dtype, pairs: bool = True):
-        """Row-ring schedule sized so that (slabs x runs) fills the SMs about twice over.  ``pairs``: allow the
+        """Row-ring schedule sized so that (slabs x runs x panels) gives every SM about TASKS_PER_SM tasks.  ``pairs``: allow the
         two-targets-per-lane layout of the register-resident kernel (conservative NaN modes only)."""
         if not self.use_ring:
             return None
         rows, cols = self._host_bands(n_rows, n_cols)
         sms = max(sm_count(), 1)
-        n_runs = int(min(rows.n_out, max(1, -(-2 * sms // max(batch, 1)))))
+        # (slab, run, panel) tasks are dealt round-robin to 1 - 4 persistent CTAs per SM: enough of them that the
+        # last, partial round does not matter (256 slabs x 2 runs on 148 CTAs = 3.46 rounds ran at 86 %), but runs of
+        # at least MIN_RUN_ROWS target rows (a run re-reads the k_max - 1 source rows it shares with its neighbour)
+        def runs_for(n_panels):
+            want = -(-TASKS_PER_SM * sms // max(batch * n_panels, 1))
+            return int(min(max(1, rows.n_out // MIN_RUN_ROWS), max(1, want)))
+
+        n_runs = runs_for(1)
         vec = 2 if dtype == torch.float64 else 4
         key = (n_runs, n_rows, n_cols, vec, self.use_lanes, pairs)
         if key not in self._rings:
             host = tables.row_ring_schedule(rows, n_runs, cols, vec, allow_pairs=pairs and self.use_lanes)
+            if host is not None and host.n_panels > 1 and runs_for(host.n_panels) != n_runs:
+                host = tables.row_ring_schedule(rows, runs_for(host.n_panels), cols, vec,
+                                                allow_pairs=pairs and self.use_lanes)
             if host is not None and not self.use_lanes:
                 host.lane_cols = 0
             self._rings[key] = None if host is None else DeviceRing(host, rows, dtype, self.device)
