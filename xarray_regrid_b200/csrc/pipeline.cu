@@ -14,6 +14,8 @@
 
 namespace rg {
 
+void stream_copy(void* dst, const void* src, size_t n);  // host_copy.cpp: non-temporal stores
+
 // Persistent worker threads for the staging memcpy of the pageable host paths.  (Spawning and joining threads
 // per call cost ~0.3 ms: more than the copy of an 8 MiB piece.)  The calling thread takes part in the copy; the
 // pool grows on demand and lives until the process exits.  One copy at a time (calls are serialised).
@@ -59,7 +61,7 @@ class CopyPool {
       if (i >= n_parts_) break;
       const size_t off = i * part_;
       const size_t n = bytes_ - off < part_ ? bytes_ - off : part_;
-      std::memcpy(dst_ + off, src_ + off, n);
+      stream_copy(dst_ + off, src_ + off, n);
     }
   }
   void grow(int helpers) {
@@ -200,7 +202,7 @@ int rg_host_copy(void* dst, const void* src, size_t bytes, int32_t n_threads) {
   if (want > 64) want = 64;
   if (want > (bytes + kMinPerThread - 1) / kMinPerThread) want = (bytes + kMinPerThread - 1) / kMinPerThread;
   if (want <= 1) {
-    std::memcpy(dst, src, bytes);
+    rg::stream_copy(dst, src, bytes);
     return RG_OK;
   }
   rg::copy_pool().run(static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), bytes,
