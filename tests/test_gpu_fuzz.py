@@ -121,3 +121,41 @@ def test_reduce_irregular_source(engine, seed):
                 np.testing.assert_array_equal(y.cpu().numpy(), want, err_msg=method)
             else:
                 _check(y, want, 1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_conservative_regular_ratio_2_to_3(engine, seed):
+    """Regular source and target grids at a random coarsening ratio in [2, 3] with random offsets, global (periodic
+    longitude, with or without wrap padding) or regional, even / odd sizes, fp64 / fp32: the block layout of the
+    register-resident kernel (one or two targets per lane, halo widths 1 - 2, panels on wide rows) -- or whatever the
+    host picks when a grid does not qualify -- against the oracle, all three NaN modes."""
+    rng = np.random.default_rng(1000 + seed)
+    dtype = np.float64 if seed % 2 == 0 else np.float32
+    res = float(rng.choice([0.25, 0.5, 1.0, 0.2]))
+    ratio = float(rng.choice([2.0, 2.5, 3.0, 2.25, 2.8]))
+    if seed % 3 == 0:  # global longitude
+        lon = np.round(np.arange(0.0, 360.0, res) + rng.choice([0.0, res / 2]), 10)
+        tlon = np.round(np.arange(0.0, 360.0, res * ratio) + rng.choice([0.0, res * ratio / 2, 0.1]), 10)
+    else:
+        n = int(rng.integers(60, 700))
+        lon0 = float(rng.uniform(-170, 20))
+        lon = np.round(lon0 + res * np.arange(n), 10)
+        tlon = np.round(np.arange(lon[0] + rng.choice([0.0, res / 2, 3 * res]), lon[-1] - res, res * ratio), 10)
+    nlat = int(rng.integers(30, 90))
+    lat = np.round(-20.0 + res * np.arange(nlat), 10)
+    tlat = np.round(np.arange(lat[0] + res, lat[-1] - res, res * ratio), 10)
+    if seed % 4 == 1:
+        lat = lat[::-1].copy()
+    B = int(rng.integers(1, 5))
+    x = (0.5 + rng.random((B, lat.size, lon.size))).astype(dtype)
+    x[rng.random(x.shape) < 0.08] = np.nan
+    plan = engine.ConservativePlan(engine.AxisSpec(lat, tlat, "lat"), engine.AxisSpec(lon, tlon, "lon"))
+    xt = torch.from_numpy(x).cuda()
+    rtol = 1e-12 if dtype == np.float64 else 2e-5
+    for skipna, thr in [(True, 0.4), (True, 1.0), (False, 1.0)]:
+        want, valid = oc.regrid_latlon(x, lat, lon, tlat, tlon, skipna=skipna, nan_threshold=thr, return_valid=True)
+        ties = np.abs(valid - oc.valid_threshold(thr)) <= (1e-13 if dtype == np.float64 else 1e-6)
+        y = plan(xt, skipna=skipna, nan_threshold=thr).cpu().numpy()
+        np.testing.assert_array_equal(np.isnan(y)[~ties], np.isnan(want)[~ties])
+        both = ~np.isnan(y) & ~np.isnan(want)
+        np.testing.assert_allclose(y[both], want[both], rtol=rtol, atol=rtol)
