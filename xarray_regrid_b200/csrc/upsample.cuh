@@ -48,15 +48,15 @@ __device__ __forceinline__ void st_stream4(double* p, const Vec4<double>& a) {
 
 // Rows [kb, kb + nk) of a band: latitude pass into the z buffers of parity BUF, one barrier, longitude
 // pass + stores.  BUF and the row slot are compile-time so that every z read is LDS [reg + immediate].
-// WIN: the four outputs of a group take their taps from one window of KC + 2 consecutive z columns (host contract,
-// rg_band_t.group_span): the window is loaded once per group (KC + 2 loads instead of 4 * KC) and every output is a
-// (KC + 2)-term dot product with its taps shifted into place (zeros elsewhere).  Used for the 4-tap cubic evaluation,
+// WIN (1 or 2): the four outputs of a group take their taps from one window of KC + WIN consecutive z columns (host contract,
+// rg_band_t.group_span): the window is loaded once per group (KC + WIN loads instead of 4 * KC) and every output is a
+// (KC + WIN)-term dot product with its taps shifted into place (zeros elsewhere).  Used for the 4-tap cubic evaluation,
 // where a NaN anywhere blanks the whole result anyway, so a zero weight times a NaN neighbour cannot matter.
 template <typename T, int KR, int KC, int G, int ZW, int NT, int BUF, int WIN, int RPS>
 __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, int nk, int W, int Wo,
                                         const T* s_x, T* s_z, const int (*s_off)[KR], const T (*s_rw)[KR],
                                         const int* s_state, const int (&ci)[G][4][KC],
-                                        const T (&cw)[G][4][KC + 2 * WIN], int tid, T nan) {
+                                        const T (&cw)[G][4][KC + WIN], int tid, T nan) {
   // ---- (A) latitude pass.  Only W values per row: 16-byte vectors, all rows of the step in flight at once
   // (the pass is latency bound, not throughput bound: few warps take part, the others go to the barrier)
   constexpr int V = 16 / sizeof(T);
@@ -112,15 +112,15 @@ __device__ __forceinline__ void up_rows(T* __restrict__ y_band, int kb_local, in
         if (l < Wo) {
           Vec4<T> out;
           if constexpr (WIN) {
-            T zw[KC + 2];
+            T zw[KC + WIN];
 #pragma unroll
-            for (int c = 0; c < KC + 2; ++c)
+            for (int c = 0; c < KC + WIN; ++c)
               zw[c] = *reinterpret_cast<const T*>(z + ci[g][0][0] + c * static_cast<int>(sizeof(T)));
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               T acc = T(0);
 #pragma unroll
-              for (int c = 0; c < KC + 2; ++c) acc = fma(cw[g][e][c], zw[c], acc);
+              for (int c = 0; c < KC + WIN; ++c) acc = fma(cw[g][e][c], zw[c], acc);
               out.v[e] = acc;
             }
           } else {
@@ -173,7 +173,7 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
   // ---- longitude taps of the columns this thread owns (registers, loaded once): byte offsets into a
   //      z row and weights; a column outside the source range gets a NaN weight (NaN * z = NaN)
   int ci[G][4][KC];
-  T cw[G][4][KC + 2 * WIN];
+  T cw[G][4][KC + WIN];
   if constexpr (WIN) {
     // window form: ci[g][0][0] = byte offset of the group's window, cw[g][e][c] = weight of window column c
 #pragma unroll
@@ -194,9 +194,9 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int l = (tid + g * NT) * 4 + e;
-        const int d = first[e] - base;  // host contract: 0 <= d, d + taps <= KC + 2 for covered outputs
+        const int d = first[e] - base;  // host contract: 0 <= d, d + taps <= KC + WIN for covered outputs
 #pragma unroll
-        for (int c = 0; c < KC + 2; ++c) {
+        for (int c = 0; c < KC + WIN; ++c) {
           const int t = c - d;
           cw[g][e][c] = (covered[e] && t >= 0 && t < n[e]) ? cols.w[t * Wo + l] : T(0);
         }
@@ -383,9 +383,12 @@ int upsample_try_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   const bool win = kc == 4 && kr == 4 && cols.group_span > 0 && cols.group_span <= 6 && W + 2 <= zw;
   if (win) {
     if (nt == 512 && groups <= 2) {
-      if (rps8) kern = groups == 1 ? upsample_kernel<T, 4, 4, 1, 512, 512, 1, 8> : upsample_kernel<T, 4, 4, 2, 512, 512, 1, 8>;
-      else if (groups == 1) kern = zw == 512 ? upsample_kernel<T, 4, 4, 1, 512, 512, 1> : upsample_kernel<T, 4, 4, 1, 1024, 512, 1>;
-      else kern = zw == 512 ? upsample_kernel<T, 4, 4, 2, 512, 512, 1> : upsample_kernel<T, 4, 4, 2, 1024, 512, 1>;
+      // (a 5-column window when the groups fit one -- x10 upsampling does: 20 instead of 24 weights and FMAs per group)
+      const bool w5 = cols.group_span <= 5;
+      if (rps8 && w5) kern = groups == 1 ? upsample_kernel<T, 4, 4, 1, 512, 512, 1, 8> : upsample_kernel<T, 4, 4, 2, 512, 512, 1, 8>;
+      else if (rps8) kern = groups == 1 ? upsample_kernel<T, 4, 4, 1, 512, 512, 2, 8> : upsample_kernel<T, 4, 4, 2, 512, 512, 2, 8>;
+      else if (groups == 1) kern = zw == 512 ? upsample_kernel<T, 4, 4, 1, 512, 512, 2> : upsample_kernel<T, 4, 4, 1, 1024, 512, 2>;
+      else kern = zw == 512 ? upsample_kernel<T, 4, 4, 2, 512, 512, 2> : upsample_kernel<T, 4, 4, 2, 1024, 512, 2>;
     }
   }
 #define RG_UP(KR_, KC_, G_)                                                                              \
