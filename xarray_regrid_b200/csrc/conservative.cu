@@ -272,11 +272,13 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     int lane_ctas = 1;
     if (lanes) {
       // block layout: M = 2 / 3 / 4 = halo columns (1, 1) / (2, 2) / (1, 2); narrow rows (<= 3 consumer warps per
-      // CTA) run four CTAs per SM -- the register cap of (160 threads, 4 CTAs) is 96
+      // CTA) run four (fp64) / five (fp32) CTAs per SM -- the register cap of (160 threads, 4 CTAs) is 96
       const bool narrow = ring_c->n_warps <= 3;
+      constexpr int kNarrowCtas = 4;  // register cap 96; fp32 (72 registers) then fits five: 3.65 TB/s on 1 -> 2.5 deg,
+                                      // an instance capped at 64 registers for six CTAs 3.44 TB/s
       const int m = !lanes2 ? 1 : ring_c->halo_l > 1 ? 3 : ring_c->halo_r > 1 ? 4 : 2;
 #define RG_BLOCKS(MV)                                                                                          \
-  (narrow ? (skipna ? conservative_lanes_kernel<T, true, 5, 5, MV, 4> : conservative_lanes_kernel<T, false, 5, 5, MV, 4>) \
+  (narrow ? (skipna ? conservative_lanes_kernel<T, true, 5, 5, MV, kNarrowCtas> : conservative_lanes_kernel<T, false, 5, 5, MV, kNarrowCtas>) \
           : (skipna ? conservative_lanes_kernel<T, true, 14, 5, MV> : conservative_lanes_kernel<T, false, 14, 5, MV>))
       lk = m == 3 ? RG_BLOCKS(3) : m == 4 ? RG_BLOCKS(4) : m == 2 ? RG_BLOCKS(2)
 #undef RG_BLOCKS
@@ -288,7 +290,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       const int regs = (fa.numRegs + 7) / 8 * 8;  // allocated per warp in units of 8 registers per thread
       lane_ctas = 65536 / ((ring_c->n_warps + 2) * 32 * regs);
     }
-    const int min_ctas = lanes ? (lane_ctas > 4 ? 4 : lane_ctas < 1 ? 1 : lane_ctas)
+    const int min_ctas = lanes ? (lane_ctas > 8 ? 8 : lane_ctas < 1 ? 1 : lane_ctas)
                          : panel_cta ? ((rows.k_max <= 4 && !(panel_tg2 && kw >= 5)) ? 3 : 2) : 1;
     const RingLayout probe =
         lanes ? ring_layout<T>(wp, 31, false, 0, 0, 0)
