@@ -15,6 +15,8 @@
 // ~0.4 per byte, far below the fp64 ridge, so tensor cores are not used.
 
 #include "common.cuh"
+#include <cstdlib>
+
 #include "conservative_ring.cuh"
 #include "pipeline.cuh"
 #include "upsample.cuh"
@@ -322,6 +324,10 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
       const RingLayout L =
           lanes ? ring_layout<T>(wp, 31, false, 0, 0, slots)
                 : ring_layout<T>(wp, ring_c->pad_shift, skipna != 0, ring_c->strip_cols_max, ring_c->n_warps, slots);
+      static const int lane_split = [] {  // (A/B switch of the split latitude pass: RG_LANE_SPLIT=0|1|2 points)
+        const char* e = std::getenv("RG_LANE_SPLIT");
+        return e ? std::atoi(e) : 2;
+      }();
       RingDev ring{ring_c->sched_row,
                    reinterpret_cast<const int4*>(ring_c->krec),
                    ring_c->wrec,
@@ -349,7 +355,8 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
                    ring_c->strip_b0,
                    ring_c->block_l0,
                    ring_c->halo_l,
-                   ring_c->halo_r};
+                   ring_c->halo_r,
+                   lane_split};
       if (!have_panels) return RG_ERR_NULL;  // (the host layer always provides the panel tables)
       using RingKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev,
                                   T, int, int);

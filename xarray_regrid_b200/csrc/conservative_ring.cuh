@@ -46,6 +46,7 @@ struct RingDev {
   const int32_t* __restrict__ strip_b0;
   const int32_t* __restrict__ block_l0;
   int halo_l, halo_r;
+  int lane_split;  // lanes kernel, one target per lane: split points of the latitude pass (0 - 2, see SPLIT)
 };
 
 constexpr int kRingMaxSlots = 32;  // ring depth cap (a tap reaches at most 15 rows back: 4-bit tap_back)
@@ -568,30 +569,43 @@ constexpr int kLaneNanPropagate = 0, kLaneNanSkip = 1, kLaneNanZero = 2;
 // the lane's byte offset into a ring row).  slots03 / slots47: ring slot of tap i in byte i (before wrap: the
 // table byte + the task's rotation, < 2 * ring_slots).  t* = sum w x (NaN-cleaned unless MODE propagates),
 // v* = valid mass (MODE skip only).
-template <typename T, int MODE, int CNT>
+template <typename T, int MODE, int CNT, int I0 = 0, bool INIT = true>
 __device__ __forceinline__ void lane_phase1(uint32_t baseA, uint32_t baseB, uint32_t row_stride,
                                             uint32_t ring_slots, uint32_t slots03, uint32_t slots47,
                                             uint32_t wk_addr, T (&t)[4], T (&v)[4], T (&one)[4]) {
-  constexpr int N = CNT > 0 ? CNT : 1;
+  // taps [I0, CNT) of the target row; INIT = false continues the sums of an earlier call (taps [0, I0))
+  constexpr int N = CNT > I0 ? CNT - I0 : 1;
   T w[N];
+  if constexpr (I0 % 2 == 0) {
 #pragma unroll
-  for (int i = 0; i < CNT; i += 2) {  // the target row's tap weights: broadcast reads of the staged table
-    const Pair2<T> p = lds_pair(wk_addr + static_cast<uint32_t>(i * sizeof(T)), T(0));
-    w[i] = p.a;
-    if (i + 1 < CNT) w[i + 1] = p.b;
+    for (int i = I0; i < CNT; i += 2) {  // the target row's tap weights: broadcast reads of the staged table
+      const Pair2<T> p = lds_pair(wk_addr + static_cast<uint32_t>(i * sizeof(T)), T(0));
+      w[i - I0] = p.a;
+      if (i + 1 < CNT) w[i + 1 - I0] = p.b;
+    }
+  } else {
+#pragma unroll
+    for (int i = I0; i < CNT; ++i) {
+      if constexpr (sizeof(T) == 8)
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(w[i - I0]) : "r"(wk_addr + static_cast<uint32_t>(i * sizeof(T))));
+      else
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[i - I0]) : "r"(wk_addr + static_cast<uint32_t>(i * sizeof(T))));
+    }
   }
   Pair2<T> xa[N], xb[N];
 #pragma unroll
-  for (int i = 0; i < CNT; ++i) {
+  for (int i = I0; i < CNT; ++i) {
     uint32_t slot = __byte_perm(i < 4 ? slots03 : slots47, 0u, 0x4440u + static_cast<uint32_t>(i & 3));
     slot = min(slot, slot - ring_slots);  // unsigned: wraps to slot when slot < ring_slots
-    xa[i] = lds_pair(baseA + slot * row_stride, T(0));
-    xb[i] = lds_pair(baseB + slot * row_stride, T(0));
+    xa[i - I0] = lds_pair(baseA + slot * row_stride, T(0));
+    xb[i - I0] = lds_pair(baseB + slot * row_stride, T(0));
+  }
+  if constexpr (INIT) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { t[e] = T(0); v[e] = T(0); }
   }
 #pragma unroll
-  for (int e = 0; e < 4; ++e) { t[e] = T(0); v[e] = T(0); }
-#pragma unroll
-  for (int i = 0; i < CNT; ++i) {
+  for (int i = 0; i < CNT - I0; ++i) {
     if constexpr (MODE == kLaneNanSkip) {
       accum_valid(t[0], v[0], w[i], xa[i].a, one[0]);
       accum_valid(t[1], v[1], w[i], xa[i].b, one[1]);
@@ -609,6 +623,34 @@ __device__ __forceinline__ void lane_phase1(uint32_t baseA, uint32_t baseB, uint
       t[3] = fma(w[i], xb[i].b, t[3]);
     }
   }
+}
+
+// Split latitude pass (lanes kernel, one target per lane, <= 5 row taps): taps [0, 2), [2, 4) and [4, 5) are contracted
+// as soon as THEIR rows have landed and released as soon as they are in registers.
+// kcnt of a staged row record with the split points packed in: bits 0-7 cnt; per split point s (after tap 2: bits
+// 8-15, after tap 4: bits 16-23) 4 bits "rows that may still be missing" (need - need_s) and 4 bits "rows that must
+// stay" (release - release_s).  Taps in any order.  A split point that gains nothing is recorded as need offset 0.
+__device__ __forceinline__ int lane_split_kcnt(const int4 raw, int points) {  // raw: the host's {need, release, kcnt, tap_back}
+  const int cnt = raw.z;
+  if (cnt <= 2 || cnt > 5) return cnt;
+  int packed = cnt;
+#pragma unroll
+  for (int sp = 0; sp < 2; ++sp) {
+    const int end = 2 + 2 * sp;  // taps [0, end) are done at this split point
+    if (end >= cnt || sp >= points) break;
+    int min_back_head = 15, max_back_tail = 0;
+#pragma unroll
+    for (int tp = 0; tp < 5; ++tp) {
+      const int back = static_cast<int>((static_cast<uint32_t>(raw.w) >> (4 * tp)) & 15u);
+      if (tp < end) min_back_head = min(min_back_head, back);
+      else if (tp < cnt) max_back_tail = max(max_back_tail, back);
+    }
+    const int rel_s = min(raw.y, raw.x - 1 - max_back_tail);  // first row the later taps (or later targets) still need
+    const int d_need = min_back_head, d_rel = raw.y - (rel_s > 0 ? rel_s : 0);
+    if (d_need <= 0 || d_need > 15 || d_rel < 0 || d_rel > 15) continue;  // nothing to gain / does not fit
+    packed |= (d_need | (d_rel << 4)) << (8 + 8 * sp);
+  }
+  return packed;
 }
 
 template <typename T, int MODE, int RMAX>
@@ -668,7 +710,19 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
     fence_mbar_init();
   }
   if (tid < 32) s_flags[tid] = 0;
-  for (int i = tid; i < n_rows_out; i += blockDim.x) s_krec[i] = ring_row_record(ring.krec[i], ring_slots);
+  // SPLIT (one target per lane, <= 5 row taps): the latitude pass of a target row runs in up to three parts -- taps
+  // [0, 2), [2, 4), [4, 5), each as soon as ITS rows have landed, released as soon as they are in registers -- so that
+  // ring slots are not held by rows waiting for the last row of their target row: more bytes in flight for the same
+  // ring (the kernel's rate follows the SM clock, i.e. it is bound by bytes in flight over latency)
+  constexpr bool SPLIT = M == 1 && RMAX <= 5;
+  for (int i = tid; i < n_rows_out; i += blockDim.x) {
+    const int4 raw = ring.krec[i];
+    int4 rec = ring_row_record(raw, ring_slots);
+    if constexpr (SPLIT) {
+      if (ring.lane_split) rec.y = lane_split_kcnt(raw, ring.lane_split);
+    }
+    s_krec[i] = rec;
+  }
   for (int i = tid; i < n_rows_out * kRingMaxTaps; i += blockDim.x) s_wrec[i] = static_cast<const T*>(ring.wrec)[i];
   int32_t* s_sched = reinterpret_cast<int32_t*>(s_wrec + static_cast<size_t>(n_rows_out) * kRingMaxTaps);
   for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
@@ -810,19 +864,61 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
     for (int k = k0; k < k1; ++k, yrow += Wo) {
       const int4 rec = s_krec[k];  // {need | release << 16, kcnt (-1: latitude not covered), slots 0-3, slots 4-7}
       const uint32_t need_g = gbase + (static_cast<uint32_t>(rec.x) & 0xffffu);
-      const int cnt = rec.y > 0 ? rec.y : 0;
-      while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(100);
-
+      const int cnt = rec.y > 0 ? (rec.y & 0xff) : 0;
       const uint32_t wk = wrec0 + static_cast<uint32_t>(k) * (kRingMaxTaps * sizeof(T));
       const uint32_t s03 = static_cast<uint32_t>(rec.z) + rot4, s47 = static_cast<uint32_t>(rec.w) + rot4;
       T t[4], v[4];
-      if constexpr (SKIPNA) {
-        lane_phase1_dispatch<T, kLaneNanSkip, RMAX>(cnt, baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);
+      const bool split = SPLIT && rec.y > 0xff;  // (warp-uniform)
+      if (split) {
+        // MODE is a compile-time constant per instance except for the zero-fill flag of the !SKIPNA kernels
+#define RG_PART(CNTV, I0V, INITV)                                                                                   \
+  do {                                                                                                                \
+    if constexpr (SKIPNA) {                                                                                           \
+      lane_phase1<T, kLaneNanSkip, CNTV, I0V, INITV>(baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);        \
+    } else {                                                                                                          \
+      if (zero_fill) lane_phase1<T, kLaneNanZero, CNTV, I0V, INITV>(baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one); \
+      else lane_phase1<T, kLaneNanPropagate, CNTV, I0V, INITV>(baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);      \
+    }                                                                                                                 \
+  } while (0)
+        const uint32_t rel_g = gbase + (static_cast<uint32_t>(rec.x) >> 16);
+        const uint32_t sp1 = (static_cast<uint32_t>(rec.y) >> 8) & 0xffu, sp2 = (static_cast<uint32_t>(rec.y) >> 16) & 0xffu;
+        if (sp1 & 15u) {  // taps [0, 2) ahead of the rest
+          while (static_cast<int>(ld_acquire_smem(flags0) - (need_g - (sp1 & 15u))) < 0) __nanosleep(100);
+          RG_PART(2, 0, true);
+          __syncwarp();
+          if (lane == 0) st_relaxed_smem(flags0 + 4u * (1 + warp), rel_g - (sp1 >> 4));
+          if (sp2 & 15u) {  // taps [2, 4) ahead of tap 4 (cnt == 5)
+            while (static_cast<int>(ld_acquire_smem(flags0) - (need_g - (sp2 & 15u))) < 0) __nanosleep(100);
+            RG_PART(4, 2, false);
+            __syncwarp();
+            if (lane == 0) st_relaxed_smem(flags0 + 4u * (1 + warp), rel_g - (sp2 >> 4));
+            while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(100);
+            RG_PART(5, 4, false);
+          } else {
+            while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(100);
+            if (cnt == 3) RG_PART(3, 2, false);
+            else if (cnt == 4) RG_PART(4, 2, false);
+            else RG_PART(5, 2, false);
+          }
+        } else {  // only the second split point: taps [0, 4), then tap 4
+          while (static_cast<int>(ld_acquire_smem(flags0) - (need_g - (sp2 & 15u))) < 0) __nanosleep(100);
+          RG_PART(4, 0, true);
+          __syncwarp();
+          if (lane == 0) st_relaxed_smem(flags0 + 4u * (1 + warp), rel_g - (sp2 >> 4));
+          while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(100);
+          RG_PART(5, 4, false);
+        }
+#undef RG_PART
       } else {
-        if (zero_fill)
-          lane_phase1_dispatch<T, kLaneNanZero, RMAX>(cnt, baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);
-        else
-          lane_phase1_dispatch<T, kLaneNanPropagate, RMAX>(cnt, baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);
+        while (static_cast<int>(ld_acquire_smem(flags0) - need_g) < 0) __nanosleep(100);
+        if constexpr (SKIPNA) {
+          lane_phase1_dispatch<T, kLaneNanSkip, RMAX>(cnt, baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);
+        } else {
+          if (zero_fill)
+            lane_phase1_dispatch<T, kLaneNanZero, RMAX>(cnt, baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);
+          else
+            lane_phase1_dispatch<T, kLaneNanPropagate, RMAX>(cnt, baseA, baseB, row_stride, slots, s03, s47, wk, t, v, one);
+        }
       }
       // every value this warp needs from the rows that die after this output is now in registers
       __syncwarp();
