@@ -1,5 +1,6 @@
-"""A/B of the block layout's launch shape (consumer warps per CTA, panels) on the ratio 2 - 2.5 grids, one process,
-one GPU: python tools/bench_blocks.py"""
+"""Conservative regridding on the ratio 2 - 4 grids, fp64 and fp32, one process, one GPU (`variants`: (TASKS_PER_SM,
+MIN_RUN_ROWS) settings of engine.BandOp._ring to A/B; the launch-shape A/Bs of profiles/r2_conservative_other_shapes.md
+were run by patching tables.lane_blocks_layout's keyword defaults the same way): python tools/bench_blocks.py"""
 import sys
 from functools import partial
 from pathlib import Path
