@@ -238,7 +238,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
   // lane_cols == 2: the register-resident kernel in its block layout (up to two targets per lane, <= 30 blocks
   // per warp, conservative NaN modes only).  That layout has no two-phase form: anything else goes to the generic
   // kernel.
-  const bool lanes2 = ring_c && ring_c->lane_cols == 2 && cols.k_max <= 6 && rows.k_max <= 5 &&
+  const bool lanes2 = ring_c && ring_c->lane_cols == 2 && cols.k_max <= 6 && rows.k_max <= 5 && rows.n_src + 2 < 65536 &&
                       (skipna || zero_fill) && ring_c->strip_targets_max <= 60 && ring_c->strip_b0 &&
                       ring_c->block_l0 && ring_c->halo_l >= 1 && ring_c->halo_l <= 2 && ring_c->halo_r >= 1 &&
                       ring_c->halo_r <= 2 && ring_c->n_panels >= 1 && ring_c->panel_strip0 && ring_c->panel_c0 &&
@@ -284,7 +284,7 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
           : (skipna ? conservative_lanes_kernel<T, true, 14, 5, MV> : conservative_lanes_kernel<T, false, 14, 5, MV>))
       lk = m == 3 ? RG_BLOCKS(3) : m == 4 ? RG_BLOCKS(4) : m == 2 ? RG_BLOCKS(2)
 #undef RG_BLOCKS
-           : rows.k_max <= 5
+           : (rows.k_max <= 5 && rows.n_src + 2 < 65536)
                ? (skipna ? conservative_lanes_kernel<T, true, 14, 5> : conservative_lanes_kernel<T, false, 14, 5>)
                : (skipna ? conservative_lanes_kernel<T, true, 14, 8> : conservative_lanes_kernel<T, false, 14, 8>);
       cudaFuncAttributes fa;
@@ -301,8 +301,13 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
     // load order (4 bytes per scheduled row) in shared memory
     // (the two-phase kernel keeps only the weights its instance can use: 4 per row for bands of <= 4 row taps)
     const int w_per_row = (panel_cta && rows.k_max <= 4) ? 4 : kRingMaxTaps;  // = RMAX of the instance picked below
-    const size_t row_tables = static_cast<size_t>(rows.n_out) * (16 + (lanes ? kRingMaxTaps : w_per_row) * sizeof(T)) +
-                              static_cast<size_t>(ring_c->n_sched) * sizeof(int32_t);
+    // (lanes instances of <= 5 row taps: 6 weights per row, 16-bit load order -- must match the kernel's carve-up)
+    const bool lanes_small = lanes && (lanes2 || rows.k_max <= 5) && rows.n_src + 2 < 65536;
+    const size_t row_tables =
+        lanes_small ? (static_cast<size_t>(rows.n_out) * (16 + kLaneWrecSmall * sizeof(T)) +
+                       (static_cast<size_t>(ring_c->n_sched) * sizeof(uint16_t) + 15) / 16 * 16)
+                    : (static_cast<size_t>(rows.n_out) * (16 + (lanes ? kRingMaxTaps : w_per_row) * sizeof(T)) +
+                       static_cast<size_t>(ring_c->n_sched) * sizeof(int32_t));
     // Several CTAs per SM = several independent row pipelines.  fp32 rows carry half the bytes of fp64 ones and
     // low coarsening ratios bring only two new source rows per target row: either way a target row leaves too
     // little time for ONE CTA's per-row dependency chain, so the shared memory is split between 2 - 3 CTAs when

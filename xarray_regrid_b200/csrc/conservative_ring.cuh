@@ -53,6 +53,9 @@ constexpr int kRingMaxSlots = 32;  // ring depth cap (a tap reaches at most 15 r
 constexpr int kRingMaxLive = 15;
 constexpr int kRingMaxTaps = 8;   // row taps per output handled by the ring kernel
 constexpr int kRingMaxWarps = 24; // consumer warps
+constexpr int kLaneWrecSmall = 6; // staged weights per target row in the lanes instances of <= 5 row taps
+template <int RMAX> struct LaneSched { using type = int32_t; };
+template <> struct LaneSched<5> { using type = uint16_t; };  // (host contract: source rows + 2 pole rows < 65536)
 
 // Shared-memory carve-up, computed identically on host and device.
 struct RingLayout {
@@ -280,9 +283,9 @@ __device__ __forceinline__ int4 ring_row_record(const int4 r, int ring_slots) {
 
 // ---------------------------------------------------------------- producer / sync roles
 // producer: one thread streams the scheduled source rows of every task into the ring with TMA bulk copies
-template <typename T>
+template <typename T, typename S = int32_t>
 __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long xbs, long long xrs,
-                                              const RingDev& ring, const int32_t* sched_row, long long tasks,
+                                              const RingDev& ring, const S* sched_row, long long tasks,
                                               int ring_slots,
                                               uint32_t row_bytes, int row_stride, uint32_t full0, uint32_t flags0,
                                               uint32_t ring0, int n_warps) {
@@ -700,6 +703,10 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
   unsigned long long* s_full = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
   uint32_t* s_flags = reinterpret_cast<uint32_t*>(smem + L.off_flags);
   // per target row tables, staged once: 16-byte record + 8 tap weights (host contract: they fit)
+  // (instances of <= 5 row taps keep 6 weights per row and the load order as 16-bit rows: on the headline shape that
+  // is what makes room for a 19th ring row)
+  constexpr int WREC = RMAX <= 5 ? kLaneWrecSmall : kRingMaxTaps;
+  using Sched = typename LaneSched<RMAX>::type;
   int4* s_krec = reinterpret_cast<int4*>(smem + L.total);
   T* s_wrec = reinterpret_cast<T*>(smem + L.total + static_cast<size_t>(n_rows_out) * 16);
 
@@ -723,9 +730,10 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
     }
     s_krec[i] = rec;
   }
-  for (int i = tid; i < n_rows_out * kRingMaxTaps; i += blockDim.x) s_wrec[i] = static_cast<const T*>(ring.wrec)[i];
-  int32_t* s_sched = reinterpret_cast<int32_t*>(s_wrec + static_cast<size_t>(n_rows_out) * kRingMaxTaps);
-  for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = ring.sched_row[i];
+  for (int i = tid; i < n_rows_out * WREC; i += blockDim.x)
+    s_wrec[i] = static_cast<const T*>(ring.wrec)[(i / WREC) * kRingMaxTaps + i % WREC];
+  Sched* s_sched = reinterpret_cast<Sched*>(s_wrec + static_cast<size_t>(n_rows_out) * WREC);
+  for (int i = tid; i < ring.n_sched; i += blockDim.x) s_sched[i] = static_cast<Sched>(ring.sched_row[i]);
   __syncthreads();
 
   const long long tasks = batch * ring.n_runs * ring.n_panels;  // (M = 1: one panel)
@@ -734,8 +742,8 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
 
   if (warp == n_warps) {
     if (lane == 0)
-      ring_producer<T>(x, xbs, xrs, ring, s_sched, tasks, ring_slots, row_bytes, L.row_stride, full0, flags0, ring0,
-                       n_warps);
+      ring_producer<T, Sched>(x, xbs, xrs, ring, s_sched, tasks, ring_slots, row_bytes, L.row_stride, full0, flags0,
+                              ring0, n_warps);
     return;
   }
   if (warp > n_warps) {
@@ -865,7 +873,7 @@ conservative_lanes_kernel(const T* __restrict__ x, T* __restrict__ y, long long 
       const int4 rec = s_krec[k];  // {need | release << 16, kcnt (-1: latitude not covered), slots 0-3, slots 4-7}
       const uint32_t need_g = gbase + (static_cast<uint32_t>(rec.x) & 0xffffu);
       const int cnt = rec.y > 0 ? (rec.y & 0xff) : 0;
-      const uint32_t wk = wrec0 + static_cast<uint32_t>(k) * (kRingMaxTaps * sizeof(T));
+      const uint32_t wk = wrec0 + static_cast<uint32_t>(k) * (WREC * sizeof(T));
       const uint32_t s03 = static_cast<uint32_t>(rec.z) + rot4, s47 = static_cast<uint32_t>(rec.w) + rot4;
       T t[4], v[4];
       const bool split = SPLIT && rec.y > 0xff;  // (warp-uniform)
