@@ -10,7 +10,10 @@ import ctypes as C
 from pathlib import Path
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = _CSRC / "libregrid_b200.so"
+import os as _os
+
+# (RG_LIB_PATH: another build of the same library, for A/B measurements of kernel variants)
+LIB_PATH = Path(_os.environ.get("RG_LIB_PATH") or (_CSRC / "libregrid_b200.so"))
 
 RG_ABI_VERSION = 4
 
