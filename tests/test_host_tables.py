@@ -398,3 +398,58 @@ def test_kron_band_is_the_kronecker_product_of_the_dense_weights():
     with pytest.raises(NotImplementedError):  # pole rows keep a weight without the spherical correction
         tables.kron_band(bo, tables.conservative_band(tables.format_lat_axis(np.arange(-89.5, 90, 1.0)),
                                                       np.arange(-90.0, 91, 5.0)))
+
+
+def test_lane_blocks_layout_invariants_random_grids():
+    """rg_row_ring_t block layout (lane_cols == 2): whatever regular grid pair the host accepts, every target belongs to
+    exactly one block, a block has at most two targets, every tap lies within halo_l / halo_r columns of its block, a
+    strip has at most 30 blocks, panels hold whole strips and their ring rows contain the blocks plus one halo block either
+    side, and bulk-copy alignment holds (even first columns; multiples of 4 for fp32 panels)."""
+    from xarray_regrid_b200 import engine
+
+    rng = np.random.default_rng(2024)
+    accepted = 0
+    for trial in range(120):
+        res = float(rng.choice([0.1, 0.125, 0.2, 0.25, 0.5, 1.0]))
+        ratio = float(rng.choice([2.0, 2.25, 2.5, 2.8, 3.0, 1.6, 3.5]))
+        vec = int(rng.choice([2, 4]))
+        if rng.random() < 0.5:
+            lon = np.round(np.arange(0.0, 360.0, res) + rng.choice([0.0, res / 2]), 10)
+            tlon = np.round(np.arange(0.0, 360.0, res * ratio) + rng.choice([0.0, res * ratio / 2]), 10)
+        else:
+            n = int(rng.integers(40, 900))
+            lon = np.round(-100.0 + res * np.arange(n), 10)
+            tlon = np.round(np.arange(lon[0] + rng.choice([0.0, res / 2, 2 * res]), lon[-1] - res, res * ratio), 10)
+        if tlon.size < 2:
+            continue
+        cols = tables.conservative_band(engine._axis(engine.AxisSpec(lon, tlon, "lon"), False), tlon)
+        lay = tables.lane_blocks_layout(cols, vec)
+        if lay is None:
+            continue
+        accepted += 1
+        W, n_out = cols.n_src, cols.n_out
+        bl0, sb0, sl0, sc0 = lay["block_l0"], lay["strip_b0"], lay["strip_l0"], lay["strip_c0"]
+        hl, hr = lay["halo_l"], lay["halo_r"]
+        assert bl0[0] == 0 and bl0[-1] == n_out and (np.diff(bl0) >= 0).all() and (np.diff(bl0) <= 2).all()
+        assert sb0[0] == 0 and sb0[-1] == bl0.size - 1 and (np.diff(sb0) >= 1).all() and (np.diff(sb0) <= 30).all()
+        assert (sl0 == bl0[sb0]).all() and 1 <= hl <= 2 and 1 <= hr <= 2 and lay["n_warps"] <= 12
+        ps0, pc0, pnc = lay["panel_strip0"], lay["panel_c0"], lay["panel_nc"]
+        assert ps0[0] == 0 and ps0[-1] == sc0.size and (np.diff(ps0) <= lay["n_warps"]).all() and (np.diff(ps0) >= 1).all()
+        n_panels = pc0.size
+        assert (sc0 % 2 == 0).all()
+        if n_panels > 1:
+            assert W % 4 == 0 and (pnc <= W).all() and (pnc % 4 == 0).all() and (pc0 % (4 if vec == 4 else 2) == 0).all()
+        else:
+            assert pc0[0] == 0 and pnc[0] == W
+        for p in range(n_panels):
+            for s in range(ps0[p], ps0[p + 1]):
+                for j in range(sb0[s + 1] - sb0[s]):
+                    c0 = int(sc0[s]) + 4 * j
+                    if n_panels > 1:
+                        rel = (c0 - int(pc0[p])) % W
+                        assert 4 <= rel and rel + 8 <= pnc[p]
+                    b = sb0[s] + j
+                    for l in range(bl0[b], bl0[b + 1]):
+                        q = (cols.idx[: cols.cnt[l], l].astype(np.int64) - (c0 - hl)) % W
+                        assert (q < 4 + hl + hr).all(), (trial, s, l, q)
+    assert accepted >= 40
