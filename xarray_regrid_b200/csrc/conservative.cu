@@ -333,6 +333,8 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
         const char* e = std::getenv("RG_LANE_SPLIT");
         return e ? std::atoi(e) : 2;
       }();
+      // (A/B switch: RG_L2_HINT=0 drops the evict-first hint of the producer's bulk copies)
+      static const int l2_hint = std::getenv("RG_L2_HINT") ? std::atoi(std::getenv("RG_L2_HINT")) : 1;
       RingDev ring{ring_c->sched_row,
                    reinterpret_cast<const int4*>(ring_c->krec),
                    ring_c->wrec,
@@ -361,7 +363,8 @@ int conservative_launch(const T* x, T* y, int64_t batch, int64_t xbs, int64_t xr
                    ring_c->block_l0,
                    ring_c->halo_l,
                    ring_c->halo_r,
-                   lane_split};
+                   lane_split,
+                   l2_hint};
       if (!have_panels) return RG_ERR_NULL;  // (the host layer always provides the panel tables)
       using RingKernel = void (*)(const T*, T*, long long, long long, long long, long long, Band<T>, RingDev,
                                   T, int, int);

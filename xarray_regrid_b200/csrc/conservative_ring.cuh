@@ -47,6 +47,7 @@ struct RingDev {
   const int32_t* __restrict__ block_l0;
   int halo_l, halo_r;
   int lane_split;  // lanes kernel, one target per lane: split points of the latitude pass (0 - 2, see SPLIT)
+  int l2_hint;     // producer: bulk copies carry an L2 evict-first hint
 };
 
 constexpr int kRingMaxSlots = 32;  // ring depth cap (a tap reaches at most 15 rows back: 4-bit tap_back)
@@ -111,6 +112,20 @@ __device__ __forceinline__ void tma_load_row(uint32_t dst_addr, const void* src,
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_addr),
       "l"(src), "r"(bytes), "r"(bar_addr)
+      : "memory");
+}
+// the same with an L2 eviction-priority hint for the source lines (streamed once, never reused)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_row_hint(uint32_t dst_addr, const void* src, uint32_t bytes,
+                                                  uint32_t bar_addr, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst_addr),
+      "l"(src), "r"(bytes), "r"(bar_addr), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_smem(uint32_t addr) {
@@ -291,6 +306,7 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
                                               uint32_t ring0, int n_warps) {
   uint32_t g = 0, freed = 0;  // rows issued / rows released by every consumer warp
   int slot = 0;
+  const uint64_t policy = l2_policy_evict_first();
   const int W = static_cast<int>(row_bytes / sizeof(T));  // source columns of a full row
   for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
     const int panel = static_cast<int>(task % ring.n_panels);
@@ -332,8 +348,13 @@ __device__ __forceinline__ void ring_producer(const T* __restrict__ x, long long
       }
       const uint32_t dst = ring0 + static_cast<uint32_t>(slot) * row_stride;
       mbar_arrive_expect_tx(full0 + 8u * slot, bytes1 + bytes2);
-      tma_load_row(dst, src + pc0, bytes1, full0 + 8u * slot);
-      if (bytes2) tma_load_row(dst + bytes1, src, bytes2, full0 + 8u * slot);
+      if (ring.l2_hint) {
+        tma_load_row_hint(dst, src + pc0, bytes1, full0 + 8u * slot, policy);
+        if (bytes2) tma_load_row_hint(dst + bytes1, src, bytes2, full0 + 8u * slot, policy);
+      } else {
+        tma_load_row(dst, src + pc0, bytes1, full0 + 8u * slot);
+        if (bytes2) tma_load_row(dst + bytes1, src, bytes2, full0 + 8u * slot);
+      }
       ++g;
       if (++slot == ring_slots) slot = 0;
     }
