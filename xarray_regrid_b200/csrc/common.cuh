@@ -59,35 +59,42 @@ template <> __device__ __forceinline__ float quiet_nan<float>() { return CUDART_
 // consumed once per CTA; reuse between neighbouring CTAs is served by the 126 MB L2).
 template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
 
+// L2 eviction policy of data that is read once (the compiler hoists the createpolicy out of loops)
+__device__ __forceinline__ unsigned long long l2_evict_first() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
 template <typename T, int VEC>
 __device__ __forceinline__ Pack<T, VEC> ld_stream(const T* p);
 
 template <> __device__ __forceinline__ Pack<double, 1> ld_stream<double, 1>(const double* p) {
   Pack<double, 1> r;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r.v[0]) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r.v[0]) : "l"(p), "l"(l2_evict_first()));
   return r;
 }
 template <> __device__ __forceinline__ Pack<double, 2> ld_stream<double, 2>(const double* p) {
   Pack<double, 2> r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
-               : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+               : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p), "l"(l2_evict_first()));
   return r;
 }
 template <> __device__ __forceinline__ Pack<float, 1> ld_stream<float, 1>(const float* p) {
   Pack<float, 1> r;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r.v[0]) : "l"(p), "l"(l2_evict_first()));
   return r;
 }
 template <> __device__ __forceinline__ Pack<float, 2> ld_stream<float, 2>(const float* p) {
   Pack<float, 2> r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];"
-               : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
+               : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p), "l"(l2_evict_first()));
   return r;
 }
 template <> __device__ __forceinline__ Pack<float, 4> ld_stream<float, 4>(const float* p) {
   Pack<float, 4> r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p), "l"(l2_evict_first()));
   return r;
 }
 

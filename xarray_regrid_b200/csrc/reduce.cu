@@ -182,7 +182,10 @@ __device__ __forceinline__ int stage_row(T* dst, const T* __restrict__ src, cons
 // waits (cp_async_wait) before reading.  Gathered segments fall back to the synchronous copy.
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+  // (source cells are read exactly once: evict-first in L2)
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
@@ -646,9 +649,11 @@ __device__ __forceinline__ bool red_mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok != 0;
 }
 __device__ __forceinline__ void red_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  uint64_t pol;  // (source cells are read exactly once: evict-first in L2)
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar)
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
       : "memory");
 }
 
