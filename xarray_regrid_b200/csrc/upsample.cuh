@@ -284,6 +284,9 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
     if (tid == 0) s_win0[buf] = rmin;
   };
   // the window's source rows -> s_x[buf], asynchronously (one element per request: any alignment)
+  // (the source is small and re-read by every band while gigabytes of output stream through L2: evict-last)
+  unsigned long long keep;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
   auto rows_issue = [&](long long task, int buf) {
     const T* xb = x + (task / n_bands) * xbs;
     const int w0 = s_win0[buf];
@@ -293,7 +296,9 @@ upsample_kernel(const T* __restrict__ x, T* __restrict__ y, long long batch, lon
       const T* src = xb + static_cast<long long>(w0 + r) * xrs;
       for (int j = tid; j < W; j += NT) {
         const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * W + j));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src + j), "n"(sizeof(T)) : "memory");
+        asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], %2, %3;" ::"r"(d), "l"(src + j),
+                     "n"(sizeof(T)), "l"(keep)
+                     : "memory");
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
