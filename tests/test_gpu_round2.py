@@ -492,3 +492,46 @@ def test_interp_over_three_coordinates(method):
     assert out.shape == want.shape
     np.testing.assert_array_equal(np.isnan(out.data), np.isnan(want))
     np.testing.assert_allclose(out.data, want, rtol=0 if method == "nearest" else 1e-10, atol=1e-12)
+
+
+def test_group_by_over_three_coordinates():
+    """flox bins any number of coordinates (methods/flox_reduce.py:89-96, 174-183).  The engine walks the bins of the
+    coordinate that is neither latitude nor longitude on the host and merges its slices into the kernels' rows axis,
+    so a (level, lat, lon) bin is reduced as one 2-D bin: against the oracle's N-D group-by, dims in two orders,
+    ascending and descending third coordinate, numpy and CUDA input."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xarray_regrid_b200.labelled import DataArray, Dataset
+
+    rng = np.random.default_rng(31)
+    lev, tlev = np.arange(0.0, 12.0, 1.0), np.arange(1.0, 12.0, 3.0)            # bins of 3 levels
+    lat, tlat = np.arange(-10.0, 10.25, 0.25), np.arange(-9.5, 10.0, 1.0)
+    lon, tlon = np.arange(0.0, 360.0, 1.0), np.arange(0.0, 360.0, 4.0)
+    x = rng.standard_normal((2, lev.size, lat.size, lon.size))
+    x[rng.random(x.shape) < 0.03] = np.nan
+    da = DataArray(x, ("time", "level", "latitude", "longitude"),
+                   {"time": np.arange(2), "level": lev, "latitude": lat, "longitude": lon})
+    tgt = Dataset({}, {"level": tlev, "latitude": tlat, "longitude": tlon})
+    xf, latf, lonf = of.format_for_regrid(x, lat, lon, tlat, tlon, stats=True)
+    for method, skipna in [("mean", True), ("var", True), ("max", False), ("median", True), ("sum", True)]:
+        out = da.regrid.stat(tgt, method, skipna=skipna)
+        want = orr.stat(xf, [lev, latf, lonf], [tlev, tlat, tlon], [-3, -2, -1], method, skipna=skipna)
+        assert out.dims == da.dims and out.shape == want.shape
+        np.testing.assert_array_equal(np.isnan(out.data), np.isnan(want))
+        np.testing.assert_allclose(out.data, want, rtol=1e-12, atol=1e-13)
+    # labels; descending third coordinate; dims in another order; CUDA input
+    labels = rng.integers(0, 6, (lat.size, lev.size, 2, lon.size)).astype(np.int32)
+    lev_d = lev[::-1].copy()
+    dal = DataArray(torch.from_numpy(labels).cuda(), ("latitude", "level", "time", "longitude"),
+                    {"time": np.arange(2), "level": lev_d, "latitude": lat, "longitude": lon})
+    lf, latf2, lonf2 = of.format_for_regrid(labels.transpose(2, 1, 0, 3), lat, lon, tlat, tlon, stats=True)
+    for op in ("most_common", "least_common"):
+        out = getattr(dal.regrid, op)(tgt, values=np.arange(6))
+        want = orr.mode(lf, [lev_d, latf2, lonf2], [tlev, tlat, tlon], [-3, -2, -1], values=np.arange(6),
+                        anti_mode=(op == "least_common"))
+        got = out.data.cpu().numpy().transpose(2, 1, 0, 3)
+        assert out.dims == dal.dims and got.shape == want.shape
+        np.testing.assert_array_equal(got, want)
+    # a third coordinate that leaves a target bin empty is refused, not guessed
+    with pytest.raises(NotImplementedError):
+        da.regrid.stat(Dataset({}, {"level": np.arange(-20.0, 12.0, 3.0), "latitude": tlat, "longitude": tlon}), "mean")

@@ -189,6 +189,63 @@ def _apply(da: DataArray, target: Dataset, names, run, coord_attrs_from: str, pr
     return DataArray(_from_device(y.contiguous(), how), da.dims, coords, dict(da.attrs), cattrs, da.name)
 
 
+def _reduce_three(da: DataArray, target: Dataset, names, call2d) -> DataArray:
+    """most_common / least_common / stat over THREE coordinates at once (flox bins any number of them,
+    methods/flox_reduce.py:89-96, 174-183): the bins of the coordinate that is neither latitude nor longitude
+    are walked on the host; for each of them the selected slices are merged into the kernels' rows axis (row i,
+    slice j -> merged row i * n + j, labelled ``row_i + j * eps`` with ``eps`` far below the distance of any row
+    label to the next bin edge, so that bin membership, trimming and coverage of the rows axis are unchanged) and the
+    ordinary two-coordinate kernels reduce a 3-D bin as ONE 2-D bin.  Needs every bin of the third coordinate
+    covered and non-empty."""
+    extra = next((n for n in sorted(names, key=da.dims.index) if _kind(n) == "other"), None)
+    if extra is None or len(names) != 3:
+        raise NotImplementedError("the group-by methods regrid at most three dimensions, one of them neither "
+                                  "latitude nor longitude")
+    rows, cols = _layout(da, [n for n in names if n != extra])
+    if rows is None or cols is None:
+        raise NotImplementedError("three regridded coordinates need a rows and a columns coordinate")
+    src_a, tgt_a = np.asarray(da.coords[extra]), np.asarray(target.coords[extra])
+    axis_a = tables.plain_axis(src_a)
+    bins = tables.bins_axis(axis_a, tgt_a)
+    if not bins.cover.all() or (bins.count == 0).any():
+        raise NotImplementedError(f"every target bin along {extra!r} must be covered by the source and non-empty")
+    lab = np.asarray(da.coords[rows], dtype=np.float64)
+    breaks = tables.bin_breaks(np.sort(np.asarray(target.coords[rows], dtype=np.float64)))
+    gaps = breaks[None, :] - lab[:, None]
+    gaps = gaps[gaps > 0]
+    n_max = int(bins.count.max())
+    eps = 0.25 * float(gaps.min()) / n_max if gaps.size else 1.0
+    if n_max > 1 and not np.all(lab + eps != lab):
+        raise NotImplementedError(f"{rows!r} labels lie too close to a bin edge to merge {extra!r} into them")
+    x, how = _to_device(da.data)
+    ia, ir = da.dims.index(extra), da.dims.index(rows)
+    keep = [i for i in range(x.dim()) if i != ia]
+    pos_r = keep.index(ir)
+    perm = keep[:pos_r + 1] + [ia] + keep[pos_r + 1:]
+    sub_dims = tuple(d for d in da.dims if d != extra)
+    sub_target = Dataset({}, {n: np.asarray(target.coords[n]) for n in (rows, cols)}, dict(target.attrs),
+                         {n: dict(target.coord_attrs.get(n, {})) for n in (rows, cols)})
+    base_coords = {k: v for k, v in da.coords.items() if k != extra}
+    base_cattrs = {k: v for k, v in da.coord_attrs.items() if k != extra}
+    outs = [None] * bins.n_out
+    for g in range(bins.n_out):
+        cnt, p0 = int(bins.count[g]), int(bins.start[g])
+        idx = torch.as_tensor(np.ascontiguousarray(axis_a.source[p0:p0 + cnt]).astype(np.int64), device=x.device)
+        xm = x.index_select(ia, idx).permute(perm)
+        shape = list(xm.shape)
+        xm = xm.reshape(shape[:pos_r] + [shape[pos_r] * cnt] + shape[pos_r + 2:])
+        coords = dict(base_coords)
+        coords[rows] = (lab[:, None] + eps * np.arange(cnt)[None, :]).reshape(-1)
+        sub = DataArray(xm, sub_dims, coords, dict(da.attrs), dict(base_cattrs), da.name)
+        outs[int(bins.out_index[g])] = call2d(sub, sub_target)
+    y = torch.stack([_to_device(o.data)[0] for o in outs], dim=ia)
+    coords = dict(outs[0].coords)
+    coords[extra] = tgt_a
+    cattrs = dict(outs[0].coord_attrs)
+    cattrs[extra] = dict(target.coord_attrs.get(extra, {}))
+    return DataArray(_from_device(y.contiguous(), how), da.dims, coords, dict(da.attrs), cattrs, da.name)
+
+
 def _conservative_nd(da: DataArray, target: Dataset, names, latitude_coord, skipna, nan_threshold) -> DataArray:
     """Conservative regridding over MORE than two coordinates at once, with the reference's joint valid mass
     (``xr.dot`` contracts all regridded dims together, methods/conservative.py:188-198): every coordinate but the
@@ -355,6 +412,9 @@ class Regridder:
                 return plan.mode_host(x, values, fill_value=fill_value, anti_mode=anti_mode)
             return plan.mode(x, values, fill_value=fill_value, anti_mode=anti_mode)
 
+        if len([n for n in names if n in self._obj.dims]) == 3:
+            return _reduce_three(self._obj, target, [n for n in names if n in self._obj.dims],
+                                 lambda sub, tgt: Regridder(sub)._mode(tgt, values, time_dim, fill_value, anti_mode, what))
         return _apply(self._obj, target, names, run, "target")
 
     def most_common(self, ds_target_grid, values, time_dim="time", fill_value=None):
@@ -384,6 +444,9 @@ class Regridder:
                     return plan.stat_host(x, method, skipna=skipna, fill_value=fill_value)
                 return plan.stat(x, method, skipna=skipna, fill_value=fill_value)
 
+            if len([n for n in names if n in da.dims]) == 3:
+                return _reduce_three(da, target, [n for n in names if n in da.dims],
+                                     lambda sub, tgt: Regridder(sub).stat(tgt, method, time_dim, skipna, fill_value))
             return _apply(da, target, names, run, "target")
 
         return _map(self._obj, one)
